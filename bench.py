@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native face-recognition hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--rows R] [--queries Q]
+
+Workload (config.workload): the gallery-sharded cosine-similarity search of BASELINE.json configs[4] — a batch of
+256 query embeddings against a synthetic 10M x 512 gallery, row-sharded over the N GPUs (strong scaling: the gallery is
+fixed, each rank scans 10M/N rows), per-shard top-1 all-gathered over NCCL and merged. One "step" = one query batch.
+
+    value  queries/s, inputs resident in HBM (device-timed with CUDA events, max over ranks)
+    e2e    queries/s through the public C-ABI call path with HOST buffers: pinned-host queries -> H2D -> search ->
+           (all-gather + merge) -> D2H of (score, idx), every step
+    roofline  fused scan kernel (cosine_topk_coarse): algorithmic bytes = shard rows x 512 x 2 B (fp16 scan copy) per launch
+              over the CUDA-event duration of that kernel, against MEASURED_PEAKS.json hbm_gbs
+    cpu_baseline  oracle port (numpy sgemm + first-max argmax, all host threads) on a bounded sample, rank 0 at N=1
+
+--impl reference times the reference path's CPU port only (the reference has no CPU implementation; its
+GPU path, src/matmul.cpp compiled verbatim into oracle/_ref, is timed beside it as `ref_gpu` when it loads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "face-recognition-cpp-tensorrt_b200"))
+
+METRIC = "queries/sec vs 10M x 512 gallery"
+UNIT = "queries/s"
+GALLERY_SEED, QUERY_SEED, PLANT_SEED = 19, 23, 29
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, threading.Event(), [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self.stop_flag.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report that, do not invent numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_search_sample(nq: int, sample_rows: int, total_rows: int, reps: int, warm: int):
+    """oracle port on the host cores: sims = Q @ G^T (fp32 sgemm) then first-max argmax; returns (queries/s scaled to
+    total_rows, seconds per sample pass, threads)"""
+    from oracle import search_oracle as so
+
+    try:
+        import torch
+
+        threads = torch.get_num_threads()
+    except Exception:
+        threads = os.cpu_count() or 1
+    rng = np.random.default_rng(GALLERY_SEED)
+    G = rng.standard_normal((sample_rows, 512), dtype=np.float32)
+    G /= np.linalg.norm(G, axis=1, keepdims=True)
+    q = so.planted_queries(G[rng.integers(0, sample_rows, nq)], 0.75, PLANT_SEED)
+    times = []
+    for it in range(warm + reps):
+        t0 = time.perf_counter()
+        idx, val = so.get_outputs(so.sims(G, q))
+        dt = time.perf_counter() - t0
+        if it >= warm:
+            times.append(dt)
+    t = float(np.mean(times))
+    qps = nq / (t * (total_rows / sample_rows))
+    return qps, t, threads
+
+
+def ref_gpu_search(nq: int, rows: int, reps: int):
+    """the reference's own GPU path (src/matmul.cpp compiled verbatim, oracle/_ref) + restated getOutputs, host buffers in/out
+    exactly as MatMul::calculate is called (src/arcface.cpp:189-217). Returns dict or None."""
+    import ctypes as C
+
+    lib = ROOT / "oracle" / "_ref" / "libref_matmul.so"
+    if not lib.exists():
+        return None
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return None
+        from oracle import search_oracle as so
+
+        L = C.CDLL(str(lib))
+        L.ref_matmul_new.restype = C.c_void_p
+        L.ref_matmul_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ref_matmul_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_matmul_free.argtypes = [C.c_void_p]
+        rng = np.random.default_rng(GALLERY_SEED)
+        G = rng.standard_normal((rows, 512), dtype=np.float32)
+        G /= np.linalg.norm(G, axis=1, keepdims=True)
+        q = so.planted_queries(G[rng.integers(0, rows, nq)], 0.75, PLANT_SEED)
+        h = L.ref_matmul_new()
+        if not h or L.ref_matmul_init(h, G.ctypes.data_as(C.c_void_p), rows, 512) != 0:
+            return None
+        out = np.empty((nq, rows), np.float32)
+        times = []
+        for it in range(reps + 1):
+            t0 = time.perf_counter()
+            if L.ref_matmul_calculate(h, q.ctypes.data_as(C.c_void_p), nq, out.ctypes.data_as(C.c_void_p)) != 0:
+                return None
+            so.get_outputs(out)
+            if it:
+                times.append(time.perf_counter() - t0)
+        L.ref_matmul_free(h)
+        t = float(np.mean(times))
+        return {"what": "reference src/matmul.cpp (cuBLASLt fp32) + host argmax, host buffers, same GPU", "rows": rows, "queries": nq,
+                "s_per_batch": t, "queries_per_s_at_sample": nq / t}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_rows = min(args.rows, args.cpu_sample_rows)
+    times = []
+    qps, t, threads = cpu_search_sample(args.queries, sample_rows, args.rows, reps=args.steps, warm=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3 * (args.rows / sample_rows), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"cosine-sim search: batch={args.queries} queries vs {args.rows}x512 gallery (CPU port of the reference path)",
+                   "queries": args.queries, "gallery_rows": args.rows, "dim": 512},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.queries} queries x {sample_rows} unit rows, numpy sgemm fp32 + first-max argmax per step; "
+                                   f"time scaled x{args.rows / sample_rows:g} to {args.rows} rows"},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    rg = ref_gpu_search(args.queries, min(args.rows, 1_000_000), reps=3)
+    if rg:
+        line["ref_gpu"] = rg
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--queries", type=int, default=256)
+    ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import frb200
+    from oracle import search_oracle as so  # checker only: verifies results outside the timed regions
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    n_gpus = world
+
+    N, Q, K = args.rows, args.queries, 1
+    per = (N + n_gpus - 1) // n_gpus
+    lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
+    gal = frb200.Gallery.synthetic(hi - lo, seed=GALLERY_SEED, device=local, row_offset=lo)
+    gal.set_path(frb200.FR_PATH_TENSOR)
+
+    # queries: planted on known global rows (same on every rank), so expected identities are known without a host gallery
+    rng = np.random.default_rng(QUERY_SEED)
+    planted = np.sort(rng.integers(0, N, Q))
+    planted_rows = so.synth_rows(planted, GALLERY_SEED)
+    q_host = so.planted_queries(planted_rows, 0.75, PLANT_SEED)
+    want_score = np.einsum("ij,ij->i", q_host.astype(np.float64), planted_rows.astype(np.float64))
+
+    q_pin = torch.from_numpy(q_host).pin_memory()
+    q_dev = torch.empty((Q, 512), dtype=torch.float32, device=dev)
+    loc_s = torch.empty((Q, K), dtype=torch.float32, device=dev)
+    loc_i = torch.empty((Q, K), dtype=torch.int64, device=dev)
+    all_s = torch.empty((n_gpus, Q, K), dtype=torch.float32, device=dev)
+    all_i = torch.empty((n_gpus, Q, K), dtype=torch.int64, device=dev)
+    out_s = torch.empty((Q, K), dtype=torch.float32, device=dev)
+    out_i = torch.empty((Q, K), dtype=torch.int64, device=dev)
+    res_s_pin = torch.empty((Q, K), dtype=torch.float32).pin_memory()
+    res_i_pin = torch.empty((Q, K), dtype=torch.int64).pin_memory()
+    stream = torch.cuda.current_stream()
+    sraw = stream.cuda_stream
+
+    def search_step():
+        """device-resident hot path: fused scan + re-score on this shard, then the cross-GPU exchange + merge"""
+        if n_gpus == 1:
+            gal.topk_dev(q_dev, K, out_s, out_i, stream=sraw)
+        else:
+            gal.topk_dev(q_dev, K, loc_s, loc_i, stream=sraw)
+            dist.all_gather_into_tensor(all_s, loc_s)
+            dist.all_gather_into_tensor(all_i, loc_i)
+            frb200.topk_merge_dev(all_s, all_i, n_gpus, Q, K, out_s, out_i, local, stream=sraw)
+
+    def e2e_step():
+        q_dev.copy_(q_pin, non_blocking=True)
+        search_step()
+        res_s_pin.copy_(out_s, non_blocking=True)
+        res_i_pin.copy_(out_i, non_blocking=True)
+        stream.synchronize()
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if n_gpus == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- correctness outside the timed region: top-1 identity exact, scores within 1e-5 of the host dot product
+    q_dev.copy_(q_pin)
+    for _ in range(args.warmup):
+        search_step()
+    torch.cuda.synchronize()
+    got_i = out_i.cpu().numpy()[:, 0]
+    got_s = out_s.cpu().numpy()[:, 0]
+    parity_ok = bool(np.array_equal(got_i, planted) and np.abs(got_s - want_score).max() <= 1e-5)
+    if not parity_ok:
+        raise SystemExit(f"bench.py: parity failure (top-1 mismatches: {int((got_i != planted).sum())}, "
+                         f"max |dscore| {float(np.abs(got_s - want_score).max()):.3e})")
+
+    # ---- device-resident timing (value)
+    sampler = ClockSampler(local)
+    gal.set_timing(True)
+    barrier()
+    sampler.start()
+    launches0 = frb200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        search_step()
+    ev1.record(stream)
+    barrier()
+    launches = frb200.launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.result()
+    scan_ms, scan_n = gal.scan_time()
+    gal.set_timing(False)
+    ms_per_step = ms_total / args.steps
+    value = Q / (ms_per_step * 1e-3)
+
+    # ---- end-to-end timing through host buffers (e2e)
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    ev3.record(stream)
+    barrier()
+    e2e_s = max_over_ranks(ev2.elapsed_time(ev3)) * 1e-3 / args.steps
+    e2e_ok = bool(np.array_equal(res_i_pin.numpy()[:, 0], planted))
+    if not e2e_ok:
+        raise SystemExit("bench.py: e2e parity failure")
+
+    hbm_peak, tf_burst, tf_sust, peak_src = peaks()
+    st = gal.last_stats()
+    scan_ms_avg = scan_ms / max(scan_n, 1)
+    achieved = st.scan_bytes / (scan_ms_avg * 1e-3) / 1e9 if scan_n else None
+    tflops = st.flops / (scan_ms_avg * 1e-3) / 1e12 if scan_n else None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 scan / f32 re-score",
+            "data": "synthetic",
+            "config": {"workload": f"gallery-sharded cosine-sim search: batch={Q} queries vs {N}x512 gallery, top-{K}, "
+                                   f"{n_gpus} GPU(s), NCCL all-gather of per-shard top-k",
+                       "queries": Q, "gallery_rows": N, "dim": 512, "rows_per_gpu": per, "parallelism": f"row-shard x{n_gpus}",
+                       "l2": f"inputs larger than L2 ({per * 1024 / 1e6:.0f} MB fp16 scan copy per GPU vs 126 MB)"},
+            "e2e": {"value": Q / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Q * 512 * 4, "d2h_bytes_per_step": Q * K * 12,
+                    "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "parity": {"top1_exact": parity_ok, "max_abs_dscore": float(np.abs(got_s - want_score).max())},
+            "roofline": {"bound": "hbm", "kernel": "cosine_topk_coarse", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": scan_ms_avg, "kernel_share_of_step": (scan_ms_avg / ms_per_step) if scan_n else None,
+                         "algorithmic_bytes_per_launch": int(st.scan_bytes), "launches_timed": scan_n},
+            "roofline_tensor": {"bound": "tensor", "achieved": tflops, "peak": tf_sust, "unit": "TFLOP/s",
+                                "frac": (tflops / tf_sust) if tflops else None, "peak_source": peak_src + " (bf16 sustained)",
+                                "flops_per_launch": int(st.flops)},
+        }
+        traffic_file = ROOT / "profiles" / "traffic.json"
+        if traffic_file.exists():
+            try:
+                tr = json.loads(traffic_file.read_text())
+                key = f"cosine_topk_coarse@{per}"
+                if key in tr:
+                    line["roofline"]["traffic"] = tr[key]
+            except Exception:
+                pass
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            sample_rows = min(N, args.cpu_sample_rows)
+            qps, t, threads = cpu_search_sample(Q, sample_rows, N, reps=3, warm=1)
+            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{Q} queries x {sample_rows} unit rows, numpy sgemm fp32 + first-max argmax "
+                                              f"({t:.3f} s/pass), scaled x{N / sample_rows:g} to {N} rows"}
+            rg = ref_gpu_search(Q, min(N, 1_000_000), reps=3)
+            if rg:
+                line["ref_gpu"] = rg
+        print(json.dumps(line), flush=True)
+    gal.close()
+    if n_gpus > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

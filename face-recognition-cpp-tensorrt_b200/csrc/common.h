@@ -1,0 +1,91 @@
+// Host-side helpers shared by the translation units of libfr_b200: error plumbing for the C ABI,
+// launch counting, TMA descriptor construction.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/fr_b200.h"
+
+namespace frb {
+
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+struct CudaError {
+    std::string msg;
+};
+
+#define FRB_CUDA(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) {                                                                             \
+            throw ::frb::CudaError{std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                   std::to_string(__LINE__) + ")"};                                          \
+        }                                                                                                    \
+    } while (0)
+
+struct ArgError {
+    std::string msg;
+};
+struct StateError {
+    std::string msg;
+};
+struct FileError {
+    int code;
+    std::string msg;
+};
+
+// Wrap the body of every extern "C" entry point: map C++ exceptions to ABI error codes.
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return FR_OK;
+    } catch (const CudaError& e) {
+        set_error(e.msg);
+        cudaGetLastError();  // clear sticky-less errors
+        return FR_ECUDA;
+    } catch (const ArgError& e) {
+        set_error(e.msg);
+        return FR_EINVAL;
+    } catch (const StateError& e) {
+        set_error(e.msg);
+        return FR_ESTATE;
+    } catch (const FileError& e) {
+        set_error(e.msg);
+        return e.code;
+    } catch (const std::exception& e) {
+        set_error(std::string("internal: ") + e.what());
+        return FR_ECUDA;
+    }
+}
+
+// Select `device`, check it is sm_100, return its SM count.
+int use_device(int device);
+
+// RAII device switch for entry points
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) FRB_CUDA(cudaSetDevice(dev));
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// 2-D row-major 16-bit tensor [rows, cols] -> TMA map with box [box_rows, box_cols], 128-byte swizzle.
+CUtensorMap make_tmap_2d_f16(const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
+// 4-D NHWC 16-bit tensor [n, h, w, c] -> TMA map with box [bn, bh, bw, bc], 128-byte swizzle, zero OOB fill.
+CUtensorMap make_tmap_nhwc_f16(const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, uint32_t bn, uint32_t bh, uint32_t bw,
+                               uint32_t bc);
+
+}  // namespace frb

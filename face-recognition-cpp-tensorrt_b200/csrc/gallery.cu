@@ -1,0 +1,418 @@
+// Gallery / cosine-similarity search: host side of the C ABI (include/fr_b200.h, "Gallery" section).
+// Replaces MatMul (/root/reference src/matmul.{h,cpp}) and the host argmax ArcFaceIR50::getOutputs (src/arcface.cpp:203-217).
+//
+// Resident layout per gallery (one shard of a row-partitioned gallery):
+//   rows_f32  n x 512 f32 row-major   master copy: dense sims and the exact re-score read it            (2 KiB / row)
+//   rows_f16  n x 512 f16 row-major   scan copy streamed by the fused tensor-core kernel through TMA    (1 KiB / row)
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "common.h"
+#include "search_kernels.cuh"
+
+using namespace frb;
+
+struct FrGallery {
+    int device = 0;
+    int sms = 0;
+    int64_t n = 0;
+    int64_t row_offset = 0;
+    float* rows_f32 = nullptr;
+    __half* rows_f16 = nullptr;
+    CUtensorMap tmap{};
+    cudaStream_t stream = nullptr;
+    // scratch, sized for one chunk of 256 queries
+    float* q_dev = nullptr;          // 256 x 512
+    float* cand_s = nullptr;         // [units][256][kKC]
+    int* cand_i = nullptr;
+    float* res_s = nullptr;          // 256 x FR_TOPK_MAX
+    long long* res_i = nullptr;
+    float* sims_ws = nullptr;        // dense-path workspace
+    size_t sims_ws_floats = 0;
+    int path = FR_PATH_AUTO;
+    FrSearchStats stats{};
+    // optional CUDA-event timing of the dominant (fused scan) kernel, for bench.py's roofline
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+};
+
+namespace {
+
+constexpr int kChunkQ = 256;
+constexpr int64_t kExactMaxRows = 2048;  // FR_PATH_AUTO: below this the exact SIMT path has the lower latency
+
+void alloc_common(FrGallery* g) {
+    FRB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    FRB_CUDA(cudaMalloc(&g->q_dev, sizeof(float) * kChunkQ * kDim));
+    FRB_CUDA(cudaMalloc(&g->cand_s, sizeof(float) * 148 * kChunkQ * kKC));
+    FRB_CUDA(cudaMalloc(&g->cand_i, sizeof(int) * 148 * kChunkQ * kKC));
+    FRB_CUDA(cudaMalloc(&g->res_s, sizeof(float) * kChunkQ * FR_TOPK_MAX));
+    FRB_CUDA(cudaMalloc(&g->res_i, sizeof(long long) * kChunkQ * FR_TOPK_MAX));
+    static bool attr_done[16] = {};
+    if (!attr_done[g->device & 15]) {
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2>::kSmemBytes));
+        attr_done[g->device & 15] = true;
+    }
+}
+
+FrGallery* new_gallery(int64_t n, int dim, int device, int64_t row_offset) {
+    if (dim != kDim) throw ArgError{"dim must be 512 (rec_outputDim)"};
+    if (n < 0 || n >= (int64_t(1) << 31) - kTileRows) throw ArgError{"row count out of range for one shard"};
+    auto* g = new FrGallery();
+    g->sms = use_device(device);
+    g->device = device;
+    g->n = n;
+    g->row_offset = row_offset;
+    try {
+        alloc_common(g);
+        if (n > 0) {
+            FRB_CUDA(cudaMalloc(&g->rows_f32, sizeof(float) * n * kDim));
+            FRB_CUDA(cudaMalloc(&g->rows_f16, sizeof(__half) * n * kDim));
+            g->tmap = make_tmap_2d_f16(g->rows_f16, static_cast<uint64_t>(n), kDim, 128, 64);
+        }
+    } catch (...) {
+        fr_gallery_destroy(g);
+        throw;
+    }
+    return g;
+}
+
+void convert_scan_copy(FrGallery* g) {
+    if (g->n == 0) return;
+    const long long n4 = g->n * kDim / 4;
+    const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, g->sms * 16LL));
+    f32_to_f16_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f16, n4);
+    count_launch();
+    FRB_CUDA(cudaGetLastError());
+    FRB_CUDA(cudaStreamSynchronize(g->stream));
+}
+
+template <int CG>
+void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tiles, cudaStream_t st) {
+    std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+    if (g->timing) {
+        if (g->ev_used == g->ev_pool.size()) {
+            cudaEvent_t a, b;
+            FRB_CUDA(cudaEventCreate(&a));
+            FRB_CUDA(cudaEventCreate(&b));
+            g->ev_pool.emplace_back(a, b);
+        }
+        ev = &g->ev_pool[g->ev_used++];
+        FRB_CUDA(cudaEventRecord(ev->first, st));
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(units * CG);
+    cfg.blockDim = dim3(kSearchThreads);
+    cfg.dynamicSmemBytes = CoarseCfg<CG>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG>, g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles, g->cand_s,
+                                g->cand_i));
+    count_launch();
+    if (ev) FRB_CUDA(cudaEventRecord(ev->second, st));
+}
+
+void ensure_sims_ws(FrGallery* g, size_t floats) {
+    if (g->sims_ws_floats >= floats) return;
+    if (g->sims_ws) cudaFree(g->sims_ws);
+    g->sims_ws = nullptr;
+    g->sims_ws_floats = 0;
+    FRB_CUDA(cudaMalloc(&g->sims_ws, floats * sizeof(float)));
+    g->sims_ws_floats = floats;
+}
+
+void launch_sims(FrGallery* g, const float* q_dev, int nq, float* out_dev, cudaStream_t st) {
+    const int warps_per_block = kSimsThreads / 32;
+    const int gx = static_cast<int>(std::min<int64_t>((g->n + warps_per_block - 1) / warps_per_block, g->sms * 8LL));
+    dim3 grid(gx, (nq + kSimsQ - 1) / kSimsQ);
+    sims_kernel<<<grid, kSimsThreads, 0, st>>>(g->rows_f32, g->n, q_dev, nq, out_dev);
+    count_launch();
+    FRB_CUDA(cudaGetLastError());
+}
+
+// one chunk (nq <= 256) of queries already on the device; results to scores_dev / idx_dev (device, nq x k)
+void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_dev, long long* idx_dev, cudaStream_t st) {
+    const bool exact = g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows);
+    g->stats = FrSearchStats{};
+    if (exact) {
+        ensure_sims_ws(g, static_cast<size_t>(nq) * g->n);
+        launch_sims(g, q_dev, nq, g->sims_ws, st);
+        topk_dense_kernel<<<nq, kSelThreads, 0, st>>>(g->sims_ws, g->n, k, g->row_offset, scores_dev, idx_dev);
+        count_launch();
+        FRB_CUDA(cudaGetLastError());
+        g->stats.scan_bytes = g->n * kDim * 4;
+        g->stats.flops = 2LL * nq * g->n * kDim;
+        g->stats.launches = 2;
+        g->stats.ctas = 0;
+        return;
+    }
+    const int tiles = static_cast<int>((g->n + kTileRows - 1) / kTileRows);
+    const int cg = nq > kQRows ? 2 : 1;
+    int units;
+    if (cg == 2) {
+        units = std::min(g->sms / 2, tiles);
+        launch_coarse<2>(g, q_dev, nq, units, tiles, st);
+    } else {
+        units = std::min(g->sms, tiles);
+        launch_coarse<1>(g, q_dev, nq, units, tiles, st);
+    }
+    topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units, cg * kQRows, q_dev, g->rows_f32, k, g->row_offset,
+                                                   scores_dev, idx_dev);
+    count_launch();
+    FRB_CUDA(cudaGetLastError());
+    g->stats.scan_bytes = g->n * kDim * 2;
+    g->stats.flops = 2LL * (cg * kQRows) * g->n * kDim;
+    g->stats.launches = 2;
+    g->stats.ctas = units * cg;
+}
+
+void check_query_args(const FrGallery* g, const void* q, int nq) {
+    if (!g) throw ArgError{"null gallery"};
+    if (!q || nq <= 0) throw ArgError{"no queries"};
+    if (g->n == 0) throw StateError{"Feature matching: No faces in database or no faces found"};  // src/arcface.cpp:198
+}
+
+}  // namespace
+
+extern "C" {
+
+int fr_gallery_create(const float* rows, int64_t n, int dim, int device, int64_t row_offset, FrGallery** out) {
+    return guarded([&] {
+        if (!out) throw ArgError{"out is null"};
+        if (n > 0 && !rows) throw ArgError{"rows is null"};
+        FrGallery* g = new_gallery(n, dim, device, row_offset);
+        try {
+            if (n > 0) {
+                FRB_CUDA(cudaMemcpyAsync(g->rows_f32, rows, sizeof(float) * n * kDim, cudaMemcpyHostToDevice, g->stream));
+                convert_scan_copy(g);
+            }
+        } catch (...) {
+            fr_gallery_destroy(g);
+            throw;
+        }
+        *out = g;
+    });
+}
+
+int fr_gallery_create_dev(const float* rows_dev, int64_t n, int dim, int device, int64_t row_offset, FrGallery** out) {
+    return guarded([&] {
+        if (!out) throw ArgError{"out is null"};
+        if (n > 0 && !rows_dev) throw ArgError{"rows is null"};
+        FrGallery* g = new_gallery(n, dim, device, row_offset);
+        try {
+            if (n > 0) {
+                FRB_CUDA(cudaMemcpyAsync(g->rows_f32, rows_dev, sizeof(float) * n * kDim, cudaMemcpyDeviceToDevice, g->stream));
+                convert_scan_copy(g);
+            }
+        } catch (...) {
+            fr_gallery_destroy(g);
+            throw;
+        }
+        *out = g;
+    });
+}
+
+int fr_gallery_create_synthetic(int64_t n, int dim, uint64_t seed, int device, int64_t row_offset, FrGallery** out) {
+    return guarded([&] {
+        if (!out) throw ArgError{"out is null"};
+        FrGallery* g = new_gallery(n, dim, device, row_offset);
+        try {
+            if (n > 0) {
+                const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, g->sms * 16LL));
+                synth_rows_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f16, n, seed, row_offset);
+                count_launch();
+                FRB_CUDA(cudaGetLastError());
+                FRB_CUDA(cudaStreamSynchronize(g->stream));
+            }
+        } catch (...) {
+            fr_gallery_destroy(g);
+            throw;
+        }
+        *out = g;
+    });
+}
+
+void fr_gallery_destroy(FrGallery* g) {
+    if (!g) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    cudaFree(g->rows_f32);
+    cudaFree(g->rows_f16);
+    cudaFree(g->q_dev);
+    cudaFree(g->cand_s);
+    cudaFree(g->cand_i);
+    cudaFree(g->res_s);
+    cudaFree(g->res_i);
+    cudaFree(g->sims_ws);
+    for (auto& e : g->ev_pool) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (g->stream) cudaStreamDestroy(g->stream);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete g;
+}
+
+int64_t fr_gallery_rows(const FrGallery* g) { return g ? g->n : -1; }
+
+int fr_gallery_set_path(FrGallery* g, int path) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        if (path != FR_PATH_AUTO && path != FR_PATH_EXACT && path != FR_PATH_TENSOR) throw ArgError{"unknown path"};
+        g->path = path;
+    });
+}
+
+int fr_gallery_read_rows(FrGallery* g, int64_t first, int64_t count, float* out_rows) {
+    return guarded([&] {
+        if (!g || !out_rows) throw ArgError{"null argument"};
+        if (first < 0 || count < 0 || first + count > g->n) throw ArgError{"row range out of bounds"};
+        DeviceGuard dg(g->device);
+        if (count == 0) return;
+        FRB_CUDA(cudaMemcpyAsync(out_rows, g->rows_f32 + first * kDim, sizeof(float) * count * kDim, cudaMemcpyDeviceToHost, g->stream));
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+    });
+}
+
+int fr_gallery_sims_dev(FrGallery* g, const float* q_dev, int nq, float* out_dev, void* stream) {
+    return guarded([&] {
+        check_query_args(g, q_dev, nq);
+        if (!out_dev) throw ArgError{"out is null"};
+        DeviceGuard dg(g->device);
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g->stream;
+        launch_sims(g, q_dev, nq, out_dev, st);
+    });
+}
+
+int fr_gallery_sims(FrGallery* g, const float* q, int nq, float* out) {
+    return guarded([&] {
+        check_query_args(g, q, nq);
+        if (!out) throw ArgError{"out is null"};
+        DeviceGuard dg(g->device);
+        // chunk the queries so that the device workspace stays bounded (the reference allocates n x m at once, src/matmul.cpp:41)
+        const int64_t max_ws_floats = int64_t(1) << 28;  // 1 GiB
+        const int step = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nq, max_ws_floats / g->n)));
+        for (int q0 = 0; q0 < nq; q0 += step) {
+            const int m = std::min(step, nq - q0);
+            float* qd = nullptr;
+            if (m <= kChunkQ) qd = g->q_dev;
+            else FRB_CUDA(cudaMalloc(&qd, sizeof(float) * m * kDim));
+            try {
+                ensure_sims_ws(g, static_cast<size_t>(m) * g->n);
+                FRB_CUDA(cudaMemcpyAsync(qd, q + static_cast<size_t>(q0) * kDim, sizeof(float) * m * kDim, cudaMemcpyHostToDevice, g->stream));
+                launch_sims(g, qd, m, g->sims_ws, g->stream);
+                FRB_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(q0) * g->n, g->sims_ws, sizeof(float) * m * g->n, cudaMemcpyDeviceToHost,
+                                         g->stream));
+                FRB_CUDA(cudaStreamSynchronize(g->stream));
+            } catch (...) {
+                if (qd != g->q_dev) cudaFree(qd);
+                throw;
+            }
+            if (qd != g->q_dev) cudaFree(qd);
+        }
+    });
+}
+
+int fr_gallery_topk_dev(FrGallery* g, const float* q_dev, int nq, int k, float* scores_dev, int64_t* idx_dev, void* stream) {
+    return guarded([&] {
+        check_query_args(g, q_dev, nq);
+        if (k < 1 || k > FR_TOPK_MAX) throw ArgError{"k out of range"};
+        if (!scores_dev || !idx_dev) throw ArgError{"null output"};
+        DeviceGuard dg(g->device);
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g->stream;
+        FrSearchStats total{};
+        for (int q0 = 0; q0 < nq; q0 += kChunkQ) {
+            const int m = std::min(kChunkQ, nq - q0);
+            topk_chunk(g, q_dev + static_cast<size_t>(q0) * kDim, m, k, scores_dev + static_cast<size_t>(q0) * k,
+                       reinterpret_cast<long long*>(idx_dev) + static_cast<size_t>(q0) * k, st);
+            total.scan_bytes += g->stats.scan_bytes;
+            total.flops += g->stats.flops;
+            total.launches += g->stats.launches;
+            total.ctas = g->stats.ctas;
+        }
+        g->stats = total;
+    });
+}
+
+int fr_gallery_topk(FrGallery* g, const float* q, int nq, int k, float* scores, int64_t* idx) {
+    return guarded([&] {
+        check_query_args(g, q, nq);
+        if (k < 1 || k > FR_TOPK_MAX) throw ArgError{"k out of range"};
+        if (!scores || !idx) throw ArgError{"null output"};
+        DeviceGuard dg(g->device);
+        FrSearchStats total{};
+        for (int q0 = 0; q0 < nq; q0 += kChunkQ) {
+            const int m = std::min(kChunkQ, nq - q0);
+            FRB_CUDA(cudaMemcpyAsync(g->q_dev, q + static_cast<size_t>(q0) * kDim, sizeof(float) * m * kDim, cudaMemcpyHostToDevice, g->stream));
+            topk_chunk(g, g->q_dev, m, k, g->res_s, g->res_i, g->stream);
+            FRB_CUDA(cudaMemcpyAsync(scores + static_cast<size_t>(q0) * k, g->res_s, sizeof(float) * m * k, cudaMemcpyDeviceToHost, g->stream));
+            FRB_CUDA(cudaMemcpyAsync(idx + static_cast<size_t>(q0) * k, g->res_i, sizeof(long long) * m * k, cudaMemcpyDeviceToHost, g->stream));
+            FRB_CUDA(cudaStreamSynchronize(g->stream));
+            total.scan_bytes += g->stats.scan_bytes;
+            total.flops += g->stats.flops;
+            total.launches += g->stats.launches;
+            total.ctas = g->stats.ctas;
+        }
+        g->stats = total;
+    });
+}
+
+int fr_topk_merge_dev(const float* scores_parts_dev, const int64_t* idx_parts_dev, int n_parts, int nq, int k, float* scores_dev,
+                      int64_t* idx_dev, int device, void* stream) {
+    return guarded([&] {
+        if (!scores_parts_dev || !idx_parts_dev || !scores_dev || !idx_dev) throw ArgError{"null argument"};
+        if (n_parts < 1 || n_parts > 64 || nq < 1 || k < 1 || k > FR_TOPK_MAX) throw ArgError{"bad merge shape"};
+        DeviceGuard dg(device);
+        topk_merge_kernel<<<nq, 64, 0, static_cast<cudaStream_t>(stream)>>>(scores_parts_dev, reinterpret_cast<const long long*>(idx_parts_dev),
+                                                                          n_parts, nq, k, scores_dev, reinterpret_cast<long long*>(idx_dev));
+        count_launch();
+        FRB_CUDA(cudaGetLastError());
+    });
+}
+
+int fr_gallery_set_timing(FrGallery* g, int enable) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        g->timing = enable != 0;
+        g->ev_used = 0;
+    });
+}
+
+int fr_gallery_scan_time(FrGallery* g, double* total_ms, int* launches) {
+    return guarded([&] {
+        if (!g || !total_ms || !launches) throw ArgError{"null argument"};
+        DeviceGuard dg(g->device);
+        double sum = 0;
+        for (size_t i = 0; i < g->ev_used; ++i) {
+            FRB_CUDA(cudaEventSynchronize(g->ev_pool[i].second));
+            float ms = 0;
+            FRB_CUDA(cudaEventElapsedTime(&ms, g->ev_pool[i].first, g->ev_pool[i].second));
+            sum += ms;
+        }
+        *total_ms = sum;
+        *launches = static_cast<int>(g->ev_used);
+        g->ev_used = 0;
+    });
+}
+
+int fr_gallery_last_stats(const FrGallery* g, FrSearchStats* out) {
+    return guarded([&] {
+        if (!g || !out) throw ArgError{"null argument"};
+        *out = g->stats;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+"""ctypes binding of libfr_b200.so (include/fr_b200.h) used by tests/, bench.py and __graft_entry__.py.
+
+This is test/bench plumbing around the C ABI, not a second implementation: every call goes straight into the CUDA
+library and raises if the library is missing — there is no CPU fallback here or anywhere in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libfr_b200.so"
+
+FR_OK, FR_EINVAL, FR_ENODEVICE, FR_ECUDA, FR_ENOENT, FR_EFORMAT, FR_ESTATE = 0, -1, -2, -3, -4, -5, -6
+FR_TOPK_MAX = 8
+FR_PATH_AUTO, FR_PATH_EXACT, FR_PATH_TENSOR = 0, 1, 2
+
+
+class FrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fr_b200 error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class FrBbox(C.Structure):
+    _fields_ = [("x1", C.c_int), ("y1", C.c_int), ("x2", C.c_int), ("y2", C.c_int), ("score", C.c_float)]
+
+
+class FrSearchStats(C.Structure):
+    _fields_ = [("scan_bytes", C.c_int64), ("flops", C.c_int64), ("launches", C.c_int), ("ctas", C.c_int)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the library (once). Fails loudly if it was not built: run face-recognition-cpp-tensorrt_b200/build.py."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} is missing: build it with `python {PKG / 'build.py'}` (no CPU fallback exists)")
+        L = C.CDLL(str(LIB_PATH))
+        L.fr_last_error.restype = C.c_char_p
+        L.fr_launch_count.restype = C.c_uint64
+        L.fr_gallery_rows.restype = C.c_int64
+        L.fr_gallery_rows.argtypes = [C.c_void_p]
+        L.fr_gallery_destroy.restype = None
+        L.fr_gallery_destroy.argtypes = [C.c_void_p]
+        L.fr_gallery_create.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+        L.fr_gallery_create_dev.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+        L.fr_gallery_create_synthetic.argtypes = [C.c_int64, C.c_int, C.c_uint64, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+        L.fr_gallery_set_path.argtypes = [C.c_void_p, C.c_int]
+        L.fr_gallery_read_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        L.fr_gallery_sims.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.fr_gallery_sims_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.fr_gallery_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.fr_gallery_topk_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fr_topk_merge_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.fr_gallery_last_stats.argtypes = [C.c_void_p, C.POINTER(FrSearchStats)]
+        L.fr_gallery_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.fr_gallery_scan_time.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != FR_OK:
+        raise FrError(rc, lib().fr_last_error().decode(errors="replace"))
+
+
+def launch_count() -> int:
+    return int(lib().fr_launch_count())
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(x):
+    """host numpy array -> void*, torch tensor (any device) -> data_ptr, int -> itself"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data_as(C.c_void_p)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    return C.c_void_p(x.data_ptr())
+
+
+class Gallery:
+    """One shard of the gallery resident on one GPU (MatMul::init, /root/reference src/matmul.cpp:9-34)."""
+
+    def __init__(self, handle: C.c_void_p, device: int):
+        self._h = handle
+        self.device = device
+
+    @classmethod
+    def from_rows(cls, rows, device: int = 0, row_offset: int = 0) -> "Gallery":
+        rows = _f32(rows)
+        n, dim = (rows.shape if rows.ndim == 2 else (0, 512))
+        h = C.c_void_p()
+        check(lib().fr_gallery_create(_ptr(rows) if n else None, n, dim, device, row_offset, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
+    def from_device_rows(cls, rows_t, device: int = 0, row_offset: int = 0) -> "Gallery":
+        h = C.c_void_p()
+        check(lib().fr_gallery_create_dev(_ptr(rows_t), rows_t.shape[0], rows_t.shape[1], device, row_offset, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
+    def synthetic(cls, n: int, seed: int, device: int = 0, row_offset: int = 0, dim: int = 512) -> "Gallery":
+        h = C.c_void_p()
+        check(lib().fr_gallery_create_synthetic(n, dim, seed, device, row_offset, C.byref(h)))
+        return cls(h, device)
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_gallery_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def rows(self) -> int:
+        return int(lib().fr_gallery_rows(self._h))
+
+    def set_path(self, path: int) -> None:
+        check(lib().fr_gallery_set_path(self._h, path))
+
+    def read_rows(self, first: int, count: int) -> np.ndarray:
+        out = np.empty((count, 512), np.float32)
+        check(lib().fr_gallery_read_rows(self._h, first, count, _ptr(out)))
+        return out
+
+    def sims(self, q) -> np.ndarray:
+        """MatMul::calculate (src/matmul.cpp:36-77): out[i, j] = <q_i, row_j> in exact fp32."""
+        q = _f32(q)
+        out = np.empty((q.shape[0], max(self.rows, 0)), np.float32)
+        check(lib().fr_gallery_sims(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        return out
+
+    def topk(self, q, k: int = 1, scores_out=None, idx_out=None):
+        """host queries -> (scores nq x k f32, idx nq x k int64), order (score desc, row asc)."""
+        q = _f32(q) if isinstance(q, np.ndarray) or not hasattr(q, "data_ptr") else q
+        nq = q.shape[0]
+        scores = scores_out if scores_out is not None else np.empty((nq, k), np.float32)
+        idx = idx_out if idx_out is not None else np.empty((nq, k), np.int64)
+        check(lib().fr_gallery_topk(self._h, _ptr(q), nq, k, _ptr(scores), _ptr(idx)))
+        return scores, idx
+
+    def topk_dev(self, q_t, k, scores_t, idx_t, stream: int = 0) -> None:
+        """device tensors in/out (torch), launched on `stream` (raw cudaStream_t value; 0 = the handle's own stream)."""
+        check(lib().fr_gallery_topk_dev(self._h, _ptr(q_t), q_t.shape[0], k, _ptr(scores_t), _ptr(idx_t), C.c_void_p(stream)))
+
+    def sims_dev(self, q_t, out_t, stream: int = 0) -> None:
+        check(lib().fr_gallery_sims_dev(self._h, _ptr(q_t), q_t.shape[0], _ptr(out_t), C.c_void_p(stream)))
+
+    def set_timing(self, enable: bool) -> None:
+        check(lib().fr_gallery_set_timing(self._h, int(enable)))
+
+    def scan_time(self):
+        """(summed ms, launches) of the fused scan kernel since timing was enabled / last read"""
+        ms, n = C.c_double(), C.c_int()
+        check(lib().fr_gallery_scan_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def last_stats(self) -> FrSearchStats:
+        st = FrSearchStats()
+        check(lib().fr_gallery_last_stats(self._h, C.byref(st)))
+        return st
+
+
+def topk_merge_dev(scores_parts_t, idx_parts_t, n_parts: int, nq: int, k: int, scores_t, idx_t, device: int, stream: int = 0) -> None:
+    check(lib().fr_topk_merge_dev(_ptr(scores_parts_t), _ptr(idx_parts_t), n_parts, nq, k, _ptr(scores_t), _ptr(idx_t), device,
+                                  C.c_void_p(stream)))

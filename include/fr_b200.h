@@ -1,0 +1,118 @@
+/*
+ * fr_b200.h — C ABI of the B200-native face-recognition hot path.
+ *
+ * This is the drop-in boundary underneath the reference's C++ classes. The reference
+ * (nghiapq77/face-recognition-cpp-tensorrt) has no FFI layer of its own: its "operator API"
+ * is the public part of src/retinaface.h, src/arcface.h, src/matmul.h and src/common.h, compiled
+ * into the same executable. The header-only C++ shim in
+ * face-recognition-cpp-tensorrt_b200/cpp/{common,retinaface,arcface,matmul}.h re-creates those classes
+ * on top of the entry points below; each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FR_E* code on failure; the message for the
+ *     calling thread's last failure is returned by fr_last_error(). No C++ exception crosses the ABI.
+ *   - handles are opaque, own all their device memory and one CUDA stream, and are NOT re-entrant
+ *     (same contract as the reference objects: one instance = one stream, src/retinaface.h:44,
+ *     src/arcface.h:55, src/matmul.h:31). Different handles may be used from different threads.
+ *   - all output buffers are caller-allocated. "host" pointers are ordinary host memory, "_dev"
+ *     entry points take device pointers on the handle's device plus a cudaStream_t passed as void*
+ *     (NULL = the handle's own stream) and do not synchronise.
+ *   - there is no CPU fallback: if no sm_100 device is present, *_create fails with FR_ENODEVICE.
+ */
+#ifndef FR_B200_H
+#define FR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR_OK 0
+#define FR_EINVAL (-1)    /* bad argument */
+#define FR_ENODEVICE (-2) /* no usable sm_100 GPU */
+#define FR_ECUDA (-3)     /* CUDA runtime/driver error (text in fr_last_error) */
+#define FR_ENOENT (-4)    /* weight file missing ("Cant find engine file", src/retinaface.cpp:53) */
+#define FR_EFORMAT (-5)   /* weight file malformed */
+#define FR_ESTATE (-6)    /* call not valid in this state (e.g. empty gallery, src/arcface.cpp:198) */
+
+const char *fr_last_error(void);
+/* library/ABI version, bumped on any signature change */
+int fr_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t fr_launch_count(void);
+
+/* ---- a1: detection record. Same layout as `struct Bbox`, src/common.h:13-16.
+ *      x = row (vertical), y = column (horizontal): src/retinaface.cpp:165,171-174. */
+typedef struct FrBbox {
+    int x1, y1, x2, y2;
+    float score;
+} FrBbox;
+
+/* =====================================================================================
+ * Gallery / cosine-similarity search  (replaces MatMul, src/matmul.{h,cpp}, and the host
+ * argmax ArcFaceIR50::getOutputs, src/arcface.cpp:203-217)
+ * ===================================================================================== */
+typedef struct FrGallery FrGallery;
+
+/* MatMul::MatMul + MatMul::init (src/matmul.cpp:3-34): upload `rows` (n x dim, row-major f32, host)
+ * to `device`. The rows are copied; the caller may free them. dim must be 512 (rec_outputDim,
+ * app/config.json:16). `row_offset` is added to every index the search returns (global row id of
+ * local row 0 when the gallery is one shard of a row-partitioned gallery; 0 otherwise).
+ * n may be 0 (search calls then fail with FR_ESTATE, as featureMatching throws, src/arcface.cpp:198). */
+int fr_gallery_create(const float *rows, int64_t n, int dim, int device, int64_t row_offset, FrGallery **out);
+/* Same, rows already on `device` (f32). */
+int fr_gallery_create_dev(const float *rows_dev, int64_t n, int dim, int device, int64_t row_offset, FrGallery **out);
+/* Bench/test utility: fill a gallery on the device with a counter-based generator so that the host
+ * can regenerate any row bit-exactly (oracle/search_oracle.py: synth_rows). Row r (global id
+ * row_offset + r) = L2-normalised vector of 512 hashed normals keyed by (seed, global id). */
+int fr_gallery_create_synthetic(int64_t n, int dim, uint64_t seed, int device, int64_t row_offset, FrGallery **out);
+void fr_gallery_destroy(FrGallery *g);
+int64_t fr_gallery_rows(const FrGallery *g);
+/* copy rows [first, first+count) (f32) back to the host — test hook */
+int fr_gallery_read_rows(FrGallery *g, int64_t first, int64_t count, float *out_rows);
+
+/* MatMul::calculate (src/matmul.cpp:36-77): out[i*n_rows + j] = <q_i, row_j>, exact fp32
+ * (CUDA_R_32F / CUBLAS_COMPUTE_32F, src/matmul.h:24-25). q: nq x dim host f32; out: nq x n_rows host f32. */
+int fr_gallery_sims(FrGallery *g, const float *q, int nq, float *out);
+int fr_gallery_sims_dev(FrGallery *g, const float *q_dev, int nq, float *out_dev, void *stream);
+
+/* Fused search: featureMatching + getOutputs (src/arcface.cpp:189-217) without materialising the
+ * similarity matrix. For each query the k best rows ordered by (score descending, row index ascending)
+ * — for k = 1 this is std::max_element's "first maximum wins" (src/arcface.cpp:210).
+ * scores: nq x k f32 (exact fp32 dot products), idx: nq x k int64 (row_offset + local row).
+ * If fewer than k rows exist, the tail is filled with score = -inf, idx = -1. 1 <= k <= FR_TOPK_MAX. */
+#define FR_TOPK_MAX 8
+int fr_gallery_topk(FrGallery *g, const float *q, int nq, int k, float *scores, int64_t *idx);
+int fr_gallery_topk_dev(FrGallery *g, const float *q_dev, int nq, int k, float *scores_dev, int64_t *idx_dev, void *stream);
+
+/* Cross-shard merge (the step after the all-gather of per-shard results): parts holds
+ * n_parts blocks of nq x k (score, idx) results; writes the nq x k best by (score desc, idx asc). */
+int fr_topk_merge_dev(const float *scores_parts_dev, const int64_t *idx_parts_dev, int n_parts, int nq, int k, float *scores_dev,
+                      int64_t *idx_dev, int device, void *stream);
+
+/* Test/bench hook: which kernels fr_gallery_topk uses. AUTO = exact SIMT path below 2048 rows (latency-bound sizes),
+ * fused tensor-core scan + exact re-score otherwise. Both return exact fp32 scores in the same summation order. */
+#define FR_PATH_AUTO 0
+#define FR_PATH_EXACT 1
+#define FR_PATH_TENSOR 2
+int fr_gallery_set_path(FrGallery *g, int path);
+
+/* roofline bookkeeping for bench.py: algorithmic bytes/flops of the dominant kernel of the last topk call */
+typedef struct FrSearchStats {
+    int64_t scan_bytes; /* bytes of the resident scan copy streamed (n_rows * dim * 2) */
+    int64_t flops;      /* 2 * nq_padded * n_rows * dim */
+    int launches;       /* kernels launched by the last call */
+    int ctas;           /* CTAs of the fused kernel */
+} FrSearchStats;
+int fr_gallery_last_stats(const FrGallery *g, FrSearchStats *out);
+/* bench.py's live roofline measurement: when enabled, every launch of the fused scan kernel is bracketed by CUDA events on
+ * the stream it is launched on; fr_gallery_scan_time waits for them, returns their summed duration and count, and resets. */
+int fr_gallery_set_timing(FrGallery *g, int enable);
+int fr_gallery_scan_time(FrGallery *g, double *total_ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FR_B200_H */

@@ -1,0 +1,207 @@
+"""GPU parity of the cosine-similarity search through the C ABI against oracle/search_oracle.py.
+Tolerances: row indices bit-exact (top-1 identity exact, BASELINE.json north_star); scores |d| <= 1e-5 (north_star allows 1e-3)."""
+import numpy as np
+import pytest
+
+import frb200
+from oracle import search_oracle as so
+
+pytestmark = pytest.mark.gpu
+SCORE_TOL = 1e-5
+
+
+def _check_topk(g_scores, g_idx, sim, k, row_offset=0):
+    o_scores, o_idx = so.topk(sim, k, row_offset)
+    assert g_idx.shape == o_idx.shape
+    assert np.all(np.abs(np.where(np.isinf(o_scores), 0, g_scores - o_scores)) <= SCORE_TOL)
+    assert np.array_equal(np.isinf(g_scores), np.isinf(o_scores))
+    bad = np.argwhere(g_idx != o_idx)
+    for qi, j in bad:  # a differing index is only acceptable for an fp32-rounding-level tie between distinct rows
+        gi = g_idx[qi, j] - row_offset
+        assert gi >= 0 and abs(sim[qi, gi] - o_scores[qi, j]) <= 2e-6, (qi, j, g_idx[qi, j], o_idx[qi, j])
+    # top-1 must be exact on these inputs (planted or well separated)
+    return len(bad)
+
+
+def test_synthetic_rows_bit_exact_with_oracle():
+    for n, off, seed in ((1000, 0, 19), (300, 9_999_900, 19), (257, 12345678000, 7)):
+        g = frb200.Gallery.synthetic(n, seed=seed, row_offset=off)
+        got = g.read_rows(0, n)
+        want = so.synth_rows(np.arange(off, off + n), seed)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        g.close()
+
+
+@pytest.mark.parametrize("path", [frb200.FR_PATH_EXACT, frb200.FR_PATH_TENSOR, frb200.FR_PATH_AUTO])
+def test_config1_one_query_1000_rows_top1_exact(path):
+    # BASELINE.json configs[0] / SURVEY §8d config 1
+    rng = np.random.default_rng(1234)
+    G = so.l2_normalise(rng.standard_normal((1000, 512)))
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(path)
+    rq = np.random.default_rng(1235)
+    for r in (0, 999, 517, 255, 256):
+        q = so.l2_normalise(G[r : r + 1] + 0.5 * rq.standard_normal((1, 512)).astype(np.float32) / np.sqrt(512) * 1.0)
+        s, i = g.topk(q, 1)
+        oi, ov = so.get_outputs(so.sims(G, q))
+        assert i[0, 0] == oi[0] == r
+        assert abs(s[0, 0] - ov[0]) <= SCORE_TOL
+    g.close()
+
+
+@pytest.mark.parametrize("path", [frb200.FR_PATH_EXACT, frb200.FR_PATH_TENSOR])
+def test_adversarial_ties(path):
+    rng = np.random.default_rng(5)
+    G = so.l2_normalise(rng.standard_normal((3000, 512)))
+    # exact duplicate rows -> lowest index wins (std::max_element, src/arcface.cpp:210)
+    G[2900] = G[40]
+    G[1500] = G[40]
+    G[41] = G[2999]
+    q = np.stack([G[40], G[2999]])
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(path)
+    s, i = g.topk(q, 4)
+    assert i[0, :3].tolist() == [40, 1500, 2900] and i[1, :2].tolist() == [41, 2999]
+    assert np.all(np.abs(s[:, 0] - 1.0) < 1e-5)
+    g.close()
+    # all rows identical -> every score equal -> indices 0..k-1
+    G2 = np.repeat(G[:1], 777, axis=0)
+    g = frb200.Gallery.from_rows(G2)
+    g.set_path(path)
+    s, i = g.topk(G[:1], 8)
+    assert i[0].tolist() == list(range(8))
+    # query orthogonal to everything / zero query: all scores 0 -> first row
+    s, i = g.topk(np.zeros((1, 512), np.float32), 1)
+    assert i[0, 0] == 0 and s[0, 0] == 0.0
+    g.close()
+
+
+@pytest.mark.parametrize("n,nq", [(1, 1), (7, 3), (1000, 4), (5000, 33), (70000, 17)])
+def test_dense_sims_matches_matmul_calculate_contract(n, nq):
+    rng = np.random.default_rng(n + nq)
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    q = so.l2_normalise(rng.standard_normal((nq, 512)))
+    g = frb200.Gallery.from_rows(G)
+    out = g.sims(q)
+    ref = (q.astype(np.float64) @ G.astype(np.float64).T)
+    assert out.shape == (nq, n)
+    assert np.abs(out - ref).max() <= 2e-6
+    assert np.abs(out - so.sims(G, q)).max() <= SCORE_TOL
+    g.close()
+
+
+@pytest.mark.parametrize("n", [256, 1000, 4096 + 37, 33333, 150_001])
+@pytest.mark.parametrize("nq,k", [(1, 1), (5, 4), (128, 1), (129, 8), (256, 1), (300, 2)])
+def test_tensor_path_topk_matches_oracle(n, nq, k):
+    rng = np.random.default_rng(n * 7 + nq)
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    planted = rng.integers(0, n, nq)
+    q = so.planted_queries(G[planted], noise=0.75, seed=n + nq)
+    g = frb200.Gallery.from_rows(G, row_offset=1000)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    s, i = g.topk(q, k)
+    sim = so.sims(G, q)
+    _check_topk(s, i, sim, k, row_offset=1000)
+    assert np.array_equal(i[:, 0], planted + 1000)
+    st = g.last_stats()
+    assert st.launches >= 2 and st.scan_bytes == n * 512 * 2 * ((nq + 255) // 256)
+    g.close()
+
+
+def test_tensor_and_exact_paths_agree_bitwise_on_scores():
+    rng = np.random.default_rng(77)
+    G = so.l2_normalise(rng.standard_normal((20000, 512)))
+    q = so.l2_normalise(rng.standard_normal((64, 512)))
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(frb200.FR_PATH_EXACT)
+    s1, i1 = g.topk(q, 4)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    s2, i2 = g.topk(q, 4)
+    assert np.array_equal(i1, i2)
+    assert np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
+    dense = g.sims(q)
+    assert np.array_equal(dense[np.arange(64), i1[:, 0]].view(np.uint32), s1[:, 0].view(np.uint32))
+    g.close()
+
+
+def test_edge_cases_and_errors():
+    G = so.l2_normalise(np.random.default_rng(1).standard_normal((5, 512)))
+    g = frb200.Gallery.from_rows(G)
+    s, i = g.topk(G[:2], 8)  # fewer rows than k -> (-inf, -1) padding
+    assert i[0, :1].tolist() == [0] and i[1, 0] == 1 and np.all(i[:, 5:] == -1) and np.all(np.isinf(s[:, 5:]))
+    g.set_path(frb200.FR_PATH_TENSOR)
+    s, i = g.topk(G[:2], 8)
+    assert i[0, 0] == 0 and i[1, 0] == 1 and np.all(i[:, 5:] == -1)
+    with pytest.raises(frb200.FrError) as e:
+        g.topk(G[:1], 9)
+    assert e.value.code == frb200.FR_EINVAL
+    with pytest.raises(frb200.FrError) as e:
+        g.topk(np.zeros((0, 512), np.float32), 1)
+    assert e.value.code == frb200.FR_EINVAL
+    g.close()
+    empty = frb200.Gallery.from_rows(np.zeros((0, 512), np.float32))
+    with pytest.raises(frb200.FrError) as e:  # featureMatching throws on an empty database, src/arcface.cpp:195-199
+        empty.topk(G[:1], 1)
+    assert e.value.code == frb200.FR_ESTATE and "No faces in database" in e.value.msg
+    empty.close()
+    with pytest.raises(frb200.FrError) as e:
+        frb200.Gallery.from_rows(np.zeros((4, 128), np.float32))
+    assert e.value.code == frb200.FR_EINVAL
+
+
+def test_sharded_search_merge_equals_single_gallery():
+    import torch
+
+    rng = np.random.default_rng(9)
+    n, nq, k = 50_000, 200, 4
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    G[41000] = G[123]
+    planted = rng.integers(0, n, nq)
+    planted[0] = 123
+    q = so.planted_queries(G[planted], noise=0.6, seed=4)
+    q[0] = G[123]
+    full = frb200.Gallery.from_rows(G)
+    full.set_path(frb200.FR_PATH_TENSOR)
+    fs, fi = full.topk(q, k)
+    for shards in (2, 3, 8):
+        bounds = np.linspace(0, n, shards + 1).astype(int)
+        ps = torch.empty((shards, nq, k), dtype=torch.float32, device="cuda")
+        pi = torch.empty((shards, nq, k), dtype=torch.int64, device="cuda")
+        qd = torch.from_numpy(q).cuda()
+        gs = []
+        for r, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+            sh = frb200.Gallery.from_rows(G[a:b], row_offset=int(a))
+            sh.set_path(frb200.FR_PATH_TENSOR)
+            sh.topk_dev(qd, k, ps[r], pi[r], stream=torch.cuda.current_stream().cuda_stream)
+            gs.append(sh)
+        ms = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        mi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        frb200.topk_merge_dev(ps, pi, shards, nq, k, ms, mi, 0, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(mi.cpu().numpy(), fi)
+        assert np.array_equal(ms.cpu().numpy().view(np.uint32), fs.view(np.uint32))
+        for sh in gs:
+            sh.close()
+    assert fi[0, 0] == 123 and fi[0, 1] == 41000
+    full.close()
+
+
+def test_large_synthetic_gallery_planted_top1():
+    # size-independent property at a size the host cannot hold as a matrix: planted rows must come back as top-1 with the
+    # score the host computes from the regenerated row
+    n, seed = 3_000_000, 19
+    g = frb200.Gallery.synthetic(n, seed=seed)
+    rng = np.random.default_rng(23)
+    planted = np.sort(rng.integers(0, n, 256))
+    planted[:3] = [0, n - 1, n - 257]
+    rows = so.synth_rows(planted, seed)
+    q = so.planted_queries(rows, noise=0.75, seed=29)
+    s, i = g.topk(q, 2)
+    assert np.array_equal(i[:, 0], planted)
+    want = np.einsum("ij,ij->i", q.astype(np.float64), rows.astype(np.float64))
+    assert np.abs(s[:, 0] - want).max() <= SCORE_TOL
+    # runner-up is an impostor: far below, and its reported score equals the host dot with the regenerated row
+    r2 = so.synth_rows(i[:, 1], seed)
+    want2 = np.einsum("ij,ij->i", q.astype(np.float64), r2.astype(np.float64))
+    assert np.abs(s[:, 1] - want2).max() <= SCORE_TOL and np.all(s[:, 1] < 0.4)
+    g.close()
