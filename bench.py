@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--queries", type=int, default=256)
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ramp-s", type=float, default=1.0, help="untimed busy period before the timed region (clock ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -238,8 +239,11 @@ def main():
     out_i = torch.empty((Q, K), dtype=torch.int64, device=dev)
     res_s_pin = torch.empty((Q, K), dtype=torch.float32).pin_memory()
     res_i_pin = torch.empty((Q, K), dtype=torch.int64).pin_memory()
-    stream = torch.cuda.current_stream()
+    # a non-default stream: the C ABI treats a NULL stream as "the handle's own stream", and NCCL + events must share it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sraw = stream.cuda_stream
+    assert sraw != 0
 
     def search_step():
         """device-resident hot path: fused scan + re-score on this shard, then the cross-GPU exchange + merge"""
@@ -275,6 +279,12 @@ def main():
     for _ in range(args.warmup):
         search_step()
     torch.cuda.synchronize()
+    # untimed clock ramp: keep the GPU busy for ~args.ramp_s so that the timed region sees steady-state clocks
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < args.ramp_s:
+        for _ in range(8):
+            search_step()
+        torch.cuda.synchronize()
     got_i = out_i.cpu().numpy()[:, 0]
     got_s = out_s.cpu().numpy()[:, 0]
     parity_ok = bool(np.array_equal(got_i, planted) and np.abs(got_s - want_score).max() <= 1e-5)

@@ -2,8 +2,9 @@
 // Replaces MatMul (/root/reference src/matmul.{h,cpp}) and the host argmax ArcFaceIR50::getOutputs (src/arcface.cpp:203-217).
 //
 // Resident layout per gallery (one shard of a row-partitioned gallery):
-//   rows_f32  n x 512 f32 row-major   master copy: dense sims and the exact re-score read it            (2 KiB / row)
-//   rows_f16  n x 512 f16 row-major   scan copy streamed by the fused tensor-core kernel through TMA    (1 KiB / row)
+//   rows_f32  n x 512 f32 row-major   master copy: dense sims, exact re-score and exact scan read it     (2 KiB / row)
+//   rows_f16  n x 512 f16 row-major   scan copy streamed by the fused tensor-core kernel through TMA     (1 KiB / row)
+//   gmax      largest row norm (device scalar): scales the provable error margin of the fp16 scan
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -22,12 +23,16 @@ struct FrGallery {
     int64_t row_offset = 0;
     float* rows_f32 = nullptr;
     __half* rows_f16 = nullptr;
+    float* gmax = nullptr;
     CUtensorMap tmap{};
     cudaStream_t stream = nullptr;
     // scratch, sized for one chunk of 256 queries
     float* q_dev = nullptr;          // 256 x 512
-    float* cand_s = nullptr;         // [units][256][kKC]
+    float* cand_s = nullptr;         // [lists <= 296][256][16]
     int* cand_i = nullptr;
+    int* flags = nullptr;            // 256
+    float* part_s = nullptr;         // exact scan partials [256][slices][8]
+    long long* part_i = nullptr;
     float* res_s = nullptr;          // 256 x FR_TOPK_MAX
     long long* res_i = nullptr;
     float* sims_ws = nullptr;        // dense-path workspace
@@ -43,19 +48,27 @@ struct FrGallery {
 namespace {
 
 constexpr int kChunkQ = 256;
-constexpr int64_t kExactMaxRows = 2048;  // FR_PATH_AUTO: below this the exact SIMT path has the lower latency
+constexpr int kMaxLists = 2 * 148;
+constexpr int64_t kExactMaxRows = 2048;  // FR_PATH_AUTO: below this the exact scan has the lower latency
 
 void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     FRB_CUDA(cudaMalloc(&g->q_dev, sizeof(float) * kChunkQ * kDim));
-    FRB_CUDA(cudaMalloc(&g->cand_s, sizeof(float) * 148 * kChunkQ * kKC));
-    FRB_CUDA(cudaMalloc(&g->cand_i, sizeof(int) * 148 * kChunkQ * kKC));
+    FRB_CUDA(cudaMalloc(&g->cand_s, sizeof(float) * kMaxLists * kChunkQ * 16));
+    FRB_CUDA(cudaMalloc(&g->cand_i, sizeof(int) * kMaxLists * kChunkQ * 16));
+    FRB_CUDA(cudaMalloc(&g->flags, sizeof(int) * kChunkQ));
+    FRB_CUDA(cudaMalloc(&g->part_s, sizeof(float) * kChunkQ * kScanSlicesMax * kTopkMax));
+    FRB_CUDA(cudaMalloc(&g->part_i, sizeof(long long) * kChunkQ * kScanSlicesMax * kTopkMax));
     FRB_CUDA(cudaMalloc(&g->res_s, sizeof(float) * kChunkQ * FR_TOPK_MAX));
     FRB_CUDA(cudaMalloc(&g->res_i, sizeof(long long) * kChunkQ * FR_TOPK_MAX));
+    FRB_CUDA(cudaMalloc(&g->gmax, sizeof(float)));
+    FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
     static bool attr_done[16] = {};
     if (!attr_done[g->device & 15]) {
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2>::kSmemBytes));
         attr_done[g->device & 15] = true;
     }
 }
@@ -82,17 +95,17 @@ FrGallery* new_gallery(int64_t n, int dim, int device, int64_t row_offset) {
     return g;
 }
 
-void convert_scan_copy(FrGallery* g) {
+// fp16 scan copy (unless the generator already wrote it) + largest row norm
+void finish_rows(FrGallery* g, bool write_f16) {
     if (g->n == 0) return;
-    const long long n4 = g->n * kDim / 4;
-    const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, g->sms * 16LL));
-    f32_to_f16_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f16, n4);
+    const int blocks = static_cast<int>(std::min<int64_t>((g->n + 7) / 8, g->sms * 16LL));
+    make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, write_f16 ? g->rows_f16 : nullptr, g->n, g->gmax);
     count_launch();
     FRB_CUDA(cudaGetLastError());
     FRB_CUDA(cudaStreamSynchronize(g->stream));
 }
 
-template <int CG>
+template <int CG, int KSEL>
 void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tiles, cudaStream_t st) {
     std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
     if (g->timing) {
@@ -117,8 +130,8 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG>, g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles, g->cand_s,
-                                g->cand_i));
+    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL>, g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles,
+                                static_cast<const float*>(g->gmax), g->cand_s, g->cand_i));
     count_launch();
     if (ev) FRB_CUDA(cudaEventRecord(ev->second, st));
 }
@@ -141,17 +154,23 @@ void launch_sims(FrGallery* g, const float* q_dev, int nq, float* out_dev, cudaS
     FRB_CUDA(cudaGetLastError());
 }
 
+// exact scan of the queries flagged in `flags` (nullptr = all): two launches, both return at once for unflagged queries
+void launch_exact(FrGallery* g, const float* q_dev, int nq, int k, const int* flags, float* scores_dev, long long* idx_dev,
+                  cudaStream_t st) {
+    const int slices = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->n + 7) / 8, std::min(kScanSlicesMax, 2 * g->sms))));
+    exact_scan_kernel<<<dim3(slices, nq), kScanThreads, 0, st>>>(g->rows_f32, g->n, q_dev, flags, g->part_s, g->part_i);
+    exact_merge_kernel<<<nq, kSelThreads, 0, st>>>(g->part_s, g->part_i, slices, flags, k, g->row_offset, scores_dev, idx_dev);
+    count_launch(2);
+    FRB_CUDA(cudaGetLastError());
+}
+
 // one chunk (nq <= 256) of queries already on the device; results to scores_dev / idx_dev (device, nq x k)
 void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_dev, long long* idx_dev, cudaStream_t st) {
     const bool exact = g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows);
     g->stats = FrSearchStats{};
     if (exact) {
-        ensure_sims_ws(g, static_cast<size_t>(nq) * g->n);
-        launch_sims(g, q_dev, nq, g->sims_ws, st);
-        topk_dense_kernel<<<nq, kSelThreads, 0, st>>>(g->sims_ws, g->n, k, g->row_offset, scores_dev, idx_dev);
-        count_launch();
-        FRB_CUDA(cudaGetLastError());
-        g->stats.scan_bytes = g->n * kDim * 4;
+        launch_exact(g, q_dev, nq, k, nullptr, scores_dev, idx_dev, st);
+        g->stats.scan_bytes = g->n * kDim * 4 * nq;
         g->stats.flops = 2LL * nq * g->n * kDim;
         g->stats.launches = 2;
         g->stats.ctas = 0;
@@ -159,21 +178,26 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     }
     const int tiles = static_cast<int>((g->n + kTileRows - 1) / kTileRows);
     const int cg = nq > kQRows ? 2 : 1;
+    const int kc = k == 1 ? 8 : 16;
     int units;
     if (cg == 2) {
         units = std::min(g->sms / 2, tiles);
-        launch_coarse<2>(g, q_dev, nq, units, tiles, st);
+        if (k == 1) launch_coarse<2, 1>(g, q_dev, nq, units, tiles, st);
+        else launch_coarse<2, 8>(g, q_dev, nq, units, tiles, st);
     } else {
         units = std::min(g->sms, tiles);
-        launch_coarse<1>(g, q_dev, nq, units, tiles, st);
+        if (k == 1) launch_coarse<1, 1>(g, q_dev, nq, units, tiles, st);
+        else launch_coarse<1, 8>(g, q_dev, nq, units, tiles, st);
     }
-    topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units, cg * kQRows, q_dev, g->rows_f32, k, g->row_offset,
-                                                   scores_dev, idx_dev);
+    topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->gmax, k,
+                                                   g->row_offset, scores_dev, idx_dev, g->flags);
     count_launch();
     FRB_CUDA(cudaGetLastError());
+    // queries whose candidate set may be incomplete (flagged by the re-rank) are recomputed exactly; no-op otherwise
+    launch_exact(g, q_dev, nq, k, g->flags, scores_dev, idx_dev, st);
     g->stats.scan_bytes = g->n * kDim * 2;
     g->stats.flops = 2LL * (cg * kQRows) * g->n * kDim;
-    g->stats.launches = 2;
+    g->stats.launches = 4;
     g->stats.ctas = units * cg;
 }
 
@@ -181,6 +205,13 @@ void check_query_args(const FrGallery* g, const void* q, int nq) {
     if (!g) throw ArgError{"null gallery"};
     if (!q || nq <= 0) throw ArgError{"no queries"};
     if (g->n == 0) throw StateError{"Feature matching: No faces in database or no faces found"};  // src/arcface.cpp:198
+}
+
+void add_stats(FrSearchStats& total, const FrSearchStats& s) {
+    total.scan_bytes += s.scan_bytes;
+    total.flops += s.flops;
+    total.launches += s.launches;
+    total.ctas = s.ctas;
 }
 
 }  // namespace
@@ -195,7 +226,7 @@ int fr_gallery_create(const float* rows, int64_t n, int dim, int device, int64_t
         try {
             if (n > 0) {
                 FRB_CUDA(cudaMemcpyAsync(g->rows_f32, rows, sizeof(float) * n * kDim, cudaMemcpyHostToDevice, g->stream));
-                convert_scan_copy(g);
+                finish_rows(g, true);
             }
         } catch (...) {
             fr_gallery_destroy(g);
@@ -213,7 +244,7 @@ int fr_gallery_create_dev(const float* rows_dev, int64_t n, int dim, int device,
         try {
             if (n > 0) {
                 FRB_CUDA(cudaMemcpyAsync(g->rows_f32, rows_dev, sizeof(float) * n * kDim, cudaMemcpyDeviceToDevice, g->stream));
-                convert_scan_copy(g);
+                finish_rows(g, true);
             }
         } catch (...) {
             fr_gallery_destroy(g);
@@ -233,7 +264,7 @@ int fr_gallery_create_synthetic(int64_t n, int dim, uint64_t seed, int device, i
                 synth_rows_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f16, n, seed, row_offset);
                 count_launch();
                 FRB_CUDA(cudaGetLastError());
-                FRB_CUDA(cudaStreamSynchronize(g->stream));
+                finish_rows(g, false);
             }
         } catch (...) {
             fr_gallery_destroy(g);
@@ -251,9 +282,13 @@ void fr_gallery_destroy(FrGallery* g) {
     if (g->stream) cudaStreamSynchronize(g->stream);
     cudaFree(g->rows_f32);
     cudaFree(g->rows_f16);
+    cudaFree(g->gmax);
     cudaFree(g->q_dev);
     cudaFree(g->cand_s);
     cudaFree(g->cand_i);
+    cudaFree(g->flags);
+    cudaFree(g->part_s);
+    cudaFree(g->part_i);
     cudaFree(g->res_s);
     cudaFree(g->res_i);
     cudaFree(g->sims_ws);
@@ -304,24 +339,15 @@ int fr_gallery_sims(FrGallery* g, const float* q, int nq, float* out) {
         DeviceGuard dg(g->device);
         // chunk the queries so that the device workspace stays bounded (the reference allocates n x m at once, src/matmul.cpp:41)
         const int64_t max_ws_floats = int64_t(1) << 28;  // 1 GiB
-        const int step = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nq, max_ws_floats / g->n)));
+        const int step = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min(nq, kChunkQ), max_ws_floats / g->n)));
         for (int q0 = 0; q0 < nq; q0 += step) {
             const int m = std::min(step, nq - q0);
-            float* qd = nullptr;
-            if (m <= kChunkQ) qd = g->q_dev;
-            else FRB_CUDA(cudaMalloc(&qd, sizeof(float) * m * kDim));
-            try {
-                ensure_sims_ws(g, static_cast<size_t>(m) * g->n);
-                FRB_CUDA(cudaMemcpyAsync(qd, q + static_cast<size_t>(q0) * kDim, sizeof(float) * m * kDim, cudaMemcpyHostToDevice, g->stream));
-                launch_sims(g, qd, m, g->sims_ws, g->stream);
-                FRB_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(q0) * g->n, g->sims_ws, sizeof(float) * m * g->n, cudaMemcpyDeviceToHost,
-                                         g->stream));
-                FRB_CUDA(cudaStreamSynchronize(g->stream));
-            } catch (...) {
-                if (qd != g->q_dev) cudaFree(qd);
-                throw;
-            }
-            if (qd != g->q_dev) cudaFree(qd);
+            ensure_sims_ws(g, static_cast<size_t>(m) * g->n);
+            FRB_CUDA(cudaMemcpyAsync(g->q_dev, q + static_cast<size_t>(q0) * kDim, sizeof(float) * m * kDim, cudaMemcpyHostToDevice, g->stream));
+            launch_sims(g, g->q_dev, m, g->sims_ws, g->stream);
+            FRB_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(q0) * g->n, g->sims_ws, sizeof(float) * m * g->n, cudaMemcpyDeviceToHost,
+                                     g->stream));
+            FRB_CUDA(cudaStreamSynchronize(g->stream));
         }
     });
 }
@@ -338,10 +364,7 @@ int fr_gallery_topk_dev(FrGallery* g, const float* q_dev, int nq, int k, float* 
             const int m = std::min(kChunkQ, nq - q0);
             topk_chunk(g, q_dev + static_cast<size_t>(q0) * kDim, m, k, scores_dev + static_cast<size_t>(q0) * k,
                        reinterpret_cast<long long*>(idx_dev) + static_cast<size_t>(q0) * k, st);
-            total.scan_bytes += g->stats.scan_bytes;
-            total.flops += g->stats.flops;
-            total.launches += g->stats.launches;
-            total.ctas = g->stats.ctas;
+            add_stats(total, g->stats);
         }
         g->stats = total;
     });
@@ -361,10 +384,7 @@ int fr_gallery_topk(FrGallery* g, const float* q, int nq, int k, float* scores, 
             FRB_CUDA(cudaMemcpyAsync(scores + static_cast<size_t>(q0) * k, g->res_s, sizeof(float) * m * k, cudaMemcpyDeviceToHost, g->stream));
             FRB_CUDA(cudaMemcpyAsync(idx + static_cast<size_t>(q0) * k, g->res_i, sizeof(long long) * m * k, cudaMemcpyDeviceToHost, g->stream));
             FRB_CUDA(cudaStreamSynchronize(g->stream));
-            total.scan_bytes += g->stats.scan_bytes;
-            total.flops += g->stats.flops;
-            total.launches += g->stats.launches;
-            total.ctas = g->stats.ctas;
+            add_stats(total, g->stats);
         }
         g->stats = total;
     });

@@ -1,11 +1,15 @@
 // Device code of the cosine-similarity search:
-//   cosine_topk_coarse<CG>  fused  Q x 512 · (N x 512)^T  on tcgen05 tensor cores (fp16 in, fp32 accumulate in TMEM)
-//                           + running top-KC per query in registers; the similarity matrix is never written.
-//   topk_rerank_kernel      merges the per-CTA candidates, re-scores the KC survivors per query in exact fp32
-//                           from the fp32 master rows and orders them by (score desc, row asc).
-//   sims_kernel             exact fp32 dense similarities (MatMul::calculate, /root/reference src/matmul.cpp:36-77).
-//   topk_dense_kernel       top-k of a dense similarity matrix (ArcFaceIR50::getOutputs, src/arcface.cpp:203-217).
-//   topk_merge_kernel       merge of per-shard (score, idx) lists after the cross-GPU all-gather.
+//   cosine_topk_coarse<CG,KSEL>  fused  Q x 512 · (N x 512)^T  on tcgen05 tensor cores (fp16 in, fp32 accumulate in TMEM)
+//                                + running candidate list per query in registers; the similarity matrix is never written.
+//   topk_rerank_kernel           merges the per-CTA candidate lists, keeps every row whose coarse score is within the
+//                                provable fp16 error margin of the k-th best, re-scores those in exact fp32 from the fp32 master
+//                                rows and orders them by (score desc, row asc). Queries whose candidate set could be
+//                                incomplete are flagged and recomputed by the exact scan.
+//   exact_scan_kernel / exact_merge_kernel   exact fp32 scan (small galleries, flagged queries, FR_PATH_EXACT).
+//   sims_kernel                  exact fp32 dense similarities (MatMul::calculate, /root/reference src/matmul.cpp:36-77).
+//   topk_merge_kernel            merge of per-shard (score, idx) lists after the cross-GPU all-gather.
+// Ordering everywhere: (score descending, row index ascending) — for k = 1 this is std::max_element's "first maximum"
+// (ArcFaceIR50::getOutputs, /root/reference src/arcface.cpp:210).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -21,12 +25,17 @@ constexpr int kDim = 512;          // rec_outputDim, app/config.json:16
 constexpr int kKBlocks = 8;        // 512 / 64 : one 128-byte swizzle span of fp16 per k-block
 constexpr int kTileRows = 256;     // gallery rows per accumulator tile (UMMA N)
 constexpr int kQRows = 128;        // queries per CTA (UMMA M per CTA = TMEM lanes)
-constexpr int kKC = 8;             // coarse candidates kept per query per CTA (and re-scored per query)
+constexpr int kTopkMax = 8;        // FR_TOPK_MAX
 constexpr int kQTileBytes = kQRows * 128;            // one k-block of the query operand: 16 KiB
 constexpr int kQBytes = kKBlocks * kQTileBytes;      // 128 KiB
 constexpr int kHalfTileBytes = 128 * 128;            // 128 gallery rows x 64 fp16 : one TMA box, 16 KiB
-constexpr int kSearchThreads = 256;                  // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-7: epilogue
+constexpr int kEpiWarps = 8;                         // 2 column halves x 4 TMEM lane quarters
+constexpr int kSearchThreads = 128 + kEpiWarps * 32; // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: epilogue
 constexpr int kRingBytes = 96 * 1024;                // gallery stage ring
+constexpr int kLdCols = 16;                          // accumulator columns per tcgen05.ld
+// |coarse - exact| <= kCoarseEps * |q| * |row|: fp16 round-to-nearest of both operands (2 * 2^-11) plus the tensor core's fp32
+// accumulation, bounded through Cauchy-Schwarz. Candidates within 2 eps of the k-th best coarse score are re-scored exactly.
+constexpr float kCoarseEps = 1.25e-3f;
 
 template <int CG>
 struct CoarseCfg {
@@ -34,17 +43,23 @@ struct CoarseCfg {
     static constexpr int kStages = kRingBytes / kStageBytes;     // 3 (single CTA) or 6 (CTA pair)
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kQBytes + kRingBytes + 256 /*barriers*/;
 };
+// candidate list length per epilogue thread: KSEL = 1 (top-1 search) keeps 8, KSEL = 8 (k <= 8) keeps 16
+template <int KSEL>
+struct ListCfg {
+    static constexpr int kKC = KSEL == 1 ? 8 : 16;
+};
 
-__device__ __forceinline__ bool better(float sa, int64_t ia, float sb, int64_t ib) {
+__device__ __forceinline__ bool better(float sa, long long ia, float sb, long long ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
 
-// insert (v, id) into a descending list of kKC entries held in registers; ties keep the earlier entry first
-__device__ __forceinline__ void topk_insert(float (&s)[kKC], int (&ix)[kKC], float v, int id) {
-    s[kKC - 1] = v;
-    ix[kKC - 1] = id;
+// insert (v, id) into a descending list held in registers; ties keep the earlier (lower row) entry first
+template <int KC>
+__device__ __forceinline__ void topk_insert(float (&s)[KC], int (&ix)[KC], float v, int id) {
+    s[KC - 1] = v;
+    ix[KC - 1] = id;
 #pragma unroll
-    for (int t = kKC - 1; t > 0; --t) {
+    for (int t = KC - 1; t > 0; --t) {
         if (s[t] > s[t - 1]) {
             float ts = s[t];
             s[t] = s[t - 1];
@@ -59,13 +74,17 @@ __device__ __forceinline__ void topk_insert(float (&s)[kKC], int (&ix)[kKC], flo
 // ----------------------------------------------------------------------------------------------------------
 // Fused coarse search. Grid: CG * units CTAs (cluster of CG). Unit u scans gallery tiles u, u+units, ...
 // q: nq x 512 f32 (device). CTA rank r of a pair owns queries [128 r, 128 r + 128).
-// cand_s / cand_i: [units][CG*128][kKC]  (score, local row) per unit and query, descending, (-inf,-1) padded.
+// Epilogue warp e (0..7): TMEM lane quarter e & 3, accumulator column half e >> 2.
+// cand_s / cand_i: [units * 2 lists][CG*128 queries][KC]  (coarse score, local row), descending, (-inf,-1) padded.
+// A thread keeps a row iff its coarse score exceeds max(KC-th best, KSEL-th best - 2 eps |q| gmax): every row that can
+// still reach the exact top-KSEL survives unless more than KC such rows exist (detected in topk_rerank_kernel).
 // ----------------------------------------------------------------------------------------------------------
-template <int CG>
+template <int CG, int KSEL>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ q, int nq, long long n_rows, int num_tiles,
-                   float* __restrict__ cand_s, int* __restrict__ cand_i) {
+                   const float* __restrict__ gmax_ptr, float* __restrict__ cand_s, int* __restrict__ cand_i) {
     using Cfg = CoarseCfg<CG>;
+    constexpr int KC = ListCfg<KSEL>::kKC;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -91,7 +110,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
-            mbar_init(&tempty_bar[b], CG * 4);  // one arrive per epilogue warp of every CTA of the unit
+            mbar_init(&tempty_bar[b], CG * kEpiWarps);  // one arrive per epilogue warp of every CTA of the unit
         }
         fence_mbar_init();
     }
@@ -191,46 +210,84 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: running top-KC per query, in registers =====================
-        float best_s[kKC];
-        int best_i[kKC];
+        // ===================== epilogue: running candidate list per query, in registers =====================
+        const int ew = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
+        const int half = (warp - 4) >> 2;  // accumulator column half
+        const int qrow = static_cast<int>(cta_rank) * kQRows + ew * 32 + lane;
+        // margin = 2 eps |q| gmax, |q| from the fp32 query (read while the first tile is still in the tensor pipe)
+        float margin = 0.f;
+        if (qrow < nq) {
+            const float4* qp = reinterpret_cast<const float4*>(q + static_cast<size_t>(qrow) * kDim);
+            float ss = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < kDim / 4; ++i) {
+                const float4 v = __ldg(qp + i);
+                ss = fmaf(v.x, v.x, ss);
+                ss = fmaf(v.y, v.y, ss);
+                ss = fmaf(v.z, v.z, ss);
+                ss = fmaf(v.w, v.w, ss);
+            }
+            margin = 2.f * kCoarseEps * sqrtf(ss) * __ldg(gmax_ptr);
+        }
+        float best_s[KC];
+        int best_i[KC];
 #pragma unroll
-        for (int j = 0; j < kKC; ++j) {
+        for (int j = 0; j < KC; ++j) {
             best_s[j] = -INFINITY;
             best_i[j] = -1;
         }
-        const int ew = warp & 3;  // TMEM lane quarter this warp may access
+        float thr = -INFINITY;
         const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
+        constexpr int kChunks = (kTileRows / 2) / kLdCols;  // 8 loads of 16 columns per tile half
+
+        auto consume = [&](const uint32_t (&raw)[kLdCols], int col0, int valid, int row_base) {
+            float v[kLdCols];
+#pragma unroll
+            for (int j = 0; j < kLdCols; ++j) v[j] = __uint_as_float(raw[j]);
+            if (valid < kTileRows) {  // last, partial tile: rows beyond the gallery are TMA zero fill
+#pragma unroll
+                for (int j = 0; j < kLdCols; ++j)
+                    if (col0 + j >= valid) v[j] = -INFINITY;
+            }
+            float m[kLdCols / 2];
+#pragma unroll
+            for (int j = 0; j < kLdCols / 2; ++j) m[j] = fmaxf(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+            for (int w = kLdCols / 4; w > 0; w >>= 1)
+#pragma unroll
+                for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
+            if (m[0] > thr) {
+#pragma unroll
+                for (int j = 0; j < kLdCols; ++j) {
+                    if (v[j] > thr) {
+                        topk_insert<KC>(best_s, best_i, v[j], row_base + col0 + j);
+                        thr = fmaxf(best_s[KC - 1], best_s[KSEL - 1] - margin);
+                    }
+                }
+            }
+        };
+
         int it = 0;
         for (int t = unit; t < num_tiles; t += num_units, ++it) {
             const int buf = it & 1;
             mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * kTileRows;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * kTileRows + half * (kTileRows / 2);
             const long long row0 = static_cast<long long>(t) * kTileRows;
             const int valid = (n_rows - row0 >= kTileRows) ? kTileRows : static_cast<int>(n_rows - row0);
+            const int row_base = static_cast<int>(row0);
+            const int cbase = half * (kTileRows / 2);
+            // software pipeline: the load of chunk c+1 is in flight while chunk c is consumed
+            uint32_t ra[kLdCols], rb[kLdCols];
+            tmem_ld_32x32b_x16(taddr, ra);
 #pragma unroll 1
-            for (int c = 0; c < kTileRows / 32; ++c) {
-                uint32_t raw[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, raw);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                if (valid < kTileRows) {  // last, partial tile: rows beyond the gallery are TMA zero fill
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c * 32 + j >= valid) v[j] = -INFINITY;
-                }
-                float m = v[0];
-#pragma unroll
-                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-                if (m > best_s[kKC - 1]) {
-                    const int base = static_cast<int>(row0) + c * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (v[j] > best_s[kKC - 1]) topk_insert(best_s, best_i, v[j], base + j);
-                }
+            for (int c = 0; c < kChunks; c += 2) {
+                tmem_ld_wait_x16(ra);
+                tmem_ld_32x32b_x16(taddr + (c + 1) * kLdCols, rb);
+                consume(ra, cbase + c * kLdCols, valid, row_base);
+                tmem_ld_wait_x16(rb);
+                if (c + 2 < kChunks) tmem_ld_32x32b_x16(taddr + (c + 2) * kLdCols, ra);
+                consume(rb, cbase + (c + 1) * kLdCols, valid, row_base);
             }
             tc_fence_before();
             __syncwarp();
@@ -239,10 +296,9 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 else mbar_arrive(&tempty_bar[buf]);
             }
         }
-        const int qrow = static_cast<int>(cta_rank) * kQRows + ew * 32 + lane;
-        const size_t o = (static_cast<size_t>(unit) * (CG * kQRows) + qrow) * kKC;
+        const size_t o = ((static_cast<size_t>(unit) * 2 + half) * (CG * kQRows) + qrow) * KC;
 #pragma unroll
-        for (int j = 0; j < kKC; ++j) {
+        for (int j = 0; j < KC; ++j) {
             cand_s[o + j] = best_s[j];
             cand_i[o + j] = best_i[j];
         }
@@ -259,7 +315,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
 
 // ----------------------------------------------------------------------------------------------------------
 // exact fp32 dot of two 512-vectors by one warp, fixed summation order (shared by every exact-score producer
-// so that sims, re-rank and dense top-k agree bit for bit).  a: 16 registers per lane, element (lane + 32 i) * 4 + e.
+// so that sims, re-rank and exact scan agree bit for bit).  a: 16 registers per lane, element (lane + 32 i) * 4 + e.
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load512(const float* __restrict__ p, int lane, float4 (&r)[4]) {
 #pragma unroll
@@ -338,64 +394,160 @@ __device__ inline void block_select(float* cs, long long* ci, int count, int K, 
 }
 
 constexpr int kSelThreads = 256;
-constexpr int kSelMaxCand = 148 * kKC;  // one candidate list per CTA of the coarse kernel at most
+constexpr int kHeadMax = 2 * 148 * kTopkMax;  // first k entries of every candidate list
+constexpr int kRescoreMax = 64;               // rows re-scored exactly per query before the query is declared "overflowed"
 
-// One block per query: merge `units` coarse lists, exact fp32 re-score of the kKC best, final order, write top-k.
+// One block per query. lists x kc coarse candidates -> exact top-k, or flag[q] = 1 when the candidate set may be incomplete
+// (more than kRescoreMax rows inside the margin, or a list that was full of rows inside the margin).
 // out_s: nq x k, out_i: nq x k (row_offset + local row), padded with (-inf, -1).
 __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* __restrict__ cand_s, const int* __restrict__ cand_i,
-                                                                  int units, int q_stride, const float* __restrict__ q,
-                                                                  const float* __restrict__ rows, int k, long long row_offset,
-                                                                  float* __restrict__ out_s, long long* __restrict__ out_i) {
-    __shared__ float cs[kSelMaxCand];
-    __shared__ long long ci[kSelMaxCand];
-    __shared__ float sel_s[kKC];
-    __shared__ long long sel_i[kKC];
+                                                                  int lists, int q_stride, int kc, const float* __restrict__ q,
+                                                                  const float* __restrict__ rows, const float* __restrict__ gmax_ptr,
+                                                                  int k, long long row_offset, float* __restrict__ out_s,
+                                                                  long long* __restrict__ out_i, int* __restrict__ flags) {
+    __shared__ float cs[kHeadMax];
+    __shared__ long long ci[kHeadMax];
+    __shared__ float sel_s[kTopkMax];
+    __shared__ long long sel_i[kTopkMax];
     __shared__ float red_s[32];
     __shared__ long long red_i[32];
     __shared__ int red_p[32];
+    __shared__ float rs[kRescoreMax];
+    __shared__ long long ri[kRescoreMax];
+    __shared__ int n_resc, overflow;
+    __shared__ float qnorm2;
     const int qi = blockIdx.x;
-    const int count = units * kKC;
-    for (int p = threadIdx.x; p < count; p += blockDim.x) {
-        const int u = p / kKC, j = p % kKC;
-        const size_t o = (static_cast<size_t>(u) * q_stride + qi) * kKC + j;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        n_resc = 0;
+        overflow = 0;
+    }
+    // phase 1: k-th best coarse score over all lists (lists are sorted, so only their first k entries matter)
+    const int head = lists * k;
+    for (int p = threadIdx.x; p < head; p += blockDim.x) {
+        const int l = p / k, j = p % k;
+        const size_t o = (static_cast<size_t>(l) * q_stride + qi) * kc + j;
         cs[p] = cand_s[o];
         ci[p] = cand_i[o];
     }
-    __syncthreads();
-    block_select(cs, ci, count, kKC, sel_s, sel_i, red_s, red_i, red_p);
-    // exact scores: warp w re-scores candidate w
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < kKC) {
-        const long long id = sel_i[warp];
-        float s = -INFINITY;
-        if (id >= 0) {
-            float4 a[4], b[4];
-            load512(q + static_cast<size_t>(qi) * kDim, lane, a);
-            load512(rows + static_cast<size_t>(id) * kDim, lane, b);
-            s = dot512(a, b);
-        }
-        if (lane == 0) sel_s[warp] = s;
+    float4 qa[4];
+    load512(q + static_cast<size_t>(qi) * kDim, lane, qa);
+    if (warp == 0) {
+        const float n2 = dot512(qa, qa);
+        if (lane == 0) qnorm2 = n2;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // insertion sort of kKC entries by (exact score desc, row asc); invalid entries last
-        for (int a = 1; a < kKC; ++a) {
-            const float s = sel_s[a];
-            const long long id = sel_i[a];
-            int b = a - 1;
-            while (b >= 0 && id >= 0 && (sel_i[b] < 0 || better(s, id, sel_s[b], sel_i[b]))) {
-                sel_s[b + 1] = sel_s[b];
-                sel_i[b + 1] = sel_i[b];
-                --b;
-            }
-            sel_s[b + 1] = s;
-            sel_i[b + 1] = id;
+    block_select(cs, ci, head, k, sel_s, sel_i, red_s, red_i, red_p);
+    const float ck = sel_s[k - 1];  // -inf when fewer than k rows exist
+    const float thr = ck - 2.f * kCoarseEps * sqrtf(qnorm2) * __ldg(gmax_ptr);
+    // phase 2: every candidate with coarse >= thr is re-scored
+    const int total = lists * kc;
+    for (int p = threadIdx.x; p < total; p += blockDim.x) {
+        const int l = p / kc, j = p % kc;
+        const size_t o = (static_cast<size_t>(l) * q_stride + qi) * kc + j;
+        const int id = cand_i[o];
+        if (id < 0) continue;
+        const float s = cand_s[o];
+        if (s >= thr) {
+            if (j == kc - 1) overflow = 1;  // this list was full of in-margin rows: it may have dropped one
+            const int slot = atomicAdd(&n_resc, 1);
+            if (slot < kRescoreMax) ri[slot] = id;
         }
-        for (int j = 0; j < k; ++j) {
-            const bool ok = j < kKC && sel_i[j] >= 0;
-            out_s[static_cast<size_t>(qi) * k + j] = ok ? sel_s[j] : -INFINITY;
-            out_i[static_cast<size_t>(qi) * k + j] = ok ? sel_i[j] + row_offset : -1;
+    }
+    __syncthreads();
+    const int nr = min(n_resc, kRescoreMax);
+    if (n_resc > kRescoreMax) overflow = 1;
+    // phase 3: exact scores
+    for (int c = warp; c < nr; c += (blockDim.x >> 5)) {
+        float4 b[4];
+        load512(rows + static_cast<size_t>(ri[c]) * kDim, lane, b);
+        const float s = dot512(qa, b);
+        if (lane == 0) rs[c] = s;
+    }
+    __syncthreads();
+    // phase 4: final order by (exact score desc, row asc)
+    block_select(rs, ri, nr, k, sel_s, sel_i, red_s, red_i, red_p);
+    if (threadIdx.x < k) {
+        const long long id = sel_i[threadIdx.x];
+        out_s[static_cast<size_t>(qi) * k + threadIdx.x] = sel_s[threadIdx.x];
+        out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
+    }
+    if (threadIdx.x == 0) flags[qi] = overflow;
+}
+
+// exact fp32 scan for the queries with flags[q] != 0 (flags == nullptr: all queries). grid (slices, nq), 256 threads:
+// warp w of slice s scores rows s*8+w, s*8+w + 8*slices, ... and keeps its top-k; the block merges its 8 warps.
+// part_s / part_i: [nq][slices][kTopkMax]
+constexpr int kScanThreads = 256;
+__global__ void __launch_bounds__(kScanThreads) exact_scan_kernel(const float* __restrict__ rows, long long n, const float* __restrict__ q,
+                                                                  const int* __restrict__ flags, float* __restrict__ part_s,
+                                                                  long long* __restrict__ part_i) {
+    const int qi = blockIdx.y;
+    if (flags && !flags[qi]) return;
+    __shared__ float cs[8 * kTopkMax];
+    __shared__ long long ci[8 * kTopkMax];
+    __shared__ float sel_s[kTopkMax];
+    __shared__ long long sel_i[kTopkMax];
+    __shared__ float red_s[32];
+    __shared__ long long red_i[32];
+    __shared__ int red_p[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 qa[4];
+    load512(q + static_cast<size_t>(qi) * kDim, lane, qa);
+    float bs[kTopkMax];
+    int bi[kTopkMax];
+#pragma unroll
+    for (int j = 0; j < kTopkMax; ++j) {
+        bs[j] = -INFINITY;
+        bi[j] = -1;
+    }
+    const long long stride = static_cast<long long>(gridDim.x) * 8;
+    for (long long r = static_cast<long long>(blockIdx.x) * 8 + warp; r < n; r += stride) {
+        float4 b[4];
+        load512(rows + static_cast<size_t>(r) * kDim, lane, b);
+        const float s = dot512(qa, b);  // identical in every lane
+        if ((bi[kTopkMax - 1] < 0 || s > bs[kTopkMax - 1]) && s == s) topk_insert<kTopkMax>(bs, bi, s, static_cast<int>(r));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < kTopkMax; ++j) {
+            cs[warp * kTopkMax + j] = bs[j];
+            ci[warp * kTopkMax + j] = bi[j];
         }
+    }
+    __syncthreads();
+    block_select(cs, ci, 8 * kTopkMax, kTopkMax, sel_s, sel_i, red_s, red_i, red_p);
+    if (threadIdx.x < kTopkMax) {
+        const size_t o = (static_cast<size_t>(qi) * gridDim.x + blockIdx.x) * kTopkMax + threadIdx.x;
+        part_s[o] = sel_s[threadIdx.x];
+        part_i[o] = sel_i[threadIdx.x];
+    }
+}
+// second half of the exact scan: merge the slices of each flagged query and write the final nq x k result
+constexpr int kScanSlicesMax = 148 * 2;
+__global__ void __launch_bounds__(kSelThreads) exact_merge_kernel(const float* __restrict__ part_s, const long long* __restrict__ part_i,
+                                                                  int slices, const int* __restrict__ flags, int k, long long row_offset,
+                                                                  float* __restrict__ out_s, long long* __restrict__ out_i) {
+    const int qi = blockIdx.x;
+    if (flags && !flags[qi]) return;
+    __shared__ float cs[kScanSlicesMax * kTopkMax];
+    __shared__ long long ci[kScanSlicesMax * kTopkMax];
+    __shared__ float sel_s[kTopkMax];
+    __shared__ long long sel_i[kTopkMax];
+    __shared__ float red_s[32];
+    __shared__ long long red_i[32];
+    __shared__ int red_p[32];
+    const int count = slices * kTopkMax;
+    for (int p = threadIdx.x; p < count; p += blockDim.x) {
+        cs[p] = part_s[static_cast<size_t>(qi) * count + p];
+        ci[p] = part_i[static_cast<size_t>(qi) * count + p];
+    }
+    __syncthreads();
+    block_select(cs, ci, count, k, sel_s, sel_i, red_s, red_i, red_p);
+    if (threadIdx.x < k) {
+        const long long id = sel_i[threadIdx.x];
+        out_s[static_cast<size_t>(qi) * k + threadIdx.x] = sel_s[threadIdx.x];
+        out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
     }
 }
 
@@ -426,53 +578,13 @@ __global__ void __launch_bounds__(kSimsThreads) sims_kernel(const float* __restr
     }
 }
 
-// top-k of each row of a dense similarity matrix (first maximum wins on ties = std::max_element, src/arcface.cpp:210)
-__global__ void __launch_bounds__(kSelThreads) topk_dense_kernel(const float* __restrict__ sims, long long n, int k,
-                                                                 long long row_offset, float* __restrict__ out_s,
-                                                                 long long* __restrict__ out_i) {
-    __shared__ float cs[kSelThreads * kKC];
-    __shared__ long long ci[kSelThreads * kKC];
-    __shared__ float sel_s[kKC];
-    __shared__ long long sel_i[kKC];
-    __shared__ float red_s[32];
-    __shared__ long long red_i[32];
-    __shared__ int red_p[32];
-    const int qi = blockIdx.x;
-    float bs[kKC];
-    int bi[kKC];
-#pragma unroll
-    for (int j = 0; j < kKC; ++j) {
-        bs[j] = -INFINITY;
-        bi[j] = -1;
-    }
-    const float* row = sims + static_cast<size_t>(qi) * n;
-    for (long long j = threadIdx.x; j < n; j += blockDim.x) {
-        const float v = row[j];
-        if (bi[kKC - 1] < 0 || v > bs[kKC - 1]) {
-            if (!(v != v)) topk_insert(bs, bi, v, static_cast<int>(j));
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < kKC; ++j) {
-        cs[threadIdx.x * kKC + j] = bs[j];
-        ci[threadIdx.x * kKC + j] = bi[j];
-    }
-    __syncthreads();
-    block_select(cs, ci, kSelThreads * kKC, k, sel_s, sel_i, red_s, red_i, red_p);
-    if (threadIdx.x < k) {
-        const long long id = sel_i[threadIdx.x];
-        out_s[static_cast<size_t>(qi) * k + threadIdx.x] = sel_s[threadIdx.x];
-        out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
-    }
-}
-
 // merge of n_parts per-shard results (each nq x k, global indices) -> nq x k, order (score desc, idx asc)
 __global__ void __launch_bounds__(64) topk_merge_kernel(const float* __restrict__ ps, const long long* __restrict__ pi, int n_parts,
                                                         int nq, int k, float* __restrict__ out_s, long long* __restrict__ out_i) {
-    __shared__ float cs[64 * kKC];
-    __shared__ long long ci[64 * kKC];
-    __shared__ float sel_s[kKC];
-    __shared__ long long sel_i[kKC];
+    __shared__ float cs[64 * kTopkMax];
+    __shared__ long long ci[64 * kTopkMax];
+    __shared__ float sel_s[kTopkMax];
+    __shared__ long long sel_i[kTopkMax];
     __shared__ float red_s[32];
     __shared__ long long red_i[32];
     __shared__ int red_p[32];
@@ -532,16 +644,29 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(float* __restrict__ row
     }
 }
 
-__global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n4) {
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
-        __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
-        uint2 o;
-        o.x = *reinterpret_cast<uint32_t*>(&a);
-        o.y = *reinterpret_cast<uint32_t*>(&b);
-        reinterpret_cast<uint2*>(dst)[i] = o;
+// scan copy + largest row norm (the margin of the coarse pass scales with it). One warp per row.
+__global__ void __launch_bounds__(256) make_scan_copy_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n,
+                                                             float* __restrict__ gmax) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    float wmax = 0.f;
+    for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps) {
+        float4 a[4];
+        load512(src + static_cast<size_t>(r) * kDim, lane, a);
+        if (dst) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __half2 lo = __floats2half2_rn(a[i].x, a[i].y), hi = __floats2half2_rn(a[i].z, a[i].w);
+                uint2 o;
+                o.x = *reinterpret_cast<uint32_t*>(&lo);
+                o.y = *reinterpret_cast<uint32_t*>(&hi);
+                reinterpret_cast<uint2*>(dst + static_cast<size_t>(r) * kDim)[lane + 32 * i] = o;
+            }
+        }
+        wmax = fmaxf(wmax, dot512(a, a));
     }
+    // non-negative floats order like their bit patterns
+    if (lane == 0 && wmax > 0.f) atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(sqrtf(wmax) * 1.0000002f));
 }
 
 }  // namespace frb

@@ -168,15 +168,17 @@ def test_sharded_search_merge_equals_single_gallery():
         ps = torch.empty((shards, nq, k), dtype=torch.float32, device="cuda")
         pi = torch.empty((shards, nq, k), dtype=torch.int64, device="cuda")
         qd = torch.from_numpy(q).cuda()
+        ms = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        mi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        st = torch.cuda.Stream()  # one explicit stream for the shard searches and the merge (a NULL stream means "handle's own")
         gs = []
         for r, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
             sh = frb200.Gallery.from_rows(G[a:b], row_offset=int(a))
             sh.set_path(frb200.FR_PATH_TENSOR)
-            sh.topk_dev(qd, k, ps[r], pi[r], stream=torch.cuda.current_stream().cuda_stream)
+            sh.topk_dev(qd, k, ps[r], pi[r], stream=st.cuda_stream)
             gs.append(sh)
-        ms = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-        mi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
-        frb200.topk_merge_dev(ps, pi, shards, nq, k, ms, mi, 0, stream=torch.cuda.current_stream().cuda_stream)
+        frb200.topk_merge_dev(ps, pi, shards, nq, k, ms, mi, 0, stream=st.cuda_stream)
         torch.cuda.synchronize()
         assert np.array_equal(mi.cpu().numpy(), fi)
         assert np.array_equal(ms.cpu().numpy().view(np.uint32), fs.view(np.uint32))
@@ -204,4 +206,24 @@ def test_large_synthetic_gallery_planted_top1():
     r2 = so.synth_rows(i[:, 1], seed)
     want2 = np.einsum("ij,ij->i", q.astype(np.float64), r2.astype(np.float64))
     assert np.abs(s[:, 1] - want2).max() <= SCORE_TOL and np.all(s[:, 1] < 0.4)
+    g.close()
+
+
+@pytest.mark.parametrize("cluster,k", [(12, 1), (40, 4), (100, 8)])
+def test_near_tie_cluster_inside_fp16_margin(cluster, k):
+    # many rows within the fp16 error margin of the best one: the coarse pass cannot order them; the exact re-score
+    # (<= 64 rows) or, beyond that, the flagged exact scan must reproduce the fp32 order
+    rng = np.random.default_rng(cluster)
+    n = 30_000
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    base = G[777].copy()
+    where = rng.choice(n, cluster, replace=False)
+    G[where] = so.l2_normalise(base[None, :] + 2e-4 * rng.standard_normal((cluster, 512)).astype(np.float32) / np.sqrt(512))
+    q = np.concatenate([base[None, :], so.l2_normalise(rng.standard_normal((3, 512)))]).astype(np.float32)
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    s, i = g.topk(q, k)
+    sim = so.sims(G, q)
+    _check_topk(s, i, sim, k)
+    assert set(i[0].tolist()) <= set(where.tolist()) | {777}
     g.close()
