@@ -52,6 +52,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, threading.Event(), [], set(), None
+        self.ready, self.recording = threading.Event(), threading.Event()  # NVML is initialised before the timed region starts
 
     def run(self):
         try:
@@ -67,15 +68,20 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
             }
+            self.ready.set()
             while not self.stop_flag.is_set():
+                if not self.recording.is_set():
+                    time.sleep(0.002)
+                    continue
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.005)
         except Exception as e:  # NVML missing: report that, do not invent numbers
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def result(self):
         self.stop_flag.set()
@@ -294,9 +300,11 @@ def main():
 
     # ---- device-resident timing (value)
     sampler = ClockSampler(local)
+    sampler.start()
+    sampler.ready.wait(timeout=10)
     gal.set_timing(True)
     barrier()
-    sampler.start()
+    sampler.recording.set()
     launches0 = frb200.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -304,6 +312,7 @@ def main():
         search_step()
     ev1.record(stream)
     barrier()
+    sampler.recording.clear()
     launches = frb200.launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.result()

@@ -30,7 +30,7 @@ struct FrGallery {
     float* q_dev = nullptr;          // 256 x 512
     float* cand_s = nullptr;         // [lists <= 296][256][16]
     int* cand_i = nullptr;
-    int* flags = nullptr;            // 256
+    int* flags = nullptr;            // [0] = count, [1..256] = queries handed to the exact scan
     float* part_s = nullptr;         // exact scan partials [256][slices][8]
     long long* part_i = nullptr;
     float* res_s = nullptr;          // 256 x FR_TOPK_MAX
@@ -56,7 +56,7 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMalloc(&g->q_dev, sizeof(float) * kChunkQ * kDim));
     FRB_CUDA(cudaMalloc(&g->cand_s, sizeof(float) * kMaxLists * kChunkQ * 16));
     FRB_CUDA(cudaMalloc(&g->cand_i, sizeof(int) * kMaxLists * kChunkQ * 16));
-    FRB_CUDA(cudaMalloc(&g->flags, sizeof(int) * kChunkQ));
+    FRB_CUDA(cudaMalloc(&g->flags, sizeof(int) * (kChunkQ + 1)));
     FRB_CUDA(cudaMalloc(&g->part_s, sizeof(float) * kChunkQ * kScanSlicesMax * kTopkMax));
     FRB_CUDA(cudaMalloc(&g->part_i, sizeof(long long) * kChunkQ * kScanSlicesMax * kTopkMax));
     FRB_CUDA(cudaMalloc(&g->res_s, sizeof(float) * kChunkQ * FR_TOPK_MAX));
@@ -131,7 +131,7 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL>, g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles,
-                                static_cast<const float*>(g->gmax), g->cand_s, g->cand_i));
+                                static_cast<const float*>(g->gmax), g->cand_s, g->cand_i, g->flags));
     count_launch();
     if (ev) FRB_CUDA(cudaEventRecord(ev->second, st));
 }
@@ -158,8 +158,11 @@ void launch_sims(FrGallery* g, const float* q_dev, int nq, float* out_dev, cudaS
 void launch_exact(FrGallery* g, const float* q_dev, int nq, int k, const int* flags, float* scores_dev, long long* idx_dev,
                   cudaStream_t st) {
     const int slices = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->n + 7) / 8, std::min(kScanSlicesMax, 2 * g->sms))));
-    exact_scan_kernel<<<dim3(slices, nq), kScanThreads, 0, st>>>(g->rows_f32, g->n, q_dev, flags, g->part_s, g->part_i);
-    exact_merge_kernel<<<nq, kSelThreads, 0, st>>>(g->part_s, g->part_i, slices, flags, k, g->row_offset, scores_dev, idx_dev);
+    // flagged-query fix-up: one pass of blocks that loop over the (normally empty) list; exact path: spread the queries too
+    const int qsplit = flags ? 1 : std::min(nq, 64);
+    exact_scan_kernel<<<dim3(slices, qsplit), kScanThreads, 0, st>>>(g->rows_f32, g->n, q_dev, nq, flags, g->part_s, g->part_i);
+    exact_merge_kernel<<<flags ? 8 : std::min(nq, 148), kSelThreads, 0, st>>>(g->part_s, g->part_i, slices, nq, flags, k, g->row_offset,
+                                                                          scores_dev, idx_dev);
     count_launch(2);
     FRB_CUDA(cudaGetLastError());
 }

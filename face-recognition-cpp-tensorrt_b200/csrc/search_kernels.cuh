@@ -82,8 +82,10 @@ __device__ __forceinline__ void topk_insert(float (&s)[KC], int (&ix)[KC], float
 template <int CG, int KSEL>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ q, int nq, long long n_rows, int num_tiles,
-                   const float* __restrict__ gmax_ptr, float* __restrict__ cand_s, int* __restrict__ cand_i) {
+                   const float* __restrict__ gmax_ptr, float* __restrict__ cand_s, int* __restrict__ cand_i,
+                   int* __restrict__ flag_list) {
     using Cfg = CoarseCfg<CG>;
+    if (blockIdx.x == 0 && threadIdx.x == 0) flag_list[0] = 0;  // list of queries the re-rank hands to the exact scan
     constexpr int KC = ListCfg<KSEL>::kKC;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
                                                                   int lists, int q_stride, int kc, const float* __restrict__ q,
                                                                   const float* __restrict__ rows, const float* __restrict__ gmax_ptr,
                                                                   int k, long long row_offset, float* __restrict__ out_s,
-                                                                  long long* __restrict__ out_i, int* __restrict__ flags) {
+                                                                  long long* __restrict__ out_i, int* __restrict__ flag_list) {
     __shared__ float cs[kHeadMax];
     __shared__ long long ci[kHeadMax];
     __shared__ float sel_s[kTopkMax];
@@ -472,18 +474,19 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
         out_s[static_cast<size_t>(qi) * k + threadIdx.x] = sel_s[threadIdx.x];
         out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
     }
-    if (threadIdx.x == 0) flags[qi] = overflow;
+    if (threadIdx.x == 0 && overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
 }
 
-// exact fp32 scan for the queries with flags[q] != 0 (flags == nullptr: all queries). grid (slices, nq), 256 threads:
-// warp w of slice s scores rows s*8+w, s*8+w + 8*slices, ... and keeps its top-k; the block merges its 8 warps.
-// part_s / part_i: [nq][slices][kTopkMax]
+// exact fp32 scan. flag_list == nullptr: all nq queries; else the flag_list[0] queries listed in flag_list[1..].
+// grid (slices, qsplit), 256 threads: block (s, y) handles queries y, y + qsplit, ...; warp w of slice s scores rows
+// s*8+w, s*8+w + 8*slices, ... and keeps its top-k; the block merges its 8 warps.  part_s / part_i: [nq][slices][kTopkMax]
 constexpr int kScanThreads = 256;
 __global__ void __launch_bounds__(kScanThreads) exact_scan_kernel(const float* __restrict__ rows, long long n, const float* __restrict__ q,
-                                                                  const int* __restrict__ flags, float* __restrict__ part_s,
+                                                                  int nq, const int* __restrict__ flag_list, float* __restrict__ part_s,
                                                                   long long* __restrict__ part_i) {
-    const int qi = blockIdx.y;
-    if (flags && !flags[qi]) return;
+    const int total = flag_list ? flag_list[0] : nq;
+    for (int f = blockIdx.y; f < total; f += gridDim.y) {
+    const int qi = flag_list ? flag_list[1 + f] : f;
     __shared__ float cs[8 * kTopkMax];
     __shared__ long long ci[8 * kTopkMax];
     __shared__ float sel_s[kTopkMax];
@@ -522,14 +525,18 @@ __global__ void __launch_bounds__(kScanThreads) exact_scan_kernel(const float* _
         part_s[o] = sel_s[threadIdx.x];
         part_i[o] = sel_i[threadIdx.x];
     }
+    __syncthreads();
+    }
 }
 // second half of the exact scan: merge the slices of each flagged query and write the final nq x k result
 constexpr int kScanSlicesMax = 148 * 2;
 __global__ void __launch_bounds__(kSelThreads) exact_merge_kernel(const float* __restrict__ part_s, const long long* __restrict__ part_i,
-                                                                  int slices, const int* __restrict__ flags, int k, long long row_offset,
-                                                                  float* __restrict__ out_s, long long* __restrict__ out_i) {
-    const int qi = blockIdx.x;
-    if (flags && !flags[qi]) return;
+                                                                  int slices, int nq, const int* __restrict__ flag_list, int k,
+                                                                  long long row_offset, float* __restrict__ out_s,
+                                                                  long long* __restrict__ out_i) {
+    const int total = flag_list ? flag_list[0] : nq;
+    for (int f = blockIdx.x; f < total; f += gridDim.x) {
+    const int qi = flag_list ? flag_list[1 + f] : f;
     __shared__ float cs[kScanSlicesMax * kTopkMax];
     __shared__ long long ci[kScanSlicesMax * kTopkMax];
     __shared__ float sel_s[kTopkMax];
@@ -548,6 +555,8 @@ __global__ void __launch_bounds__(kSelThreads) exact_merge_kernel(const float* _
         const long long id = sel_i[threadIdx.x];
         out_s[static_cast<size_t>(qi) * k + threadIdx.x] = sel_s[threadIdx.x];
         out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
+    }
+    __syncthreads();
     }
 }
 
