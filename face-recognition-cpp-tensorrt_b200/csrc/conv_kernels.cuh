@@ -1,0 +1,265 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores for the ArcFace IR-(SE)50 body and the RetinaFace 64-channel convs
+// (network spec: /root/reference conversion/arcface/model_irse.py:48-90,139-147; conversion/retina/models/net.py).
+//
+// Activation layout ("shared-halo flat NHWC"): a feature map of B images of H x W pixels with C channels (fp16) is a matrix
+// [P, C], P = B * (H+1) * (W+1): position p = img*(H+1)*(W+1) + r*(W+1) + c. Column c == W and row r == H of every image
+// are zero and are never written, so the 3x3 neighbour (dy, dx) of position p is simply row p + (dy-1)*(W+1) + (dx-1) of the
+// matrix — the zero column / row (and TMA's zero fill before row 0 and after row P-1) supply the convolution's zero padding.
+// A conv is then  D[p, n] = sum_tap sum_c  X[p + shift(tap), c] * Wt[n, tap*Cin + c] : for each tap a plain 2-D TMA box
+// [128 positions x 64 channels] at a shifted row coordinate, no im2col buffer.
+// Stride-2 3x3 convs read a "phase-split" input written by their producer: four (H/2 x W/2) maps X_pq[i,j] = X[2i+p, 2j+q] in
+// the same layout; tap (dy,dx) reads phase (dy!=1, dx!=1) shifted by (dy==0 ? -1 : 0, dx==0 ? -1 : 0).
+//
+// One CTA computes a [128 positions x BN output channels] tile: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias / PReLU / residual / next-unit BN -> fp16 stores).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ptx_sm100.cuh"
+
+namespace frb {
+
+constexpr int kConvBM = 128;
+constexpr int kConvThreads = 256;
+constexpr int kConvStages = 3;  // 3 x 32 KiB (BN = 128) leaves room for two CTAs per SM
+
+enum ConvOutMode { kOutNormal = 0, kOutPhaseSplit = 1 };
+enum ConvResMode { kResNone = 0, kResSame = 1, kResSubsample = 2 };
+
+struct ConvGemmParams {
+    int P;             // output positions (GEMM rows)
+    int H, W;          // valid extent of the output geometry (Wp = W+1, HpWp = (H+1)*(W+1))
+    int cin_blocks;    // Cin / 64
+    int taps;          // 9 or 1
+    int tap_phase;     // 1: stride-2 taps over a phase-split input of the output's geometry
+    int phase_rows;    // rows per phase map (tap_phase) = P
+    int cout;          // total output channels (row stride of the outputs)
+    int kb_per_split;  // k-blocks per blockIdx.z (split-K); taps*cin_blocks when not split
+    const float* bias;     // [cout] or null
+    const float* prelu;    // [cout] or null : PReLU slopes applied after bias
+    const __half* res;     // residual source or null
+    int res_mode;          // ConvResMode; kResSubsample: source geometry (2H, 2W) normal layout, read at (2r, 2c)
+    __half* out;           // [P_out, cout] fp16 or null
+    int out_mode;          // ConvOutMode; kOutPhaseSplit: out geometry (H/2, W/2) x 4 phases
+    long long out_phase_rows;  // rows between the phase maps of `out` (fixed at the handle's maximum batch)
+    __half* out_bn;        // second output: out * bn_s + bn_b (the next unit's pre-activation BatchNorm), same layout as out
+    const float* bn_s;
+    const float* bn_b;
+    __half* out_sub;       // third output: out at even (r, c) written in geometry (H/2, W/2) (input of a stride-2 1x1 shortcut)
+    float* partial;        // split-K: fp32 accumulators [split][P][cout], no epilogue math
+};
+
+template <int BN>
+struct ConvCfg {
+    static constexpr int kABytes = kConvBM * 128;
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kSmemBytes = 1024 + kConvStages * kStageBytes + 256;
+    static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ ConvGemmParams prm) {
+    using Cfg = ConvCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kConvStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + kConvStages;
+    uint64_t* acc_bar = empty_bar + kConvStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int p0 = blockIdx.x * kConvBM;
+    const int n0 = blockIdx.y * BN;
+    const int Wp = prm.W + 1;
+    const int kb_begin = blockIdx.z * prm.kb_per_split;
+    const int kb_total = prm.taps * prm.cin_blocks;
+    const int kb_end = min(kb_total, kb_begin + prm.kb_per_split);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kConvStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(acc_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                const int tap = kb / prm.cin_blocks;
+                const int cb = kb - tap * prm.cin_blocks;
+                int row;
+                if (prm.taps == 1) {
+                    row = p0;
+                } else {
+                    const int dy = tap / 3, dx = tap - dy * 3;
+                    if (prm.tap_phase) {
+                        const int ph = (dy != 1 ? 2 : 0) + (dx != 1 ? 1 : 0);
+                        row = ph * prm.phase_rows + p0 + (dy == 0 ? -Wp : 0) + (dx == 0 ? -1 : 0);
+                    } else {
+                        row = p0 + (dy - 1) * Wp + (dx - 1);
+                    }
+                }
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
+                uint8_t* b_dst = a_dst + Cfg::kABytes;
+                mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                tma_load_2d(a_dst, &tmap_a, &full_bar[stage], cb * 64, row, kEvictNormal);
+                tma_load_2d(b_dst, &tmap_b, &full_bar[stage], kb * 64, n0, kEvictLast);
+                if (++stage == kConvStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc(kConvBM, BN, 0, 0);
+            uint32_t stage = 0, phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_ss(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                (kb > kb_begin || k > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);
+                if (++stage == kConvStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(acc_bar);
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue: lane = output position ----------------
+        const int ew = warp & 3;
+        const int p = p0 + ew * 32 + lane;
+        const int HpWp = (prm.H + 1) * Wp;
+        const int img = p / HpWp;
+        const int rem = p - img * HpWp;
+        const int r = rem / Wp;
+        const int c = rem - r * Wp;
+        const bool valid = p < prm.P && r < prm.H && c < prm.W;
+        // destinations
+        size_t o_main = 0, o_sub = 0, o_res = 0;
+        bool sub_ok = false;
+        if (valid) {
+            if (prm.out_mode == kOutPhaseSplit) {
+                const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                const int ph = ((r & 1) << 1) | (c & 1);
+                o_main = static_cast<size_t>(ph) * prm.out_phase_rows + static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
+            } else {
+                o_main = static_cast<size_t>(p);
+            }
+            if (prm.out_sub && !(r & 1) && !(c & 1)) {
+                const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                o_sub = static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
+                sub_ok = true;
+            }
+            if (prm.res_mode == kResSame) {
+                o_res = static_cast<size_t>(p);
+            } else if (prm.res_mode == kResSubsample) {
+                const int W2p = 2 * prm.W + 1, H2pW2p = (2 * prm.H + 1) * W2p;
+                o_res = static_cast<size_t>(img) * H2pW2p + (2 * r) * W2p + 2 * c;
+            }
+        }
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 16) {
+            uint32_t raw[16];
+            tmem_ld_32x32b_x16(taddr + cc, raw);
+            tmem_ld_wait_x16(raw);
+            if (!valid) continue;
+            const int n = n0 + cc;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+            if (prm.partial) {
+                float4* dst = reinterpret_cast<float4*>(prm.partial + (static_cast<size_t>(blockIdx.z) * prm.P + p) * prm.cout + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                continue;
+            }
+            if (prm.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += __ldg(prm.bias + n + j);
+            }
+            if (prm.prelu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * __ldg(prm.prelu + n + j);
+            }
+            if (prm.res_mode != kResNone) {
+                const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * prm.cout + n);
+                const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+                    v[2 * j] += a.x;
+                    v[2 * j + 1] += a.y;
+                    v[8 + 2 * j] += b.x;
+                    v[8 + 2 * j + 1] += b.y;
+                }
+            }
+            uint4 pk[2];
+            __half2* hp = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hp[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            if (prm.out) {
+                uint4* dst = reinterpret_cast<uint4*>(prm.out + o_main * prm.cout + n);
+                dst[0] = pk[0];
+                dst[1] = pk[1];
+            }
+            if (sub_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(prm.out_sub + o_sub * prm.cout + n);
+                dst[0] = pk[0];
+                dst[1] = pk[1];
+            }
+            if (prm.out_bn) {
+                // the stored (fp16-rounded) value is what the next unit's shortcut sees; its BN input is the same value
+                uint4 pb[2];
+                __half2* hb = reinterpret_cast<__half2*>(pb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 y = __half22float2(hp[j]);
+                    hb[j] = __floats2half2_rn(fmaf(y.x, __ldg(prm.bn_s + n + 2 * j), __ldg(prm.bn_b + n + 2 * j)),
+                                              fmaf(y.y, __ldg(prm.bn_s + n + 2 * j + 1), __ldg(prm.bn_b + n + 2 * j + 1)));
+                }
+                uint4* dst = reinterpret_cast<uint4*>(prm.out_bn + o_main * prm.cout + n);
+                dst[0] = pb[0];
+                dst[1] = pb[1];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+}  // namespace frb

@@ -1,0 +1,522 @@
+// ArcFace IR-50 / IR-SE-50 embedder: host side of the C ABI ("Embedder" section of include/fr_b200.h).
+// Replaces the TensorRT half of ArcFaceIR50 (/root/reference src/arcface.cpp:21-103,131-148); the network arithmetic is the
+// reference's conversion/arcface/model_irse.py (see oracle/arcface_oracle.py for the fp32 restatement it is tested against).
+//
+// Execution plan per forward (IR mode; IR_SE adds gate + apply kernels per unit):
+//   stem (direct conv, CUDA cores)  ->  24 units x { [shortcut 1x1 GEMM]  conv1 GEMM (+PReLU)  conv2 GEMM (+bias +shortcut,
+//   writes y, BN_next(y), y[::2,::2]) }  ->  folded Linear as split-K GEMM  ->  partial reduce + bias + L2 normalise.
+// Every GEMM is conv_gemm_kernel (tcgen05, csrc/conv_kernels.cuh). Activations are fp16 in the shared-halo flat layout.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "conv_kernels.cuh"
+#include "embed_kernels.cuh"
+#include "weights.h"
+
+using namespace frb;
+
+namespace {
+
+constexpr int kGeo[5] = {112, 56, 28, 14, 7};
+constexpr int kStageC[5] = {64, 64, 128, 256, 512};   // channels of the map living at geometry g (index 0 = stem output)
+constexpr int kStageUnits[5] = {0, 3, 4, 14, 3};
+constexpr int kFcSplits = 32;
+constexpr int kRunAll = 1 << 30;  // stop_after_unit value for a complete forward
+constexpr int kFcK = 64 * 512;  // 8 x 8 padded positions x 512 channels
+
+inline int hpwp(int g) { return (kGeo[g] + 1) * (kGeo[g] + 1); }
+
+struct DevBuf {
+    __half* p = nullptr;
+    size_t rows = 0;
+    int C = 0;
+    CUtensorMap tmap{};
+};
+
+struct GemmStep {
+    CUtensorMap ta{}, tb{};
+    ConvGemmParams prm{};
+    int bn = 128;
+    int out_geo = 0;     // geometry index of the OUTPUT grid (P = batch * hpwp(out_geo)); -1: FC (P = batch)
+    int splits = 1;
+};
+
+struct SeStep {
+    const __half* u = nullptr;
+    const float* fc1 = nullptr;
+    const float* fc2 = nullptr;
+    int geo = 0, C = 0;
+    const __half* res = nullptr;
+    int res_mode = 0;
+    __half* y = nullptr;
+    __half* y_bn = nullptr;
+    const float* bn_s = nullptr;
+    const float* bn_b = nullptr;
+    __half* y_sub = nullptr;
+};
+
+struct Step {
+    int kind = 0;  // 0 = GEMM, 1 = SE gate+apply
+    GemmStep g;
+    SeStep se;
+    int unit = -1;  // body unit this step belongs to (trace / stop_after)
+};
+
+}  // namespace
+
+struct FrEmbedder {
+    int device = 0, sms = 0, mode = FR_MODE_IR, max_batch = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;       // everything cudaMalloc'ed (weights + activations)
+    // stem
+    float *stem_w = nullptr, *stem_b = nullptr, *stem_prelu = nullptr, *u0_bn_s = nullptr, *u0_bn_b = nullptr;
+    DevBuf stem_y, stem_yb;
+    float* in_f32 = nullptr;         // max_batch x 3 x 112 x 112
+    uint8_t* in_u8 = nullptr;        // max_batch x 112 x 112 x 3
+    float* gate = nullptr;           // max_batch x 512
+    float* fc_partial = nullptr;     // kFcSplits x max_batch x 512
+    float* fc_bias = nullptr;
+    float* out_dev = nullptr;        // max_batch x 512
+    std::vector<Step> steps;
+    std::vector<std::pair<const __half*, int>> unit_out;  // per unit: (y buffer, geometry index) for fr_embedder_trace
+    int last_batch = 0;
+    bool last_u8 = false;
+};
+
+namespace {
+
+template <class T>
+T* dev_alloc(FrEmbedder* e, size_t count, bool zero) {
+    T* p = nullptr;
+    FRB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    e->allocs.push_back(p);
+    if (zero) FRB_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), e->stream));
+    return p;
+}
+
+template <class T>
+T* upload(FrEmbedder* e, const HostTensor& t) {
+    T* p = dev_alloc<T>(e, static_cast<size_t>(t.numel()), false);
+    FRB_CUDA(cudaMemcpyAsync(p, t.data, t.nbytes, cudaMemcpyHostToDevice, e->stream));
+    return p;
+}
+
+DevBuf make_buf(FrEmbedder* e, size_t rows, int C) {
+    DevBuf b;
+    b.rows = rows;
+    b.C = C;
+    b.p = dev_alloc<__half>(e, rows * C, true);  // zero once: pad rows/columns are never written afterwards
+    b.tmap = make_tmap_2d_f16(b.p, rows, static_cast<uint64_t>(C), 128, 64);
+    return b;
+}
+
+template <int BN>
+void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
+    ConvGemmParams prm = s.prm;
+    prm.P = P;
+    dim3 grid((P + kConvBM - 1) / kConvBM, prm.cout / BN, s.splits);
+    conv_gemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
+    count_launch();
+}
+
+void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit) {
+    cudaStream_t st = e->stream;
+    const long long pixels = static_cast<long long>(batch) * 112 * 112;
+    const int blocks = static_cast<int>((pixels + 127) / 128);
+    if (u8_input)
+        arcface_stem_kernel<true><<<blocks, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
+                                                          e->stem_y.p, e->stem_yb.p);
+    else
+        arcface_stem_kernel<false><<<blocks, 128, 0, st>>>(e->in_f32, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
+                                                           e->stem_y.p, e->stem_yb.p);
+    count_launch();
+    for (const Step& s : e->steps) {
+        if (s.unit > stop_after_unit) break;
+        if (s.kind == 0) {
+            const int P = s.g.out_geo >= 0 ? batch * hpwp(s.g.out_geo) : batch;
+            GemmStep g = s.g;
+            if (g.out_geo < 0) {  // FC: one GEMM row per image
+                g.prm.W = batch;
+                g.prm.H = 1;
+            }
+            if (g.bn == 64) launch_gemm<64>(g, P, st);
+            else launch_gemm<128>(g, P, st);
+        } else {
+            const SeStep& q = s.se;
+            const int H = kGeo[q.geo], P = batch * hpwp(q.geo);
+            se_gate_kernel<<<batch, 256, 0, st>>>(q.u, hpwp(q.geo), H * H, q.C, q.fc1, q.fc2, e->gate);
+            const long long threads = static_cast<long long>(P) * (q.C / 8);
+            se_apply_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(q.u, e->gate, P, H, H, q.C, q.res, q.res_mode, q.y, q.y_bn,
+                                                                                    q.bn_s, q.bn_b, q.y_sub);
+            count_launch(2);
+        }
+    }
+    if (stop_after_unit == kRunAll) {
+        fc_reduce_l2norm_kernel<<<batch, 512, 0, st>>>(e->fc_partial, kFcSplits, batch, e->fc_bias, e->out_dev);
+        count_launch();
+    }
+    FRB_CUDA(cudaGetLastError());
+}
+
+void build_plan(FrEmbedder* e, const WeightFile& wf) {
+    const bool se = e->mode == FR_MODE_IR_SE;
+    const int B = e->max_batch;
+    auto f32 = [&](const std::string& n, int64_t numel) { return upload<float>(e, wf.get(n, 0, numel)); };
+    auto f16 = [&](const std::string& n, int64_t numel) { return upload<__half>(e, wf.get(n, 1, numel)); };
+
+    e->stem_w = f32("stem.w", 64 * 27);
+    e->stem_b = f32("stem.b", 64);
+    e->stem_prelu = f32("stem.prelu", 64);
+    e->in_f32 = dev_alloc<float>(e, static_cast<size_t>(B) * 3 * 112 * 112, false);
+    e->in_u8 = dev_alloc<uint8_t>(e, static_cast<size_t>(B) * 112 * 112 * 3, false);
+    e->gate = dev_alloc<float>(e, static_cast<size_t>(B) * 512, false);
+    e->fc_partial = dev_alloc<float>(e, static_cast<size_t>(kFcSplits) * B * 512, false);
+    e->out_dev = dev_alloc<float>(e, static_cast<size_t>(B) * 512, false);
+    e->stem_y = make_buf(e, static_cast<size_t>(B) * hpwp(0), 64);
+    e->stem_yb = make_buf(e, static_cast<size_t>(B) * hpwp(0), 64);
+
+    // per-unit parameters
+    struct UnitW {
+        int cin, d, stride;
+        float *bn1_s, *bn1_b, *prelu, *b2, *bs = nullptr, *fc1 = nullptr, *fc2 = nullptr;
+        __half *w1, *w2, *ws = nullptr;
+        CUtensorMap t1, t2, ts;
+    };
+    std::vector<UnitW> uw;
+    {
+        int cin = 64;
+        for (int stage = 1; stage <= 4; ++stage) {
+            for (int j = 0; j < kStageUnits[stage]; ++j) {
+                UnitW u{};
+                u.cin = (j == 0) ? cin : kStageC[stage];
+                u.d = kStageC[stage];
+                u.stride = (j == 0) ? 2 : 1;
+                const std::string q = "u" + std::to_string(uw.size()) + ".";
+                u.bn1_s = f32(q + "bn1.s", u.cin);
+                u.bn1_b = f32(q + "bn1.b", u.cin);
+                u.w1 = f16(q + "conv1.w", static_cast<int64_t>(u.d) * 9 * u.cin);
+                u.prelu = f32(q + "prelu", u.d);
+                u.w2 = f16(q + "conv2.w", static_cast<int64_t>(u.d) * 9 * u.d);
+                u.b2 = f32(q + "conv2.b", u.d);
+                const int bn = u.d == 64 ? 64 : 128;
+                u.t1 = make_tmap_2d_f16(u.w1, u.d, 9ull * u.cin, bn, 64);
+                u.t2 = make_tmap_2d_f16(u.w2, u.d, 9ull * u.d, bn, 64);
+                if (u.cin != u.d) {
+                    u.ws = f16(q + "sc.w", static_cast<int64_t>(u.d) * u.cin);
+                    u.bs = f32(q + "sc.b", u.d);
+                    u.ts = make_tmap_2d_f16(u.ws, u.d, u.cin, bn, 64);
+                }
+                if (se) {
+                    u.fc1 = f32(q + "se.fc1", static_cast<int64_t>(u.d / 16) * u.d);
+                    u.fc2 = f32(q + "se.fc2", static_cast<int64_t>(u.d) * (u.d / 16));
+                }
+                uw.push_back(u);
+            }
+            cin = kStageC[stage];
+        }
+    }
+    e->u0_bn_s = uw[0].bn1_s;
+    e->u0_bn_b = uw[0].bn1_b;
+
+    // activation buffers per stage
+    struct StageBufs {
+        DevBuf tphase, t, y[2], yb[2], sc, ysub, u;
+    };
+    StageBufs sb[5];
+    for (int s = 1; s <= 4; ++s) {
+        const size_t P = static_cast<size_t>(B) * hpwp(s);
+        const int C = kStageC[s];
+        sb[s].tphase = make_buf(e, 4 * P, C);
+        sb[s].t = make_buf(e, P, C);
+        for (int k = 0; k < 2; ++k) {
+            sb[s].y[k] = make_buf(e, P, C);
+            sb[s].yb[k] = make_buf(e, P, C);
+        }
+        if (s >= 2) {
+            sb[s].sc = make_buf(e, P, C);
+            sb[s].ysub = make_buf(e, P, kStageC[s - 1]);
+        }
+        if (se) sb[s].u = make_buf(e, P, C);
+    }
+
+    auto base_prm = [](int geo, int cin, int taps, int cout) {
+        ConvGemmParams p{};
+        p.H = p.W = kGeo[geo];
+        p.cin_blocks = cin / 64;
+        p.taps = taps;
+        p.cout = cout;
+        p.kb_per_split = taps * (cin / 64);
+        return p;
+    };
+
+    int ui = 0;
+    const DevBuf* in_y = &e->stem_y;
+    const DevBuf* in_yb = &e->stem_yb;
+    for (int stage = 1; stage <= 4; ++stage) {
+        int cur = 0;
+        for (int j = 0; j < kStageUnits[stage]; ++j, ++ui) {
+            const UnitW& u = uw[ui];
+            const bool first = j == 0;
+            const bool last_unit = ui + 1 == static_cast<int>(uw.size());
+            const int bn = u.d == 64 ? 64 : 128;
+            const int in_geo = first ? stage - 1 : stage;
+            // ---- shortcut 1x1 stride-2 conv + BN (folded) on the subsampled input (model_irse.py:54-56)
+            if (first && u.cin != u.d) {
+                Step s;
+                s.unit = ui;
+                s.g.ta = sb[stage].ysub.tmap;
+                s.g.tb = u.ts;
+                s.g.bn = bn;
+                s.g.out_geo = stage;
+                s.g.prm = base_prm(stage, u.cin, 1, u.d);
+                s.g.prm.bias = u.bs;
+                s.g.prm.out = sb[stage].sc.p;
+                e->steps.push_back(s);
+            }
+            // ---- conv1: 3x3 stride 1 on BN1(x) + PReLU (:57-59); a stride-2 unit stores it phase-split for conv2
+            {
+                Step s;
+                s.unit = ui;
+                s.g.ta = in_yb->tmap;
+                s.g.tb = u.t1;
+                s.g.bn = bn;
+                s.g.out_geo = in_geo;
+                s.g.prm = base_prm(in_geo, u.cin, 9, u.d);
+                s.g.prm.prelu = u.prelu;
+                if (first) {
+                    s.g.prm.out = sb[stage].tphase.p;
+                    s.g.prm.out_mode = kOutPhaseSplit;
+                    s.g.prm.out_phase_rows = static_cast<long long>(B) * hpwp(stage);
+                } else {
+                    s.g.prm.out = sb[stage].t.p;
+                }
+                e->steps.push_back(s);
+            }
+            // ---- conv2: 3x3 stride s + BN (folded) [+ shortcut] (:59-65)
+            const int nxt = first ? 0 : cur ^ 1;
+            const __half* res = nullptr;
+            int res_mode = kResNone;
+            if (first && u.cin == u.d) {
+                res = in_y->p;  // MaxPool2d(1, 2): x[::2, ::2]
+                res_mode = kResSubsample;
+            } else if (first) {
+                res = sb[stage].sc.p;
+                res_mode = kResSame;
+            } else {
+                res = in_y->p;
+                res_mode = kResSame;
+            }
+            __half* y = sb[stage].y[nxt].p;
+            __half* yb = last_unit ? nullptr : sb[stage].yb[nxt].p;
+            const float* nbs = last_unit ? nullptr : uw[ui + 1].bn1_s;
+            const float* nbb = last_unit ? nullptr : uw[ui + 1].bn1_b;
+            const bool next_is_first = !last_unit && (j + 1 == kStageUnits[stage]);
+            __half* ysub = next_is_first ? sb[stage + 1].ysub.p : nullptr;
+            {
+                Step s;
+                s.unit = ui;
+                s.g.ta = first ? sb[stage].tphase.tmap : sb[stage].t.tmap;
+                s.g.tb = u.t2;
+                s.g.bn = bn;
+                s.g.out_geo = stage;
+                s.g.prm = base_prm(stage, u.d, 9, u.d);
+                s.g.prm.bias = u.b2;
+                if (first) {
+                    s.g.prm.tap_phase = 1;
+                    s.g.prm.phase_rows = B * hpwp(stage);
+                }
+                if (se) {
+                    s.g.prm.out = sb[stage].u.p;
+                } else {
+                    s.g.prm.res = res;
+                    s.g.prm.res_mode = res_mode;
+                    s.g.prm.out = y;
+                    s.g.prm.out_bn = yb;
+                    s.g.prm.bn_s = nbs;
+                    s.g.prm.bn_b = nbb;
+                    s.g.prm.out_sub = ysub;
+                }
+                e->steps.push_back(s);
+            }
+            if (se) {
+                Step s;
+                s.kind = 1;
+                s.unit = ui;
+                s.se.u = sb[stage].u.p;
+                s.se.fc1 = u.fc1;
+                s.se.fc2 = u.fc2;
+                s.se.geo = stage;
+                s.se.C = u.d;
+                s.se.res = res;
+                s.se.res_mode = res_mode;
+                s.se.y = y;
+                s.se.y_bn = yb;
+                s.se.bn_s = nbs;
+                s.se.bn_b = nbb;
+                s.se.y_sub = ysub;
+                e->steps.push_back(s);
+            }
+            e->unit_out.emplace_back(y, stage);
+            in_y = &sb[stage].y[nxt];
+            in_yb = &sb[stage].yb[nxt];
+            cur = nxt;
+        }
+    }
+    // ---- output_layer: BN2d + Flatten + Linear + BN1d folded into one GEMM over the padded 8x8x512 map (:142-147)
+    {
+        __half* fcw = f16("fc.w", 512ll * kFcK);
+        e->fc_bias = f32("fc.b", 512);
+        Step s;
+        s.unit = 1000;
+        s.g.ta = make_tmap_2d_f16(in_y->p, static_cast<uint64_t>(B), kFcK, 128, 64);
+        s.g.tb = make_tmap_2d_f16(fcw, 512, kFcK, 128, 64);
+        s.g.bn = 128;
+        s.g.out_geo = -1;
+        s.g.splits = kFcSplits;
+        s.g.prm.cin_blocks = kFcK / 64;
+        s.g.prm.taps = 1;
+        s.g.prm.cout = 512;
+        s.g.prm.kb_per_split = (kFcK / 64) / kFcSplits;
+        s.g.prm.partial = e->fc_partial;
+        e->steps.push_back(s);
+    }
+    FRB_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+void check_batch(const FrEmbedder* e, const void* in, int batch, const void* out) {
+    if (!e) throw ArgError{"null embedder"};
+    if (!in || !out) throw ArgError{"null buffer"};
+    if (batch < 1 || batch > e->max_batch) throw ArgError{"batch out of range (1..max_batch)"};
+}
+
+}  // namespace
+
+extern "C" {
+
+int fr_embedder_create(const char* weights_path, int max_batch, int device, FrEmbedder** out) {
+    return guarded([&] {
+        if (!out) throw ArgError{"out is null"};
+        if (max_batch < 1 || max_batch > 1024) throw ArgError{"max_batch out of range (1..1024)"};
+        WeightFile wf = load_weight_file(weights_path);
+        if (wf.kind != kKindArcfaceIR && wf.kind != kKindArcfaceIRSE) throw FileError{FR_EFORMAT, "weight file is not an ArcFace checkpoint"};
+        std::unique_ptr<FrEmbedder> e(new FrEmbedder());
+        e->sms = use_device(device);
+        e->device = device;
+        e->mode = wf.kind == kKindArcfaceIRSE ? FR_MODE_IR_SE : FR_MODE_IR;
+        e->max_batch = max_batch;
+        try {
+            FRB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
+            build_plan(e.get(), wf);
+        } catch (...) {
+            fr_embedder_destroy(e.release());
+            throw;
+        }
+        *out = e.release();
+    });
+}
+
+void fr_embedder_destroy(FrEmbedder* e) {
+    if (!e) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete e;
+}
+
+int fr_embedder_mode(const FrEmbedder* e) { return e ? e->mode : FR_EINVAL; }
+int fr_embedder_max_batch(const FrEmbedder* e) { return e ? e->max_batch : FR_EINVAL; }
+
+int fr_embedder_run(FrEmbedder* e, const float* chw, int batch, float* out512) {
+    return guarded([&] {
+        check_batch(e, chw, batch, out512);
+        DeviceGuard dg(e->device);
+        FRB_CUDA(cudaMemcpyAsync(e->in_f32, chw, sizeof(float) * batch * 3 * 112 * 112, cudaMemcpyHostToDevice, e->stream));
+        e->last_batch = batch;
+        e->last_u8 = false;
+        run_steps(e, batch, false, kRunAll);
+        FRB_CUDA(cudaMemcpyAsync(out512, e->out_dev, sizeof(float) * batch * 512, cudaMemcpyDeviceToHost, e->stream));
+        FRB_CUDA(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int fr_embedder_run_crops(FrEmbedder* e, const uint8_t* crops_bgr_u8, int batch, float* out512) {
+    return guarded([&] {
+        check_batch(e, crops_bgr_u8, batch, out512);
+        DeviceGuard dg(e->device);
+        FRB_CUDA(cudaMemcpyAsync(e->in_u8, crops_bgr_u8, static_cast<size_t>(batch) * 112 * 112 * 3, cudaMemcpyHostToDevice, e->stream));
+        e->last_batch = batch;
+        e->last_u8 = true;
+        run_steps(e, batch, true, kRunAll);
+        FRB_CUDA(cudaMemcpyAsync(out512, e->out_dev, sizeof(float) * batch * 512, cudaMemcpyDeviceToHost, e->stream));
+        FRB_CUDA(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int fr_embedder_run_dev(FrEmbedder* e, const float* chw_dev, int batch, float* out512_dev, void* stream) {
+    return guarded([&] {
+        check_batch(e, chw_dev, batch, out512_dev);
+        DeviceGuard dg(e->device);
+        // the plan runs on the handle's stream; order it after / before the caller's stream with events
+        cudaStream_t user = static_cast<cudaStream_t>(stream);
+        cudaEvent_t ev;
+        FRB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (user) {
+            FRB_CUDA(cudaEventRecord(ev, user));
+            FRB_CUDA(cudaStreamWaitEvent(e->stream, ev, 0));
+        }
+        FRB_CUDA(cudaMemcpyAsync(e->in_f32, chw_dev, sizeof(float) * batch * 3 * 112 * 112, cudaMemcpyDeviceToDevice, e->stream));
+        e->last_batch = batch;
+        e->last_u8 = false;
+        run_steps(e, batch, false, kRunAll);
+        FRB_CUDA(cudaMemcpyAsync(out512_dev, e->out_dev, sizeof(float) * batch * 512, cudaMemcpyDeviceToDevice, e->stream));
+        if (user) {
+            FRB_CUDA(cudaEventRecord(ev, e->stream));
+            FRB_CUDA(cudaStreamWaitEvent(user, ev, 0));
+        }
+        cudaEventDestroy(ev);
+    });
+}
+
+int fr_embedder_trace(FrEmbedder* e, int layer, float* out, int64_t cap, int64_t* n_written) {
+    return guarded([&] {
+        if (!e || !out || !n_written) throw ArgError{"null argument"};
+        if (e->last_batch < 1) throw StateError{"fr_embedder_trace: no previous run"};
+        if (layer < 0 || layer > static_cast<int>(e->unit_out.size())) throw ArgError{"layer out of range (0 = input layer, 1..24 = units)"};
+        DeviceGuard dg(e->device);
+        const int batch = e->last_batch;
+        const __half* src;
+        int geo;
+        if (layer == 0) {
+            src = e->stem_y.p;
+            geo = 0;
+        } else {
+            src = e->unit_out[layer - 1].first;
+            geo = e->unit_out[layer - 1].second;
+        }
+        const int H = kGeo[geo], C = kStageC[geo];
+        const int64_t total = static_cast<int64_t>(batch) * C * H * H;
+        if (cap < total) throw ArgError{"trace buffer too small"};
+        run_steps(e, batch, e->last_u8, layer - 1);  // re-run the retained input up to that unit (later units reuse buffers)
+        float* tmp = nullptr;
+        FRB_CUDA(cudaMalloc(&tmp, sizeof(float) * total));
+        unpack_nchw_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, e->stream>>>(src, batch, H, H, C, tmp);
+        count_launch();
+        cudaError_t err = cudaMemcpyAsync(out, tmp, sizeof(float) * total, cudaMemcpyDeviceToHost, e->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        cudaFree(tmp);
+        FRB_CUDA(err);
+        *n_written = total;
+    });
+}
+
+}  // extern "C"

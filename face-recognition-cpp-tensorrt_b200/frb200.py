@@ -181,3 +181,71 @@ class Gallery:
 def topk_merge_dev(scores_parts_t, idx_parts_t, n_parts: int, nq: int, k: int, scores_t, idx_t, device: int, stream: int = 0) -> None:
     check(lib().fr_topk_merge_dev(_ptr(scores_parts_t), _ptr(idx_parts_t), n_parts, nq, k, _ptr(scores_t), _ptr(idx_t), device,
                                   C.c_void_p(stream)))
+
+
+FR_MODE_IR, FR_MODE_IR_SE = 0, 1
+
+
+def _bind_embedder(L):
+    if getattr(L, "_emb_bound", False):
+        return
+    L.fr_embedder_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.fr_embedder_destroy.restype = None
+    L.fr_embedder_destroy.argtypes = [C.c_void_p]
+    L.fr_embedder_mode.argtypes = [C.c_void_p]
+    L.fr_embedder_max_batch.argtypes = [C.c_void_p]
+    L.fr_embedder_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.fr_embedder_run_crops.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.fr_embedder_run_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.fr_embedder_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L._emb_bound = True
+
+
+class Embedder:
+    """ArcFaceIR50's network half (/root/reference src/arcface.cpp:21-103,131-148) on the GPU."""
+
+    def __init__(self, weights_path, max_batch: int = 32, device: int = 0):
+        _bind_embedder(lib())
+        h = C.c_void_p()
+        check(lib().fr_embedder_create(str(weights_path).encode(), max_batch, device, C.byref(h)))
+        self._h, self.device, self.max_batch = h, device, max_batch
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_embedder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def mode(self) -> int:
+        return int(lib().fr_embedder_mode(self._h))
+
+    def run(self, chw) -> np.ndarray:
+        """ArcFaceIR50::doInference(float*, float*, int): n x 3 x 112 x 112 f32 -> n x 512 f32 (host)"""
+        x = _f32(chw)
+        out = np.empty((x.shape[0], 512), np.float32)
+        check(lib().fr_embedder_run(self._h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def run_crops(self, crops_bgr_u8) -> np.ndarray:
+        x = np.ascontiguousarray(crops_bgr_u8, dtype=np.uint8)
+        out = np.empty((x.shape[0], 512), np.float32)
+        check(lib().fr_embedder_run_crops(self._h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def run_dev(self, chw_t, out_t, stream: int = 0) -> None:
+        check(lib().fr_embedder_run_dev(self._h, _ptr(chw_t), chw_t.shape[0], _ptr(out_t), C.c_void_p(stream)))
+
+    def trace(self, layer: int, batch: int) -> np.ndarray:
+        geo = [112, 56, 56, 56, 28, 28, 28, 28] + [14] * 14 + [7] * 3
+        ch = [64, 64, 64, 64, 128, 128, 128, 128] + [256] * 14 + [512] * 3
+        out = np.empty((batch, ch[layer], geo[layer], geo[layer]), np.float32)
+        n = C.c_int64()
+        check(lib().fr_embedder_trace(self._h, layer, _ptr(out), out.size, C.byref(n)))
+        assert n.value == out.size
+        return out

@@ -112,6 +112,33 @@ int fr_gallery_last_stats(const FrGallery *g, FrSearchStats *out);
 int fr_gallery_set_timing(FrGallery *g, int enable);
 int fr_gallery_scan_time(FrGallery *g, double *total_ms, int *launches);
 
+/* =====================================================================================
+ * Embedder  (replaces ArcFaceIR50's network half, src/arcface.{h,cpp})
+ * ===================================================================================== */
+typedef struct FrEmbedder FrEmbedder;
+#define FR_MODE_IR 0    /* IR_50    - the deployed model, conversion/arcface/torch2trt.py:4,21 */
+#define FR_MODE_IR_SE 1 /* IR_SE_50 - conversion/arcface/model_irse.py:217-222 */
+
+/* ArcFaceIR50::ArcFaceIR50 (src/arcface.cpp:21-43). weights_path takes the place of `engineFile`: a flat weight file written
+ * by tools/pack_weights.py; the mode (IR / IR_SE) is read from its header. A missing file fails with FR_ENOENT and the
+ * message "Cant find engine file" (src/arcface.cpp:67). max_batch = rec_maxBatchSize (any batch up to it may be run). */
+int fr_embedder_create(const char *weights_path, int max_batch, int device, FrEmbedder **out);
+void fr_embedder_destroy(FrEmbedder *e);
+int fr_embedder_mode(const FrEmbedder *e);
+int fr_embedder_max_batch(const FrEmbedder *e);
+
+/* ArcFaceIR50::doInference(float*, float*, int) (src/arcface.cpp:138-148): input batch x 3 x 112 x 112 f32 planar RGB
+ * normalised ((x-127.5)*0.0078125), output batch x 512 f32, unit L2 norm. Host buffers. */
+int fr_embedder_run(FrEmbedder *e, const float *chw, int batch, float *out512);
+/* preprocessFaces + doInference (src/arcface.cpp:116-129,138-148): aligned 112x112 u8 BGR HWC crops in (the /recognize path,
+ * src/app.cpp:243-287), embeddings out. Host buffers. */
+int fr_embedder_run_crops(FrEmbedder *e, const uint8_t *crops_bgr_u8, int batch, float *out512);
+/* device buffers, ordered after/before `stream` (cudaStream_t as void*, NULL = caller synchronises itself) */
+int fr_embedder_run_dev(FrEmbedder *e, const float *chw_dev, int batch, float *out512_dev, void *stream);
+/* per-layer trace hook for parity debugging: re-runs the last input up to `layer` (0 = input_layer, 1..24 = body units) and
+ * copies that activation as f32 NCHW into out (host, cap floats); *n_written = element count. */
+int fr_embedder_trace(FrEmbedder *e, int layer, float *out, int64_t cap, int64_t *n_written);
+
 #ifdef __cplusplus
 }
 #endif
