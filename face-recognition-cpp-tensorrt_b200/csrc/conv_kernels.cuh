@@ -28,7 +28,7 @@ constexpr int kConvThreads = 256;
 constexpr int kConvStages = 3;  // 3 x 32 KiB (BN = 128) leaves room for two CTAs per SM
 
 enum ConvOutMode { kOutNormal = 0, kOutPhaseSplit = 1 };
-enum ConvResMode { kResNone = 0, kResSame = 1, kResSubsample = 2 };
+enum ConvResMode { kResNone = 0, kResSame = 1, kResSubsample = 2, kResUpsample = 3 };
 
 struct ConvGemmParams {
     int P;             // output positions (GEMM rows)
@@ -42,7 +42,11 @@ struct ConvGemmParams {
     const float* bias;     // [cout] or null
     const float* prelu;    // [cout] or null : PReLU slopes applied after bias
     const __half* res;     // residual source or null
-    int res_mode;          // ConvResMode; kResSubsample: source geometry (2H, 2W) normal layout, read at (2r, 2c)
+    int res_mode;          // ConvResMode; kResSubsample: source geometry (2H, 2W), read at (2r, 2c);
+                           // kResUpsample: source geometry (H/2, W/2), read at (r/2, c/2) (nearest x2, FPN top-down add)
+    int relu;              // ReLU after bias (before the residual add)
+    int ld_out;            // row stride (channels) of out / out_bn / out_sub; 0 = cout. out may point into a channel slice
+    int ld_res;            // row stride of res; 0 = cout
     __half* out;           // [P_out, cout] fp16 or null
     int out_mode;          // ConvOutMode; kOutPhaseSplit: out geometry (H/2, W/2) x 4 phases
     long long out_phase_rows;  // rows between the phase maps of `out` (fixed at the handle's maximum batch)
@@ -163,6 +167,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int r = rem / Wp;
         const int c = rem - r * Wp;
         const bool valid = p < prm.P && r < prm.H && c < prm.W;
+        const int ldo = prm.ld_out ? prm.ld_out : prm.cout;
+        const int ldr = prm.ld_res ? prm.ld_res : prm.cout;
         // destinations
         size_t o_main = 0, o_sub = 0, o_res = 0;
         bool sub_ok = false;
@@ -184,6 +190,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             } else if (prm.res_mode == kResSubsample) {
                 const int W2p = 2 * prm.W + 1, H2pW2p = (2 * prm.H + 1) * W2p;
                 o_res = static_cast<size_t>(img) * H2pW2p + (2 * r) * W2p + 2 * c;
+            } else if (prm.res_mode == kResUpsample) {
+                const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                o_res = static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
             }
         }
         mbar_wait(acc_bar, 0);
@@ -213,8 +222,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * __ldg(prm.prelu + n + j);
             }
+            if (prm.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
             if (prm.res_mode != kResNone) {
-                const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * prm.cout + n);
+                const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * ldr + n);
                 const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
                 const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
                 const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
@@ -232,12 +245,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j) hp[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
             if (prm.out) {
-                uint4* dst = reinterpret_cast<uint4*>(prm.out + o_main * prm.cout + n);
+                uint4* dst = reinterpret_cast<uint4*>(prm.out + o_main * ldo + n);
                 dst[0] = pk[0];
                 dst[1] = pk[1];
             }
             if (sub_ok) {
-                uint4* dst = reinterpret_cast<uint4*>(prm.out_sub + o_sub * prm.cout + n);
+                uint4* dst = reinterpret_cast<uint4*>(prm.out_sub + o_sub * ldo + n);
                 dst[0] = pk[0];
                 dst[1] = pk[1];
             }
@@ -251,7 +264,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     hb[j] = __floats2half2_rn(fmaf(y.x, __ldg(prm.bn_s + n + 2 * j), __ldg(prm.bn_b + n + 2 * j)),
                                               fmaf(y.y, __ldg(prm.bn_s + n + 2 * j + 1), __ldg(prm.bn_b + n + 2 * j + 1)));
                 }
-                uint4* dst = reinterpret_cast<uint4*>(prm.out_bn + o_main * prm.cout + n);
+                uint4* dst = reinterpret_cast<uint4*>(prm.out_bn + o_main * ldo + n);
                 dst[0] = pb[0];
                 dst[1] = pb[1];
             }

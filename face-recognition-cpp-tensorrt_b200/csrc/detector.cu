@@ -1,0 +1,489 @@
+// RetinaFace mobile0.25 detector: host side of the C ABI ("Detector" section of include/fr_b200.h).
+// Replaces RetinaFace (/root/reference src/retinaface.{h,cpp}): preprocess (:106-136), the TensorRT engine (:138-145; network =
+// conversion/retina/models/{net,retinaface_trim,retinaface}.py) and postprocessing + nms (:154-271).
+//
+// Plan per batch: stem (u8 canvas -> 8ch, fused mean subtraction) -> 13 x { depthwise 3x3 ; pointwise 1x1 } -> FPN laterals
+// (the top-down nearest-x2 add is fused into the lateral's epilogue) + merges -> 3 x SSH -> one fused 64->32 head GEMM per level
+// -> bias + softmax + anchor-major scatter -> decode + NMS, one block per image. Convs with >= 64 input channels are
+// conv_gemm_kernel launches (tcgen05); the rest are the CUDA-core kernels of det_kernels.cuh.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "conv_kernels.cuh"
+#include "det_kernels.cuh"
+#include "weights.h"
+
+using namespace frb;
+
+namespace {
+
+struct DBuf {
+    __half* p = nullptr;
+    int C = 0;
+    Geo g{0, 0};
+    CUtensorMap tmap{};
+    bool has_map = false;
+};
+
+enum StepKind { kDw, kPwSmall, kGemm, kC16, kHeads };
+
+struct DStep {
+    StepKind kind;
+    // dw / pw_small / c16
+    const __half* in = nullptr;
+    __half* out = nullptr;
+    Geo gi{0, 0}, go{0, 0};
+    int stride = 1, cin = 0, cout = 0, ld_out = 0;
+    const float* w = nullptr;
+    const float* b = nullptr;
+    // gemm
+    CUtensorMap ta{}, tb{};
+    ConvGemmParams prm{};
+    int bn = 64;
+    // heads
+    const float* head = nullptr;
+    int level_offset = 0;
+};
+
+}  // namespace
+
+struct FrDetector {
+    int device = 0, sms = 0, kind = 0;
+    int net_h = 0, net_w = 0, frame_h = 0, frame_w = 0, max_batch = 0, max_faces = 0, anchors = 0;
+    float nms_thr = 0.4f, bbox_thr = 0.6f;
+    bool landmarks = false;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    float *stem_w = nullptr, *stem_b = nullptr;
+    uint8_t* frames_dev = nullptr;   // max_batch x frame_h x frame_w x 3
+    float* chw_dev = nullptr;        // fr_detector_net input
+    __half* a0 = nullptr;            // stem output
+    Geo g[6];
+    std::vector<DStep> steps;
+    float *loc = nullptr, *conf = nullptr, *landm = nullptr;
+    DetCand* cand = nullptr;
+    FrBbox* boxes = nullptr;
+    int* counts = nullptr;
+    float* out_landm = nullptr;
+    int* out_ids = nullptr;
+};
+
+namespace {
+
+template <class T>
+T* dalloc(FrDetector* d, size_t count, bool zero) {
+    T* p = nullptr;
+    FRB_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    d->allocs.push_back(p);
+    if (zero) FRB_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), d->stream));
+    return p;
+}
+template <class T>
+T* dupload(FrDetector* d, const HostTensor& t) {
+    T* p = dalloc<T>(d, static_cast<size_t>(t.numel()), false);
+    FRB_CUDA(cudaMemcpyAsync(p, t.data, t.nbytes, cudaMemcpyHostToDevice, d->stream));
+    return p;
+}
+
+DBuf mkbuf(FrDetector* d, Geo g, int C) {
+    DBuf b;
+    b.g = g;
+    b.C = C;
+    const size_t rows = static_cast<size_t>(d->max_batch) * g.HpWp();
+    b.p = dalloc<__half>(d, rows * C, true);  // pads are zeroed once and never written
+    if (C >= 64) {
+        b.tmap = make_tmap_2d_f16(b.p, rows, static_cast<uint64_t>(C), 128, 64);
+        b.has_map = true;
+    }
+    return b;
+}
+
+void build_plan(FrDetector* d, const WeightFile& wf) {
+    auto f32 = [&](const std::string& n, int64_t numel) { return dupload<float>(d, wf.get(n, 0, numel)); };
+    auto f16 = [&](const std::string& n, int64_t numel) { return dupload<__half>(d, wf.get(n, 1, numel)); };
+    const int B = d->max_batch;
+    for (int k = 1; k <= 5; ++k) d->g[k] = Geo{d->net_h >> k, d->net_w >> k};
+    d->stem_w = f32("stem.w", 8 * 27);
+    d->stem_b = f32("stem.b", 8);
+    d->frames_dev = dalloc<uint8_t>(d, static_cast<size_t>(B) * d->frame_h * d->frame_w * 3, false);
+    d->chw_dev = dalloc<float>(d, static_cast<size_t>(B) * 3 * d->net_h * d->net_w, false);
+
+    DBuf cur = mkbuf(d, d->g[1], 8);
+    d->a0 = cur.p;
+
+    auto add_gemm = [&](const DBuf& in, int cin, int taps, int cout, const std::string& wname, const std::string& bname, bool relu,
+                        __half* out, int ld_out, const __half* res, int res_mode, float* out_f32) {
+        DStep s{};
+        s.kind = kGemm;
+        s.bn = cout >= 128 ? 128 : cout;
+        __half* w = f16(wname, static_cast<int64_t>(cout) * taps * cin);
+        s.ta = in.tmap;
+        s.tb = make_tmap_2d_f16(w, cout, static_cast<uint64_t>(taps) * cin, s.bn, 64);
+        s.go = in.g;
+        s.prm.H = in.g.H;
+        s.prm.W = in.g.W;
+        s.prm.cin_blocks = cin / 64;
+        s.prm.taps = taps;
+        s.prm.cout = cout;
+        s.prm.kb_per_split = taps * (cin / 64);
+        if (out_f32) {
+            s.prm.partial = out_f32;
+        } else {
+            s.prm.bias = f32(bname, cout);
+            s.prm.relu = relu ? 1 : 0;
+            s.prm.out = out;
+            s.prm.ld_out = ld_out;
+            s.prm.res = res;
+            s.prm.res_mode = res_mode;
+            s.prm.ld_res = 64;
+        }
+        d->steps.push_back(s);
+    };
+
+    // ---- MobileNetV1-0.25 body (net.py:102-124): 13 conv_dw blocks
+    const int dw_cin[13] = {8, 16, 32, 32, 64, 64, 128, 128, 128, 128, 128, 128, 256};
+    const int dw_cout[13] = {16, 32, 32, 64, 64, 128, 128, 128, 128, 128, 128, 256, 256};
+    const int dw_stride[13] = {1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1};
+    int level = 1;
+    DBuf c1{}, c2{}, c3{};
+    for (int n = 0; n < 13; ++n) {
+        const std::string id = std::to_string(n + 1);
+        if (dw_stride[n] == 2) ++level;
+        DBuf dwo = mkbuf(d, d->g[level], dw_cin[n]);
+        DStep s{};
+        s.kind = kDw;
+        s.in = cur.p;
+        s.out = dwo.p;
+        s.gi = cur.g;
+        s.go = dwo.g;
+        s.stride = dw_stride[n];
+        s.cin = dw_cin[n];
+        s.w = f32("dw" + id + ".w", 9 * dw_cin[n]);
+        s.b = f32("dw" + id + ".b", dw_cin[n]);
+        d->steps.push_back(s);
+        DBuf pwo = mkbuf(d, d->g[level], dw_cout[n]);
+        if (dw_cin[n] >= 64) {
+            add_gemm(dwo, dw_cin[n], 1, dw_cout[n], "pw" + id + ".w", "pw" + id + ".b", true, pwo.p, 0, nullptr, kResNone, nullptr);
+        } else {
+            DStep p{};
+            p.kind = kPwSmall;
+            p.in = dwo.p;
+            p.out = pwo.p;
+            p.go = dwo.g;
+            p.cin = dw_cin[n];
+            p.cout = dw_cout[n];
+            p.w = f32("pw" + id + ".w", static_cast<int64_t>(dw_cin[n]) * dw_cout[n]);
+            p.b = f32("pw" + id + ".b", dw_cout[n]);
+            d->steps.push_back(p);
+        }
+        cur = pwo;
+        if (n == 4) c1 = cur;
+        if (n == 10) c2 = cur;
+        if (n == 12) c3 = cur;
+    }
+    // ---- FPN (net.py:68-98): laterals, top-down nearest x2 add fused into the lateral epilogue, 3x3 merges
+    DBuf o3 = mkbuf(d, d->g[5], 64), m2in = mkbuf(d, d->g[4], 64), o2 = mkbuf(d, d->g[4], 64), m1in = mkbuf(d, d->g[3], 64),
+         o1 = mkbuf(d, d->g[3], 64);
+    add_gemm(c3, 256, 1, 64, "fpn.output3.w", "fpn.output3.b", true, o3.p, 0, nullptr, kResNone, nullptr);
+    add_gemm(c2, 128, 1, 64, "fpn.output2.w", "fpn.output2.b", true, m2in.p, 0, o3.p, kResUpsample, nullptr);
+    add_gemm(m2in, 64, 9, 64, "fpn.merge2.w", "fpn.merge2.b", true, o2.p, 0, nullptr, kResNone, nullptr);
+    add_gemm(c1, 64, 1, 64, "fpn.output1.w", "fpn.output1.b", true, m1in.p, 0, o2.p, kResUpsample, nullptr);
+    add_gemm(m1in, 64, 9, 64, "fpn.merge1.w", "fpn.merge1.b", true, o1.p, 0, nullptr, kResNone, nullptr);
+    // ---- SSH x3 (net.py:40-66) + heads (retinaface_trim.py:89-99 / retinaface.py:37-46)
+    d->anchors = (d->g[3].H * d->g[3].W + d->g[4].H * d->g[4].W + d->g[5].H * d->g[5].W) * 2;
+    d->loc = dalloc<float>(d, static_cast<size_t>(B) * d->anchors * 4, false);
+    d->conf = dalloc<float>(d, static_cast<size_t>(B) * d->anchors * 2, false);
+    d->landm = d->landmarks ? dalloc<float>(d, static_cast<size_t>(B) * d->anchors * 10, false) : nullptr;
+    const DBuf* fpn[3] = {&o1, &o2, &o3};
+    int level_offset = 0;
+    for (int lvl = 1; lvl <= 3; ++lvl) {
+        const DBuf& x = *fpn[lvl - 1];
+        const std::string p = "ssh" + std::to_string(lvl) + ".";
+        DBuf F = mkbuf(d, x.g, 64), T = mkbuf(d, x.g, 16), U = mkbuf(d, x.g, 16);
+        add_gemm(x, 64, 9, 32, p + "a.w", p + "a.b", true, F.p, 64, nullptr, kResNone, nullptr);
+        add_gemm(x, 64, 9, 16, p + "t.w", p + "t.b", true, T.p, 16, nullptr, kResNone, nullptr);
+        const char* names[3] = {"b", "u", "c"};
+        const __half* ins[3] = {T.p, T.p, U.p};
+        __half* outs[3] = {F.p + 32, U.p, F.p + 48};
+        const int lds[3] = {64, 16, 64};
+        for (int q = 0; q < 3; ++q) {
+            DStep s{};
+            s.kind = kC16;
+            s.in = ins[q];
+            s.out = outs[q];
+            s.ld_out = lds[q];
+            s.go = x.g;
+            s.w = f32(p + names[q] + ".w", 9 * 16 * 16);
+            s.b = f32(p + names[q] + ".b", 16);
+            d->steps.push_back(s);
+        }
+        float* head = dalloc<float>(d, static_cast<size_t>(B) * x.g.HpWp() * 32, false);
+        add_gemm(F, 64, 1, 32, "head" + std::to_string(lvl) + ".w", "", false, nullptr, 0, nullptr, kResNone, head);
+        DStep h{};
+        h.kind = kHeads;
+        h.head = head;
+        h.b = f32("head" + std::to_string(lvl) + ".b", 32);
+        h.go = x.g;
+        h.level_offset = level_offset;
+        d->steps.push_back(h);
+        level_offset += x.g.H * x.g.W * 2;
+    }
+    d->cand = dalloc<DetCand>(d, static_cast<size_t>(B) * d->anchors, false);
+    d->boxes = dalloc<FrBbox>(d, static_cast<size_t>(B) * d->max_faces, true);
+    d->counts = dalloc<int>(d, B, true);
+    d->out_landm = dalloc<float>(d, static_cast<size_t>(B) * d->max_faces * 10, true);
+    d->out_ids = dalloc<int>(d, static_cast<size_t>(B) * d->max_faces, true);
+    FRB_CUDA(cudaStreamSynchronize(d->stream));
+}
+
+template <int BN>
+void launch_det_gemm(const DStep& s, int batch, cudaStream_t st) {
+    ConvGemmParams prm = s.prm;
+    prm.P = batch * s.go.HpWp();
+    dim3 grid((prm.P + kConvBM - 1) / kConvBM, prm.cout / BN, 1);
+    conv_gemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
+    count_launch();
+}
+
+inline int blocks_for(long long threads, int per_block) { return static_cast<int>((threads + per_block - 1) / per_block); }
+
+// network: canvas (u8, net size) or preprocessed f32 planar input -> loc / conf / landm on the device
+void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const float* chw_dev, int batch, cudaStream_t st) {
+    const Geo g1 = d->g[1];
+    const long long px = static_cast<long long>(batch) * g1.H * g1.W;
+    if (canvas_dev) det_stem_kernel<<<blocks_for(px, 256), 256, 0, st>>>(canvas_dev, stride_bytes, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
+    else det_stem_f32_kernel<<<blocks_for(px, 256), 256, 0, st>>>(chw_dev, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
+    count_launch();
+    for (const DStep& s : d->steps) {
+        switch (s.kind) {
+            case kDw: {
+                const long long t = static_cast<long long>(batch) * s.go.H * s.go.W * (s.cin / 8);
+                dw3x3_kernel<<<blocks_for(t, 256), 256, 0, st>>>(s.in, s.gi, s.out, s.go, s.stride, s.cin, batch, s.w, s.b);
+                count_launch();
+                break;
+            }
+            case kPwSmall: {
+                const long long t = static_cast<long long>(batch) * s.go.H * s.go.W;
+                const int nb = blocks_for(t, 128);
+                if (s.cin == 8 && s.cout == 16) pw_small_kernel<8, 16><<<nb, 128, 0, st>>>(s.in, s.out, s.go, batch, s.w, s.b);
+                else if (s.cin == 16 && s.cout == 32) pw_small_kernel<16, 32><<<nb, 128, 0, st>>>(s.in, s.out, s.go, batch, s.w, s.b);
+                else if (s.cin == 32 && s.cout == 32) pw_small_kernel<32, 32><<<nb, 128, 0, st>>>(s.in, s.out, s.go, batch, s.w, s.b);
+                else if (s.cin == 32 && s.cout == 64) pw_small_kernel<32, 64><<<nb, 128, 0, st>>>(s.in, s.out, s.go, batch, s.w, s.b);
+                else throw StateError{"unexpected pointwise shape"};
+                count_launch();
+                break;
+            }
+            case kGemm:
+                if (s.bn == 16) launch_det_gemm<16>(s, batch, st);
+                else if (s.bn == 32) launch_det_gemm<32>(s, batch, st);
+                else if (s.bn == 64) launch_det_gemm<64>(s, batch, st);
+                else launch_det_gemm<128>(s, batch, st);
+                break;
+            case kC16: {
+                const long long t = static_cast<long long>(batch) * s.go.H * s.go.W;
+                conv3x3_c16_kernel<<<blocks_for(t, 128), 128, 0, st>>>(s.in, s.out, s.ld_out, s.go, batch, s.w, s.b);
+                count_launch();
+                break;
+            }
+            case kHeads: {
+                const long long t = static_cast<long long>(batch) * s.go.H * s.go.W * 2;
+                det_heads_kernel<<<blocks_for(t, 256), 256, 0, st>>>(s.head, s.b, s.go, batch, d->anchors, s.level_offset, d->loc, d->conf, d->landm);
+                count_launch();
+                break;
+            }
+        }
+    }
+    FRB_CUDA(cudaGetLastError());
+}
+
+void run_post(FrDetector* d, const float* loc, const float* conf, const float* landm, int batch, cudaStream_t st) {
+    DetPostParams p;
+    p.net_w = d->net_w;
+    p.net_h = d->net_h;
+    p.frame_w = d->frame_w;
+    p.frame_h = d->frame_h;
+    p.nms_thr = d->nms_thr;
+    p.bbox_thr = d->bbox_thr;
+    p.max_faces = d->max_faces;
+    p.anchors = d->anchors;
+    det_decode_nms_kernel<<<batch, 256, 0, st>>>(loc, conf, landm, p, d->cand, d->boxes, d->counts, d->out_landm, d->out_ids);
+    count_launch();
+    FRB_CUDA(cudaGetLastError());
+}
+
+void check_det(const FrDetector* d, int batch) {
+    if (!d) throw ArgError{"null detector"};
+    if (batch < 1 || batch > d->max_batch) throw ArgError{"batch out of range (1..max_batch)"};
+}
+
+// frames (host or device) -> canvas on the device; returns the canvas pointer and its row stride
+const uint8_t* stage_frames(FrDetector* d, const uint8_t* frames, int stride, int batch, bool on_device, int* canvas_stride, cudaStream_t st) {
+    if (stride < d->frame_w * 3) throw ArgError{"stride smaller than frame_w * 3"};
+    if (d->frame_h != d->net_h || d->frame_w != d->net_w)
+        throw ArgError{"this build runs the detector at frame size == network input size (letterbox resize not built yet)"};
+    if (on_device) {
+        *canvas_stride = stride;
+        return frames;
+    }
+    FRB_CUDA(cudaMemcpy2DAsync(d->frames_dev, static_cast<size_t>(d->frame_w) * 3, frames, stride, static_cast<size_t>(d->frame_w) * 3,
+                               static_cast<size_t>(batch) * d->frame_h, cudaMemcpyHostToDevice, st));
+    *canvas_stride = d->frame_w * 3;
+    return d->frames_dev;
+}
+
+void copy_results(FrDetector* d, int batch, FrBbox* boxes, int* counts, float* landmarks, cudaStream_t st) {
+    FRB_CUDA(cudaMemcpyAsync(boxes, d->boxes, sizeof(FrBbox) * batch * d->max_faces, cudaMemcpyDeviceToHost, st));
+    FRB_CUDA(cudaMemcpyAsync(counts, d->counts, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    if (landmarks) FRB_CUDA(cudaMemcpyAsync(landmarks, d->out_landm, sizeof(float) * batch * d->max_faces * 10, cudaMemcpyDeviceToHost, st));
+    FRB_CUDA(cudaStreamSynchronize(st));
+}
+
+void copy_raw(FrDetector* d, int batch, float* loc, float* conf, float* landm, cudaStream_t st) {
+    const size_t a = static_cast<size_t>(batch) * d->anchors;
+    if (loc) FRB_CUDA(cudaMemcpyAsync(loc, d->loc, sizeof(float) * a * 4, cudaMemcpyDeviceToHost, st));
+    if (conf) FRB_CUDA(cudaMemcpyAsync(conf, d->conf, sizeof(float) * a * 2, cudaMemcpyDeviceToHost, st));
+    if (landm) {
+        if (!d->landm) throw StateError{"detector was created without the landmark head"};
+        FRB_CUDA(cudaMemcpyAsync(landm, d->landm, sizeof(float) * a * 10, cudaMemcpyDeviceToHost, st));
+    }
+    FRB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace
+
+extern "C" {
+
+int fr_detector_create(const char* weights_path, int net_h, int net_w, int frame_h, int frame_w, int max_batch, int max_faces, float nms_thr,
+                       float bbox_thr, int with_landmarks, int device, FrDetector** out) {
+    return guarded([&] {
+        if (!out) throw ArgError{"out is null"};
+        if (net_h < 32 || net_w < 32 || (net_h % 32) || (net_w % 32)) throw ArgError{"network input height/width must be positive multiples of 32"};
+        if (frame_h < 1 || frame_w < 1) throw ArgError{"bad frame size"};
+        if (max_batch < 1 || max_batch > 1024) throw ArgError{"max_batch out of range (1..1024)"};
+        if (max_faces < 1 || max_faces > 1024) throw ArgError{"max_faces out of range (1..1024)"};
+        WeightFile wf = load_weight_file(weights_path);
+        if (wf.kind != kKindRetinaTrim && wf.kind != kKindRetinaFull) throw FileError{FR_EFORMAT, "weight file is not a RetinaFace checkpoint"};
+        if (with_landmarks && wf.kind != kKindRetinaFull) throw FileError{FR_EFORMAT, "landmarks requested but the checkpoint has no landmark head"};
+        std::unique_ptr<FrDetector> d(new FrDetector());
+        d->sms = use_device(device);
+        d->device = device;
+        d->kind = wf.kind;
+        d->net_h = net_h;
+        d->net_w = net_w;
+        d->frame_h = frame_h;
+        d->frame_w = frame_w;
+        d->max_batch = max_batch;
+        d->max_faces = max_faces;
+        d->nms_thr = nms_thr;
+        d->bbox_thr = bbox_thr;
+        d->landmarks = with_landmarks != 0;
+        try {
+            FRB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<16>::kSmemBytes));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
+            build_plan(d.get(), wf);
+        } catch (...) {
+            fr_detector_destroy(d.release());
+            throw;
+        }
+        *out = d.release();
+    });
+}
+
+void fr_detector_destroy(FrDetector* d) {
+    if (!d) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    for (void* p : d->allocs) cudaFree(p);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete d;
+}
+
+int fr_detector_num_anchors(const FrDetector* d) { return d ? d->anchors : FR_EINVAL; }
+
+int fr_detector_run(FrDetector* d, const uint8_t* frames, int stride, int batch, FrBbox* boxes, int* counts, float* landmarks) {
+    return guarded([&] {
+        check_det(d, batch);
+        if (!frames || !boxes || !counts) throw ArgError{"null buffer"};
+        DeviceGuard dg(d->device);
+        int cs = 0;
+        const uint8_t* canvas = stage_frames(d, frames, stride, batch, false, &cs, d->stream);
+        run_net(d, canvas, cs, nullptr, batch, d->stream);
+        run_post(d, d->loc, d->conf, d->landm, batch, d->stream);
+        copy_results(d, batch, boxes, counts, landmarks, d->stream);
+    });
+}
+
+int fr_detector_raw(FrDetector* d, const uint8_t* frames, int stride, int batch, float* loc, float* conf, float* landm) {
+    return guarded([&] {
+        check_det(d, batch);
+        if (!frames) throw ArgError{"null buffer"};
+        DeviceGuard dg(d->device);
+        int cs = 0;
+        const uint8_t* canvas = stage_frames(d, frames, stride, batch, false, &cs, d->stream);
+        run_net(d, canvas, cs, nullptr, batch, d->stream);
+        copy_raw(d, batch, loc, conf, landm, d->stream);
+    });
+}
+
+int fr_detector_net(FrDetector* d, const float* chw, int batch, float* loc, float* conf, float* landm) {
+    return guarded([&] {
+        check_det(d, batch);
+        if (!chw) throw ArgError{"null buffer"};
+        DeviceGuard dg(d->device);
+        FRB_CUDA(cudaMemcpyAsync(d->chw_dev, chw, sizeof(float) * batch * 3 * d->net_h * d->net_w, cudaMemcpyHostToDevice, d->stream));
+        run_net(d, nullptr, 0, d->chw_dev, batch, d->stream);
+        copy_raw(d, batch, loc, conf, landm, d->stream);
+    });
+}
+
+int fr_detector_post(FrDetector* d, const float* loc, const float* conf, const float* landm, int batch, FrBbox* boxes, int* counts,
+                     float* landmarks) {
+    return guarded([&] {
+        check_det(d, batch);
+        if (!loc || !conf || !boxes || !counts) throw ArgError{"null buffer"};
+        DeviceGuard dg(d->device);
+        const size_t a = static_cast<size_t>(batch) * d->anchors;
+        FRB_CUDA(cudaMemcpyAsync(d->loc, loc, sizeof(float) * a * 4, cudaMemcpyHostToDevice, d->stream));
+        FRB_CUDA(cudaMemcpyAsync(d->conf, conf, sizeof(float) * a * 2, cudaMemcpyHostToDevice, d->stream));
+        float* lm_dev = nullptr;
+        if (landm) {
+            if (!d->landm) {
+                d->landm = dalloc<float>(d, static_cast<size_t>(d->max_batch) * d->anchors * 10, false);
+            }
+            lm_dev = d->landm;
+            FRB_CUDA(cudaMemcpyAsync(lm_dev, landm, sizeof(float) * a * 10, cudaMemcpyHostToDevice, d->stream));
+        }
+        run_post(d, d->loc, d->conf, lm_dev, batch, d->stream);
+        copy_results(d, batch, boxes, counts, landmarks, d->stream);
+    });
+}
+
+int fr_detector_run_dev(FrDetector* d, const uint8_t* frames_dev, int stride, int batch, FrBbox* boxes_dev, int* counts_dev,
+                        float* landmarks_dev, void* stream) {
+    return guarded([&] {
+        check_det(d, batch);
+        if (!frames_dev || !boxes_dev || !counts_dev) throw ArgError{"null buffer"};
+        DeviceGuard dg(d->device);
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
+        int cs = 0;
+        const uint8_t* canvas = stage_frames(d, frames_dev, stride, batch, true, &cs, st);
+        run_net(d, canvas, cs, nullptr, batch, st);
+        run_post(d, d->loc, d->conf, d->landm, batch, st);
+        FRB_CUDA(cudaMemcpyAsync(boxes_dev, d->boxes, sizeof(FrBbox) * batch * d->max_faces, cudaMemcpyDeviceToDevice, st));
+        FRB_CUDA(cudaMemcpyAsync(counts_dev, d->counts, sizeof(int) * batch, cudaMemcpyDeviceToDevice, st));
+        if (landmarks_dev)
+            FRB_CUDA(cudaMemcpyAsync(landmarks_dev, d->out_landm, sizeof(float) * batch * d->max_faces * 10, cudaMemcpyDeviceToDevice, st));
+    });
+}
+
+}  // extern "C"

@@ -249,3 +249,90 @@ class Embedder:
         check(lib().fr_embedder_trace(self._h, layer, _ptr(out), out.size, C.byref(n)))
         assert n.value == out.size
         return out
+
+
+def _bind_detector(L):
+    if getattr(L, "_det_bound", False):
+        return
+    L.fr_detector_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p)]
+    L.fr_detector_destroy.restype = None
+    L.fr_detector_destroy.argtypes = [C.c_void_p]
+    L.fr_detector_num_anchors.argtypes = [C.c_void_p]
+    L.fr_detector_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fr_detector_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fr_detector_net.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fr_detector_post.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fr_detector_run_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L._det_bound = True
+
+
+class Detector:
+    """RetinaFace (/root/reference src/retinaface.{h,cpp}) on the GPU. Boxes use the reference's Bbox semantics:
+    x = row (vertical), y = column (horizontal)."""
+
+    def __init__(self, weights_path, net_hw, frame_hw=None, max_batch=16, max_faces=4, nms_thr=0.4, bbox_thr=0.6, landmarks=False,
+                 device=0):
+        _bind_detector(lib())
+        frame_hw = frame_hw or net_hw
+        h = C.c_void_p()
+        check(lib().fr_detector_create(str(weights_path).encode(), net_hw[0], net_hw[1], frame_hw[0], frame_hw[1], max_batch, max_faces,
+                                       nms_thr, bbox_thr, int(landmarks), device, C.byref(h)))
+        self._h, self.device = h, device
+        self.net_hw, self.frame_hw, self.max_batch, self.max_faces, self.landmarks = tuple(net_hw), tuple(frame_hw), max_batch, max_faces, landmarks
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_detector_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def anchors(self) -> int:
+        return int(lib().fr_detector_num_anchors(self._h))
+
+    def _frames(self, frames):
+        f = np.ascontiguousarray(frames, dtype=np.uint8)
+        assert f.ndim == 4 and f.shape[1:] == (self.frame_hw[0], self.frame_hw[1], 3), f.shape
+        return f
+
+    def run(self, frames):
+        """findFace for a batch: -> (boxes structured array [n, max_faces], counts [n], landmarks [n, max_faces, 10] or None)"""
+        f = self._frames(frames)
+        n = f.shape[0]
+        boxes = np.zeros((n, self.max_faces), dtype=[("x1", "<i4"), ("y1", "<i4"), ("x2", "<i4"), ("y2", "<i4"), ("score", "<f4")])
+        counts = np.zeros(n, np.int32)
+        lm = np.zeros((n, self.max_faces, 10), np.float32) if self.landmarks else None
+        check(lib().fr_detector_run(self._h, _ptr(f), f.shape[2] * 3, n, _ptr(boxes), _ptr(counts), _ptr(lm)))
+        return boxes, counts, lm
+
+    def _raw_out(self, n):
+        a = self.anchors
+        return (np.empty((n, a, 4), np.float32), np.empty((n, a, 2), np.float32), np.empty((n, a, 10), np.float32) if self.landmarks else None)
+
+    def raw(self, frames):
+        f = self._frames(frames)
+        loc, conf, lm = self._raw_out(f.shape[0])
+        check(lib().fr_detector_raw(self._h, _ptr(f), f.shape[2] * 3, f.shape[0], _ptr(loc), _ptr(conf), _ptr(lm)))
+        return loc, conf, lm
+
+    def net(self, chw):
+        x = _f32(chw)
+        loc, conf, lm = self._raw_out(x.shape[0])
+        check(lib().fr_detector_net(self._h, _ptr(x), x.shape[0], _ptr(loc), _ptr(conf), _ptr(lm)))
+        return loc, conf, lm
+
+    def post(self, loc, conf, landm=None):
+        loc, conf = _f32(loc), _f32(conf)
+        n = loc.shape[0]
+        lm_in = _f32(landm) if landm is not None else None
+        boxes = np.zeros((n, self.max_faces), dtype=[("x1", "<i4"), ("y1", "<i4"), ("x2", "<i4"), ("y2", "<i4"), ("score", "<f4")])
+        counts = np.zeros(n, np.int32)
+        lm = np.zeros((n, self.max_faces, 10), np.float32)
+        check(lib().fr_detector_post(self._h, _ptr(loc), _ptr(conf), _ptr(lm_in), n, _ptr(boxes), _ptr(counts), _ptr(lm)))
+        return boxes, counts, lm

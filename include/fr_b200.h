@@ -139,6 +139,43 @@ int fr_embedder_run_dev(FrEmbedder *e, const float *chw_dev, int batch, float *o
  * copies that activation as f32 NCHW into out (host, cap floats); *n_written = element count. */
 int fr_embedder_trace(FrEmbedder *e, int layer, float *out, int64_t cap, int64_t *n_written);
 
+/* =====================================================================================
+ * Detector  (replaces RetinaFace, src/retinaface.{h,cpp})
+ * ===================================================================================== */
+typedef struct FrDetector FrDetector;
+
+/* RetinaFace::RetinaFace (src/retinaface.cpp:3-29). weights_path takes the place of `engineFile`: a flat weight file written
+ * by tools/pack_weights.py (FR_ENOENT + "Cant find engine file" when missing, src/retinaface.cpp:53). net_h / net_w =
+ * det_inputShape[1..2] (multiples of 32); frame_h / frame_w = input_frameHeight / Width; max_faces = det_maxFacesPerScene;
+ * nms_thr / bbox_thr = det_threshold_nms / det_threshold_bbox. with_landmarks != 0 also evaluates the landmark head of
+ * conversion/retina/models/retinaface.py:37-46 (absent from the deployed trimmed model; needs a "full" checkpoint). */
+int fr_detector_create(const char *weights_path, int net_h, int net_w, int frame_h, int frame_w, int max_batch, int max_faces,
+                       float nms_thr, float bbox_thr, int with_landmarks, int device, FrDetector **out);
+void fr_detector_destroy(FrDetector *d);
+/* m_OUTPUT_SIZE_BASE (src/retinaface.cpp:13): anchors per image */
+int fr_detector_num_anchors(const FrDetector *d);
+
+/* RetinaFace::findFace (src/retinaface.cpp:147-152) for `batch` frames: preprocess (:106-136), network (:138-145),
+ * decode + threshold + sort + NMS + cap (:154-208, :248-271). frames: batch images, u8 HWC BGR, frame_h x frame_w, `stride`
+ * bytes per row, images contiguous (image b starts at b * frame_h * stride); host memory. boxes: batch x max_faces (Bbox
+ * semantics: x = row, y = column); counts: batch. landmarks (optional, may be NULL): batch x max_faces x 10 floats, (column,
+ * row) pairs in frame pixels — an extension, the reference decodes no landmarks. */
+int fr_detector_run(FrDetector *d, const uint8_t *frames, int stride, int batch, FrBbox *boxes, int *counts, float *landmarks);
+/* Parity hook at the network boundary (the tensors RetinaFace::doInference returns, src/retinaface.cpp:138-145):
+ * loc: batch x A x 4, conf: batch x A x 2 (softmax), landm: batch x A x 10 or NULL. Host memory. */
+int fr_detector_raw(FrDetector *d, const uint8_t *frames, int stride, int batch, float *loc, float *conf, float *landm);
+/* Parity hook for the network alone: input already preprocessed, f32 planar CHW (B,G,R planes, mean subtracted), exactly the
+ * tensor RetinaFace::preprocess produces (src/retinaface.cpp:128-135). */
+int fr_detector_net(FrDetector *d, const float *chw, int batch, float *loc, float *conf, float *landm);
+/* Parity hook for decode + NMS alone (RetinaFace::postprocessing, src/retinaface.cpp:154-208) on caller-provided head
+ * outputs (host). */
+int fr_detector_post(FrDetector *d, const float *loc, const float *conf, const float *landm, int batch, FrBbox *boxes, int *counts,
+                     float *landmarks);
+/* device-resident variant used by the end-to-end pipeline: frames and outputs on the detector's device, launched on `stream`
+ * (cudaStream_t as void*, NULL = the handle's own stream); does not synchronise. */
+int fr_detector_run_dev(FrDetector *d, const uint8_t *frames_dev, int stride, int batch, FrBbox *boxes_dev, int *counts_dev,
+                        float *landmarks_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
