@@ -355,6 +355,26 @@ void copy_raw(FrDetector* d, int batch, float* loc, float* conf, float* landm, c
 
 }  // namespace
 
+// internal hooks for the end-to-end pipeline (csrc/pipeline.cu)
+namespace frb {
+void detector_forward_dev(FrDetector* d, const uint8_t* frames_dev, int stride, int batch, cudaStream_t st) {
+    int cs = 0;
+    const uint8_t* canvas = stage_frames(d, frames_dev, stride, batch, true, &cs, st);
+    run_net(d, canvas, cs, nullptr, batch, st);
+    run_post(d, d->loc, d->conf, d->landm, batch, st);
+}
+uint8_t* detector_frames_buffer(FrDetector* d) { return d->frames_dev; }
+const FrBbox* detector_boxes(const FrDetector* d) { return d->boxes; }
+const int* detector_counts(const FrDetector* d) { return d->counts; }
+void detector_dims(const FrDetector* d, int* frame_h, int* frame_w, int* max_batch, int* max_faces, int* device) {
+    *frame_h = d->frame_h;
+    *frame_w = d->frame_w;
+    *max_batch = d->max_batch;
+    *max_faces = d->max_faces;
+    *device = d->device;
+}
+}  // namespace frb
+
 extern "C" {
 
 int fr_detector_create(const char* weights_path, int net_h, int net_w, int frame_h, int frame_w, int max_batch, int max_faces, float nms_thr,

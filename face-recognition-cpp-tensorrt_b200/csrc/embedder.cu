@@ -123,8 +123,8 @@ void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
     count_launch();
 }
 
-void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit) {
-    cudaStream_t st = e->stream;
+void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cudaStream_t st = nullptr) {
+    if (!st) st = e->stream;
     const long long pixels = static_cast<long long>(batch) * 112 * 112;
     const int blocks = static_cast<int>((pixels + 127) / 128);
     if (u8_input)
@@ -394,6 +394,19 @@ void check_batch(const FrEmbedder* e, const void* in, int batch, const void* out
 }
 
 }  // namespace
+
+// internal hooks for the end-to-end pipeline (csrc/pipeline.cu): crops are written straight into the embedder's u8 input
+namespace frb {
+uint8_t* embedder_u8_input(FrEmbedder* e) { return e->in_u8; }
+float* embedder_output(FrEmbedder* e) { return e->out_dev; }
+int embedder_max_batch(const FrEmbedder* e) { return e->max_batch; }
+int embedder_device(const FrEmbedder* e) { return e->device; }
+void embedder_forward_u8(FrEmbedder* e, int batch, cudaStream_t st) {
+    e->last_batch = batch;
+    e->last_u8 = true;
+    run_steps(e, batch, true, kRunAll, st);
+}
+}  // namespace frb
 
 extern "C" {
 

@@ -336,3 +336,64 @@ class Detector:
         lm = np.zeros((n, self.max_faces, 10), np.float32)
         check(lib().fr_detector_post(self._h, _ptr(loc), _ptr(conf), _ptr(lm_in), n, _ptr(boxes), _ptr(counts), _ptr(lm)))
         return boxes, counts, lm
+
+
+BOX_DTYPE = np.dtype([("x1", "<i4"), ("y1", "<i4"), ("x2", "<i4"), ("y2", "<i4"), ("score", "<f4")])
+
+
+def embed_boxes(emb: "Embedder", frame_bgr_u8, boxes, want_crops: bool = False):
+    """ArcFaceIR50::forward for one frame (/root/reference src/arcface.cpp:166-187): boxes = structured BOX_DTYPE array"""
+    L = lib()
+    L.fr_embedder_run_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    f = np.ascontiguousarray(frame_bgr_u8, dtype=np.uint8)
+    b = np.ascontiguousarray(boxes, dtype=BOX_DTYPE)
+    n = b.shape[0]
+    out = np.empty((n, 512), np.float32)
+    crops = np.empty((n, 112, 112, 3), np.uint8) if want_crops else None
+    check(L.fr_embedder_run_boxes(emb._h, _ptr(f), f.shape[0], f.shape[1], f.shape[1] * 3, _ptr(b), n, _ptr(out), _ptr(crops)))
+    return (out, crops) if want_crops else out
+
+
+class Pipeline:
+    """detect -> crop -> embed -> search on one GPU (/root/reference src/app.cpp:293-352 without the socket glue)"""
+
+    def __init__(self, det: "Detector", emb: "Embedder", gal: "Gallery | None"):
+        L = lib()
+        L.fr_pipeline_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.fr_pipeline_destroy.restype = None
+        L.fr_pipeline_destroy.argtypes = [C.c_void_p]
+        L.fr_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        h = C.c_void_p()
+        check(L.fr_pipeline_create(det._h, emb._h, gal._h if gal is not None else None, C.byref(h)))
+        self._h, self.det, self.emb, self.gal = h, det, emb, gal
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, frames, want_embeddings: bool = False, out=None):
+        """frames: n x H x W x 3 u8 (numpy, or a pinned torch tensor) -> dict(boxes, counts, idx, score[, embeddings])"""
+        if isinstance(frames, np.ndarray):
+            f = np.ascontiguousarray(frames, dtype=np.uint8)
+            n, w = f.shape[0], f.shape[2]
+        else:
+            f, n, w = frames, frames.shape[0], frames.shape[2]
+        mf = self.det.max_faces
+        o = out or {}
+        boxes = o.get("boxes") if out else np.zeros((n, mf), BOX_DTYPE)
+        counts = o.get("counts") if out else np.zeros(n, np.int32)
+        idx = o.get("idx") if out else np.zeros((n, mf), np.int64)
+        score = o.get("score") if out else np.zeros((n, mf), np.float32)
+        emb = np.zeros((n, mf, 512), np.float32) if want_embeddings else None
+        check(lib().fr_pipeline_run(self._h, _ptr(f), w * 3, n, _ptr(boxes), _ptr(counts), _ptr(idx), _ptr(score), _ptr(emb)))
+        res = {"boxes": boxes, "counts": counts, "idx": idx, "score": score}
+        if want_embeddings:
+            res["embeddings"] = emb
+        return res

@@ -176,6 +176,28 @@ int fr_detector_post(FrDetector *d, const float *loc, const float *conf, const f
 int fr_detector_run_dev(FrDetector *d, const uint8_t *frames_dev, int stride, int batch, FrBbox *boxes_dev, int *counts_dev,
                         float *landmarks_dev, void *stream);
 
+/* getCroppedFaces + preprocessFaces + doInference (src/arcface.cpp:3-17,116-129,131-148) for caller-provided boxes of ONE frame
+ * (= ArcFaceIR50::forward, src/arcface.cpp:166-187): frame u8 HWC BGR (frame_h x frame_w, stride bytes/row), n boxes with Bbox
+ * semantics (ROI = Rect(Point(y1,x1), Point(y2,x2)) = rows [x1,x2), columns [y1,y2)), bicubic resize to 112x112 on the GPU,
+ * BGR->RGB, normalise, embed. Row i of out512 = embedding of box i (the reference's chunk-offset bug, src/arcface.cpp:184, is not
+ * reproduced). crops_u8 (optional): n x 112 x 112 x 3 BGR u8 crops (= CroppedFace::face). Host buffers. */
+int fr_embedder_run_boxes(FrEmbedder *e, const uint8_t *frame, int frame_h, int frame_w, int stride, const FrBbox *boxes, int n,
+                          float *out512, uint8_t *crops_u8);
+
+/* =====================================================================================
+ * End-to-end pipeline: detect -> crop/resize -> embed -> search on one GPU
+ * (the body of the /inference handler, src/app.cpp:293-352, without the socket/JPEG glue)
+ * ===================================================================================== */
+typedef struct FrPipeline FrPipeline;
+/* The pipeline borrows the three handles (they must outlive it and live on the same device); gal may be NULL (no matching). */
+int fr_pipeline_create(FrDetector *det, FrEmbedder *emb, FrGallery *gal, FrPipeline **out);
+void fr_pipeline_destroy(FrPipeline *p);
+/* frames: batch x frame_h x frame_w x 3 u8 BGR host (pinned or pageable), `stride` bytes per row. Outputs per frame f and face
+ * slot j < max_faces: boxes[f*max_faces+j] (valid for j < counts[f]), top1_idx / top1_score [f*max_faces+j] (idx = -1 for empty
+ * slots or when there is no gallery), embeddings (optional) [f*max_faces+j][512]. */
+int fr_pipeline_run(FrPipeline *p, const uint8_t *frames, int stride, int batch, FrBbox *boxes, int *counts, int64_t *top1_idx,
+                    float *top1_score, float *embeddings);
+
 #ifdef __cplusplus
 }
 #endif

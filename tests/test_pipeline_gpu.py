@@ -1,0 +1,115 @@
+"""GPU: the glue between detector and embedder (getCroppedFaces, /root/reference src/arcface.cpp:3-17) and the end-to-end
+pipeline detect -> crop -> embed -> search (src/app.cpp:293-352) against the chained oracles.
+  crops       vs cv2.resize(INTER_CUBIC) (the OpenCV in this image, 4.13): |d| <= 1 LSB and < 0.5 % of the pixels differ
+  embeddings  of GPU crops vs the fp32 oracle on cv2 crops: |d| <= 2e-3 (1e-3 network budget + the <= 1 LSB crop budget)
+  identities  top-1 index exact for every detected face (gallery rows planted from the oracle's embeddings)
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import frb200
+from oracle import arcface_oracle as ao
+from oracle import retina_oracle as ro
+from oracle import search_oracle as so
+from oracle import synth_weights as sw
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from tools import make_golden_retina as mgr  # noqa: E402
+from tools import pack_retina as pr  # noqa: E402
+from tools import pack_weights as pw  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def cv2_crops(frame, boxes):
+    """getCroppedFaces restated with cv2 (src/arcface.cpp:5-10): Rect(Point(y1,x1), Point(y2,x2)) -> resize to 112x112, INTER_CUBIC"""
+    import cv2
+
+    out = []
+    for b in boxes:
+        r0, r1 = sorted((int(b["x1"]), int(b["x2"])))
+        c0, c1 = sorted((int(b["y1"]), int(b["y2"])))
+        roi = frame[r0:max(r1, r0 + 1), c0:max(c1, c0 + 1)]
+        out.append(cv2.resize(roi, (112, 112), interpolation=cv2.INTER_CUBIC))
+    return np.stack(out)
+
+
+@pytest.fixture(scope="module")
+def nets(tmp_path_factory):
+    d = tmp_path_factory.mktemp("e2e")
+    det_sd = sw.retina_state_dict(False, 11, mgr.DET_CLS_SHIFT)
+    arc_sd = sw.arcface_state_dict("ir_se", 7)
+    pr.save_retina(d / "det.frw", det_sd, False)
+    pw.save_arcface(d / "arc.frw", arc_sd, "ir_se")
+    det = frb200.Detector(d / "det.frw", (640, 640), max_batch=8, max_faces=4)
+    emb = frb200.Embedder(d / "arc.frw", max_batch=16)
+    yield det, emb, arc_sd
+    det.close()
+    emb.close()
+
+
+def test_crop_resize_matches_opencv_bicubic(nets):
+    det, emb, arc_sd = nets
+    rng = np.random.default_rng(5)
+    frame = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    boxes = np.zeros(7, frb200.BOX_DTYPE)
+    for i, (x1, y1, x2, y2) in enumerate([(10, 20, 35, 46), (0, 0, 112, 112), (100, 300, 300, 450), (470, 600, 479, 639), (5, 5, 6, 6),
+                                          (200, 100, 260, 147), (0, 0, 479, 639)]):
+        boxes[i] = (x1, y1, x2, y2, 0.9)
+    out, crops = frb200.embed_boxes(emb, frame, boxes, want_crops=True)
+    want = cv2_crops(frame, boxes)
+    d = np.abs(crops.astype(int) - want.astype(int))
+    frac = float((d > 0).mean())
+    print(f"crop vs cv2: max |d| = {d.max()}, differing pixels = {frac:.4%}")
+    assert d.max() <= 1 and frac < 5e-3
+    assert np.array_equal(crops[1], frame[0:112, 0:112])  # 112x112 ROI: identity resize
+    # embeddings of the GPU crops == embeddings of the same crops fed as u8 (bitwise), and close to the oracle on cv2 crops
+    again = emb.run_crops(crops)
+    assert np.array_equal(again.view(np.uint32), out.view(np.uint32))
+    ref = ao.forward(ao.to_torch(arc_sd), torch.from_numpy(ao.preprocess_faces(want[:3])), "ir_se").numpy()
+    assert np.abs(out[:3] - ref).max() <= 2e-3
+
+
+def test_end_to_end_identities(nets):
+    det, emb, arc_sd = nets
+    frames = mgr.det_frames(6, 640, 640, seed=13)
+    # oracle chain on the GPU detector's boxes: cv2 crops -> fp32 embeddings; plant them (noisy) into a gallery
+    boxes, counts, _ = det.run(frames)
+    assert counts.tolist() == [4] * 6
+    oracle_emb = []
+    for f in range(2):
+        crops = cv2_crops(frames[f], boxes[f, : counts[f]])
+        oracle_emb.append(ao.forward(ao.to_torch(arc_sd), torch.from_numpy(ao.preprocess_faces(crops)), "ir_se").numpy())
+    oracle_emb = np.concatenate(oracle_emb)  # 8 faces of frames 0 and 1
+    n_gal = 50_000
+    G = so.synth_rows(np.arange(n_gal), seed=17)
+    planted = np.array([11, 4097, 20_000, 33_333, 49_999, 256, 255, 7])
+    G[planted] = so.planted_queries(oracle_emb, noise=0.3, seed=3)
+    gal = frb200.Gallery.from_rows(G)
+    pipe = frb200.Pipeline(det, emb, gal)
+    res = pipe.run(frames, want_embeddings=True)
+    assert np.array_equal(res["counts"], counts) and np.array_equal(res["boxes"], boxes)
+    got_emb = res["embeddings"][:2].reshape(8, 512)
+    assert np.abs(got_emb - oracle_emb).max() <= 2e-3
+    # identities: exact, and equal to the oracle's search on the oracle's embeddings
+    want_idx, want_score = so.get_outputs(so.sims(G, oracle_emb))
+    assert np.array_equal(want_idx, planted)
+    assert np.array_equal(res["idx"][:2].reshape(-1), planted)
+    assert np.abs(res["score"][:2].reshape(-1) - want_score).max() <= 2e-3
+    # the remaining frames: the pipeline's own embeddings searched by the oracle give the same identities
+    e_all = res["embeddings"].reshape(-1, 512)
+    oi, ov = so.get_outputs(so.sims(G, e_all))
+    assert np.array_equal(res["idx"].reshape(-1), oi)
+    assert np.abs(res["score"].reshape(-1) - ov).max() <= 1e-5
+    # no gallery: idx = -1
+    pipe2 = frb200.Pipeline(det, emb, None)
+    r2 = pipe2.run(frames[:1])
+    assert np.all(r2["idx"] == -1) and r2["counts"][0] == 4
+    pipe.close()
+    pipe2.close()
+    gal.close()
