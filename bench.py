@@ -180,6 +180,13 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_pipeline:
+        try:
+            from tools import bench_pipeline as bp
+
+            line["cpu_baseline"]["pipeline"] = bp.run_cpu()
+        except Exception as e:
+            line["cpu_baseline"]["pipeline"] = {"error": f"{type(e).__name__}: {e}"}
     rg = ref_gpu_search(args.queries, min(args.rows, 1_000_000), reps=3)
     if rg:
         line["ref_gpu"] = rg
@@ -196,6 +203,7 @@ def main():
     ap.add_argument("--queries", type=int, default=256)
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the detect->embed->search faces/sec section")
     ap.add_argument("--ramp-s", type=float, default=1.0, help="untimed busy period before the timed region (clock ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -382,6 +390,17 @@ def main():
             rg = ref_gpu_search(Q, min(N, 1_000_000), reps=3)
             if rg:
                 line["ref_gpu"] = rg
+        if n_gpus == 1 and not args.no_pipeline:
+            # second half of BASELINE.json's metric: faces/sec end-to-end on 640x640 frames (configs[1..3]), one GPU
+            try:
+                from tools import bench_pipeline as bp
+
+                gal.close()
+                line["pipeline"] = bp.run_gpu(local, hbm_gbs=hbm_peak, tf_sust=tf_sust)
+                if not args.no_cpu_baseline:
+                    line["cpu_baseline"]["pipeline"] = bp.run_cpu()
+            except Exception as e:  # the search line above stands on its own
+                line["pipeline"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     gal.close()
     if n_gpus > 1:

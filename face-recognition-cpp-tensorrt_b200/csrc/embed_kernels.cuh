@@ -102,22 +102,23 @@ __global__ void __launch_bounds__(128) arcface_stem_kernel(const void* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// SEModule gate (model_irse.py:22-45): gate[img][c] = sigmoid(fc2 · relu(fc1 · mean_hw(u[img]))). One block per image.
+// SEModule gate (model_irse.py:22-45): gate[img][c] = sigmoid(fc2 · relu(fc1 · mean_hw(u[img]))).
 // u: [batch * HpWp, C] fp16 with zero pads, so the sum over all HpWp positions is the sum over the H*W pixels.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) se_gate_kernel(const __half* __restrict__ u, int HpWp, int HW, int C, const float* __restrict__ fc1,
-                                                      const float* __restrict__ fc2, float* __restrict__ gate) {
+constexpr int kSeChunks = 16;  // position slices per image: the pooled sum is formed in two fixed-order stages (deterministic)
+// stage 1: pool[(img * kSeChunks + chunk) * C + c] = sum of u over the chunk's positions. grid (batch, kSeChunks).
+__global__ void __launch_bounds__(256) se_pool_kernel(const __half* __restrict__ u, int HpWp, int C, float* __restrict__ pool) {
     __shared__ float part[256 * 2];
-    __shared__ float mean[512];
-    __shared__ float hid[32];
-    const int img = blockIdx.x;
+    const int img = blockIdx.x, chunk = blockIdx.y;
     const int lanes = C / 2;             // threads covering one position (2 channels each)
     const int groups = 256 / lanes;      // position groups (C = 512 -> 1, C = 64 -> 8)
     const int cpair = threadIdx.x % lanes, grp = threadIdx.x / lanes;
+    const int len = (HpWp + kSeChunks - 1) / kSeChunks;
+    const int beg = chunk * len, end = min(HpWp, beg + len);
     float sx = 0.f, sy = 0.f;
     if (grp < groups) {
         const __half2* base = reinterpret_cast<const __half2*>(u + static_cast<size_t>(img) * HpWp * C) + cpair;
-        for (int pos = grp; pos < HpWp; pos += groups) {
+        for (int pos = beg + grp; pos < end; pos += groups) {
             const float2 v = __half22float2(base[static_cast<size_t>(pos) * lanes]);
             sx += v.x;
             sy += v.y;
@@ -129,6 +130,18 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const __half* __restrict__
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
         for (int g = 0; g < groups; ++g) s += part[(g * lanes + (c >> 1)) * 2 + (c & 1)];
+        pool[(static_cast<size_t>(img) * kSeChunks + chunk) * C + c] = s;
+    }
+}
+// stage 2: one block per image
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool, int HW, int C, const float* __restrict__ fc1,
+                                                      const float* __restrict__ fc2, float* __restrict__ gate) {
+    __shared__ float mean[512];
+    __shared__ float hid[32];
+    const int img = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < kSeChunks; ++k) s += pool[(static_cast<size_t>(img) * kSeChunks + k) * C + c];
         mean[c] = s / static_cast<float>(HW);
     }
     __syncthreads();

@@ -78,6 +78,7 @@ struct FrEmbedder {
     float* in_f32 = nullptr;         // max_batch x 3 x 112 x 112
     uint8_t* in_u8 = nullptr;        // max_batch x 112 x 112 x 3
     float* gate = nullptr;           // max_batch x 512
+    float* se_pool = nullptr;        // max_batch x kSeChunks x 512
     float* fc_partial = nullptr;     // kFcSplits x max_batch x 512
     float* fc_bias = nullptr;
     float* out_dev = nullptr;        // max_batch x 512
@@ -148,11 +149,12 @@ void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cud
         } else {
             const SeStep& q = s.se;
             const int H = kGeo[q.geo], P = batch * hpwp(q.geo);
-            se_gate_kernel<<<batch, 256, 0, st>>>(q.u, hpwp(q.geo), H * H, q.C, q.fc1, q.fc2, e->gate);
+            se_pool_kernel<<<dim3(batch, kSeChunks), 256, 0, st>>>(q.u, hpwp(q.geo), q.C, e->se_pool);
+            se_gate_kernel<<<batch, 256, 0, st>>>(e->se_pool, H * H, q.C, q.fc1, q.fc2, e->gate);
             const long long threads = static_cast<long long>(P) * (q.C / 8);
             se_apply_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(q.u, e->gate, P, H, H, q.C, q.res, q.res_mode, q.y, q.y_bn,
                                                                                     q.bn_s, q.bn_b, q.y_sub);
-            count_launch(2);
+            count_launch(3);
         }
     }
     if (stop_after_unit == kRunAll) {
@@ -174,6 +176,7 @@ void build_plan(FrEmbedder* e, const WeightFile& wf) {
     e->in_f32 = dev_alloc<float>(e, static_cast<size_t>(B) * 3 * 112 * 112, false);
     e->in_u8 = dev_alloc<uint8_t>(e, static_cast<size_t>(B) * 112 * 112 * 3, false);
     e->gate = dev_alloc<float>(e, static_cast<size_t>(B) * 512, false);
+    e->se_pool = dev_alloc<float>(e, static_cast<size_t>(B) * kSeChunks * 512, false);
     e->fc_partial = dev_alloc<float>(e, static_cast<size_t>(kFcSplits) * B * 512, false);
     e->out_dev = dev_alloc<float>(e, static_cast<size_t>(B) * 512, false);
     e->stem_y = make_buf(e, static_cast<size_t>(B) * hpwp(0), 64);
