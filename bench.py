@@ -231,8 +231,10 @@ def main():
     n_gpus = world
 
     N, Q, K = args.rows, args.queries, 1
+    import sharding
+
     per = (N + n_gpus - 1) // n_gpus
-    lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
+    lo, hi = sharding.shard_bounds(N, n_gpus, rank)
     gal = frb200.Gallery.synthetic(hi - lo, seed=GALLERY_SEED, device=local, row_offset=lo)
     gal.set_path(frb200.FR_PATH_TENSOR)
 
@@ -265,8 +267,7 @@ def main():
             gal.topk_dev(q_dev, K, out_s, out_i, stream=sraw)
         else:
             gal.topk_dev(q_dev, K, loc_s, loc_i, stream=sraw)
-            dist.all_gather_into_tensor(all_s, loc_s)
-            dist.all_gather_into_tensor(all_i, loc_i)
+            sharding.all_gather_topk(dist, loc_s, loc_i, all_s, all_i)
             frb200.topk_merge_dev(all_s, all_i, n_gpus, Q, K, out_s, out_i, local, stream=sraw)
 
     def e2e_step():
