@@ -312,7 +312,7 @@ def main():
     # is captured once into a CUDA graph and replayed; the eager pass after it (with the library's event pairs around the fused
     # scan kernel) feeds the roofline. --no-graph times the eager launches instead.
     graph, graph_note = None, None
-    if not args.no_graph:
+    if not args.no_graph and n_gpus == 1:  # NCCL collectives stay eager: capturing them across ranks hung on this stack
         try:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
