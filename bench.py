@@ -203,6 +203,8 @@ def main():
     ap.add_argument("--queries", type=int, default=256)
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: fused peer-memory exchange+merge kernel (default) or NCCL all-gather + merge kernel")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the detect->embed->search faces/sec section")
     ap.add_argument("--ramp-s", type=float, default=1.0, help="untimed busy period before the timed region (clock ramp)")
@@ -262,10 +264,23 @@ def main():
     sraw = stream.cuda_stream
     assert sraw != 0
 
+    exchange = None
+    if n_gpus > 1 and args.exchange == "p2p":
+        exchange = frb200.Exchange(local, n_gpus, rank, nq_max=Q, k_max=K)
+        mine = torch.from_numpy(exchange.local_handle()).to(dev)
+        allh = torch.empty((n_gpus, mine.numel()), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh.view(-1), mine)      # setup only: the 64-byte IPC handles of the mailboxes
+        exchange.connect(allh.cpu().numpy())
+        dist.barrier()
+
     def search_step():
         """device-resident hot path: fused scan + re-score on this shard, then the cross-GPU exchange + merge"""
         if n_gpus == 1:
             gal.topk_dev(q_dev, K, out_s, out_i, stream=sraw)
+        elif exchange is not None:
+            # fused exchange + merge over NVLink peer memory: no NCCL call, no host sync in the step
+            gal.topk_dev(q_dev, K, loc_s, loc_i, stream=sraw)
+            exchange.merge_dev(loc_s, loc_i, out_s, out_i, stream=sraw)
         else:
             gal.topk_dev(q_dev, K, loc_s, loc_i, stream=sraw)
             sharding.all_gather_topk(dist, loc_s, loc_i, all_s, all_i)
@@ -312,7 +327,7 @@ def main():
     # is captured once into a CUDA graph and replayed; the eager pass after it (with the library's event pairs around the fused
     # scan kernel) feeds the roofline. --no-graph times the eager launches instead.
     graph, graph_note = None, None
-    if not args.no_graph and n_gpus == 1:  # NCCL collectives stay eager: capturing them across ranks hung on this stack
+    if not args.no_graph and (n_gpus == 1 or exchange is not None):  # NCCL collectives stay eager (capturing them across ranks hung)
         try:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -390,7 +405,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 scan / f32 re-score",
             "data": "synthetic",
             "config": {"workload": f"gallery-sharded cosine-sim search: batch={Q} queries vs {N}x512 gallery, top-{K}, "
-                                   f"{n_gpus} GPU(s), NCCL all-gather of per-shard top-k",
+                                   f"{n_gpus} GPU(s), " + ("single shard" if n_gpus == 1 else ("fused NVLink peer-memory exchange+merge kernel" if exchange is not None else "NCCL all-gather of per-shard top-k + merge kernel")),
                        "queries": Q, "gallery_rows": N, "dim": 512, "rows_per_gpu": per, "parallelism": f"row-shard x{n_gpus}",
                        "l2": f"inputs larger than L2 ({per * 1024 / 1e6:.0f} MB fp16 scan copy per GPU vs 126 MB)"},
             "e2e": {"value": Q / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Q * 512 * 4, "d2h_bytes_per_step": Q * K * 12,

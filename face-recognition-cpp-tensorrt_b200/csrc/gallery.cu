@@ -439,3 +439,5 @@ int fr_gallery_last_stats(const FrGallery* g, FrSearchStats* out) {
 }
 
 }  // extern "C"
+
+#include "exchange_impl.cuh"

@@ -397,3 +397,50 @@ class Pipeline:
         if want_embeddings:
             res["embeddings"] = emb
         return res
+
+
+class Exchange:
+    """Fused cross-GPU exchange + merge of per-shard top-k over NVLink peer memory (csrc/exchange.cu)."""
+
+    def __init__(self, device: int, world: int, rank: int, nq_max: int = 256, k_max: int = 8):
+        L = lib()
+        L.fr_exchange_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.fr_exchange_local_handle.argtypes = [C.c_void_p, C.c_void_p]
+        L.fr_exchange_connect.argtypes = [C.c_void_p, C.c_void_p]
+        L.fr_exchange_connect_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.fr_exchange_merge_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fr_exchange_destroy.restype = None
+        L.fr_exchange_destroy.argtypes = [C.c_void_p]
+        h = C.c_void_p()
+        check(L.fr_exchange_create(device, world, rank, nq_max, k_max, C.byref(h)))
+        self._h, self.device, self.world, self.rank = h, device, world, rank
+
+    def local_handle(self) -> np.ndarray:
+        out = np.zeros(lib().fr_exchange_handle_bytes(), np.uint8)
+        check(lib().fr_exchange_local_handle(self._h, _ptr(out)))
+        return out
+
+    def connect(self, all_handles: np.ndarray) -> None:
+        a = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        assert a.size == self.world * lib().fr_exchange_handle_bytes()
+        check(lib().fr_exchange_connect(self._h, _ptr(a)))
+
+    def connect_local(self, group: "list[Exchange]") -> None:
+        arr = (C.c_void_p * len(group))(*[g._h for g in group])
+        check(lib().fr_exchange_connect_local(self._h, arr))
+
+    def merge_dev(self, local_scores_t, local_idx_t, scores_t, idx_t, stream: int) -> None:
+        nq, k = local_scores_t.shape
+        check(lib().fr_exchange_merge_dev(self._h, _ptr(local_scores_t), _ptr(local_idx_t), nq, k, _ptr(scores_t), _ptr(idx_t),
+                                          C.c_void_p(stream)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

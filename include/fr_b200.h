@@ -99,6 +99,23 @@ int fr_topk_merge_dev(const float *scores_parts_dev, const int64_t *idx_parts_de
 #define FR_PATH_TENSOR 2
 int fr_gallery_set_path(FrGallery *g, int path);
 
+/* Fused exchange + merge over NVLink peer memory (replaces "all-gather, then fr_topk_merge_dev"): one kernel per rank stores its
+ * nq x k results into every peer's mailbox, publishes per-query flags, waits for the peers and merges. One FrExchange per rank
+ * (GPU). Setup: create on every rank, all-gather the fr_exchange_handle_bytes()-byte handles through any host channel, connect.
+ * Step: fr_exchange_merge_dev right after fr_gallery_topk_dev, on the same stream; all ranks must issue the same sequence of
+ * calls. No host synchronisation, no NCCL: the search step is CUDA-graph capturable. */
+typedef struct FrExchange FrExchange;
+int fr_exchange_create(int device, int world, int rank, int nq_max, int k_max, FrExchange **out);
+int fr_exchange_handle_bytes(void);
+int fr_exchange_local_handle(FrExchange *x, void *out_handle);
+/* all_handles: world x fr_exchange_handle_bytes() bytes, rank-major (one process per GPU; CUDA IPC) */
+int fr_exchange_connect(FrExchange *x, const void *all_handles);
+/* same-process groups (single-process multi-GPU hosts, tests): all = the world exchange objects, rank-major */
+int fr_exchange_connect_local(FrExchange *x, FrExchange *const *all);
+int fr_exchange_merge_dev(FrExchange *x, const float *local_scores_dev, const int64_t *local_idx_dev, int nq, int k, float *scores_dev,
+                          int64_t *idx_dev, void *stream);
+void fr_exchange_destroy(FrExchange *x);
+
 /* roofline bookkeeping for bench.py: algorithmic bytes/flops of the dominant kernel of the last topk call */
 typedef struct FrSearchStats {
     int64_t scan_bytes; /* bytes of the resident scan copy streamed (n_rows * dim * 2) */

@@ -227,3 +227,49 @@ def test_near_tie_cluster_inside_fp16_margin(cluster, k):
     _check_topk(s, i, sim, k)
     assert set(i[0].tolist()) <= set(where.tolist()) | {777}
     g.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_fused_exchange_merge_protocol(world):
+    # the peer-memory exchange (csrc/exchange.cu) with `world` shard "ranks" sharing this GPU, one stream per rank: every rank must
+    # end up with the single-gallery result; repeated calls exercise the two-parity mailbox and the device-resident epoch
+    import torch
+
+    rng = np.random.default_rng(world)
+    n, nq, k = 40_000, 256, 2
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    G[n - 5] = G[17]
+    bounds = np.linspace(0, n, world + 1).astype(int)
+    shards = [frb200.Gallery.from_rows(G[a:b], row_offset=int(a)) for a, b in zip(bounds[:-1], bounds[1:])]
+    for s in shards:
+        s.set_path(frb200.FR_PATH_TENSOR)
+    group = [frb200.Exchange(0, world, r, nq_max=256, k_max=8) for r in range(world)]
+    for x in group:
+        x.connect_local(group)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    full = frb200.Gallery.from_rows(G)
+    full.set_path(frb200.FR_PATH_TENSOR)
+    for call in range(5):
+        planted = rng.integers(0, n, nq)
+        planted[0] = 17
+        q = so.planted_queries(G[planted], 0.6, call)
+        q[0] = G[17]
+        qd = torch.from_numpy(q).cuda()
+        outs = []
+        torch.cuda.synchronize()
+        for r in range(world):
+            ls = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+            li = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+            os_ = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+            oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+            shards[r].topk_dev(qd, k, ls, li, stream=streams[r].cuda_stream)
+            group[r].merge_dev(ls, li, os_, oi, stream=streams[r].cuda_stream)
+            outs.append((os_, oi, ls, li))
+        torch.cuda.synchronize()
+        fs, fi = full.topk(q, k)
+        for os_, oi, _, _ in outs:
+            assert np.array_equal(oi.cpu().numpy(), fi)
+            assert np.array_equal(os_.cpu().numpy().view(np.uint32), fs.view(np.uint32))
+        assert fi[0, 0] == 17 and fi[0, 1] == n - 5
+    for o in shards + [full] + group:
+        o.close()
