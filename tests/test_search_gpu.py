@@ -263,8 +263,13 @@ def test_fused_exchange_merge_protocol(world):
             os_ = torch.empty((nq, k), dtype=torch.float32, device="cuda")
             oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
             shards[r].topk_dev(qd, k, ls, li, stream=streams[r].cuda_stream)
-            group[r].merge_dev(ls, li, os_, oi, stream=streams[r].cuda_stream)
             outs.append((os_, oi, ls, li))
+        # on ONE shared GPU the spinning exchange blocks of one rank would keep the full-SM scan kernel of another from being
+        # scheduled, so all scans are enqueued (and finished) first; on separate GPUs the two calls are simply back to back
+        torch.cuda.synchronize()
+        for r in range(world):
+            os_, oi, ls, li = outs[r]
+            group[r].merge_dev(ls, li, os_, oi, stream=streams[r].cuda_stream)
         torch.cuda.synchronize()
         fs, fi = full.topk(q, k)
         for os_, oi, _, _ in outs:
