@@ -19,6 +19,56 @@ struct Geo {  // one feature-map geometry
     __host__ __device__ int HpWp() const { return (H + 1) * (W + 1); }
 };
 
+// ---- RetinaFace::preprocess, resize + paste (src/retinaface.cpp:111-126): the frame is resized to (rw x rh) with OpenCV's u8
+//      INTER_LINEAR arithmetic (11-bit fixed-point coefficients, ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2) and pasted at
+//      (ox, oy) on a canvas filled with 128. One thread per canvas pixel. Matches cv2.resize bit for bit when shrinking
+//      (tests/test_detector_gpu.py); OpenCV is third-party arithmetic (README.md:11).
+__device__ __forceinline__ void lin_coef(int d, double scale, int ssize, int& s0, int& s1, int& a0, int& a1) {
+    float f = static_cast<float>((d + 0.5) * scale - 0.5);
+    int s = static_cast<int>(floorf(f));
+    f = __fsub_rn(f, static_cast<float>(s));
+    if (s < 0) {
+        s = 0;
+        f = 0.f;
+    }
+    if (s >= ssize - 1) {
+        s = ssize - 1;
+        f = 0.f;
+    }
+    s0 = s;
+    s1 = min(s + 1, ssize - 1);
+    a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+__global__ void __launch_bounds__(256) det_letterbox_kernel(const uint8_t* __restrict__ frames, int frame_h, int frame_w, int stride,
+                                                            int batch, int Hn, int Wn, int rw, int rh, int ox, int oy,
+                                                            uint8_t* __restrict__ canvas) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= static_cast<long long>(batch) * Hn * Wn) return;
+    const int img = static_cast<int>(t / (Hn * Wn));
+    const int rc = static_cast<int>(t - static_cast<long long>(img) * Hn * Wn);
+    const int r = rc / Wn, c = rc % Wn;
+    uint8_t* o = canvas + (static_cast<size_t>(img) * Hn * Wn + rc) * 3;
+    const int dy = r - oy, dx = c - ox;
+    if (dy < 0 || dy >= rh || dx < 0 || dx >= rw) {
+        o[0] = o[1] = o[2] = 128;
+        return;
+    }
+    int x0, x1, a0, a1, y0, y1, b0, b1;
+    lin_coef(dx, static_cast<double>(frame_w) / rw, frame_w, x0, x1, a0, a1);
+    lin_coef(dy, static_cast<double>(frame_h) / rh, frame_h, y0, y1, b0, b1);
+    const uint8_t* base = frames + static_cast<size_t>(img) * frame_h * stride;
+    const uint8_t* r0 = base + static_cast<size_t>(y0) * stride;
+    const uint8_t* r1 = base + static_cast<size_t>(y1) * stride;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const int h0 = r0[x0 * 3 + ch] * a0 + r0[x1 * 3 + ch] * a1;
+        const int h1 = r1[x0 * 3 + ch] * a0 + r1[x1 * 3 + ch] * a1;
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[ch] = static_cast<uint8_t>(min(max(v, 0), 255));
+    }
+}
+
 // ---- body.stage1.0: Conv3x3(3->8, s2, p1) + BN + ReLU on the letterboxed u8 canvas, fused with RetinaFace::preprocess's
 //      convertTo(CV_32F) and mean subtraction (104, 117, 123) in B,G,R order (src/retinaface.cpp:128-135).
 __global__ void __launch_bounds__(256) det_stem_kernel(const uint8_t* __restrict__ canvas, int stride_bytes, int batch, int Hn, int Wn,

@@ -60,6 +60,7 @@ struct FrDetector {
     std::vector<void*> allocs;
     float *stem_w = nullptr, *stem_b = nullptr;
     uint8_t* frames_dev = nullptr;   // max_batch x frame_h x frame_w x 3
+    uint8_t* canvas_dev = nullptr;   // max_batch x net_h x net_w x 3 (only when frame size != network size)
     float* chw_dev = nullptr;        // fr_detector_net input
     __half* a0 = nullptr;            // stem output
     Geo g[6];
@@ -320,19 +321,44 @@ void check_det(const FrDetector* d, int batch) {
     if (batch < 1 || batch > d->max_batch) throw ArgError{"batch out of range (1..max_batch)"};
 }
 
-// frames (host or device) -> canvas on the device; returns the canvas pointer and its row stride
+// frames (host or device) -> letterboxed canvas of the network's size on the device (RetinaFace::preprocess, :106-126);
+// returns the canvas pointer and its row stride. When the frame already has the network's size the frame IS the canvas.
 const uint8_t* stage_frames(FrDetector* d, const uint8_t* frames, int stride, int batch, bool on_device, int* canvas_stride, cudaStream_t st) {
     if (stride < d->frame_w * 3) throw ArgError{"stride smaller than frame_w * 3"};
-    if (d->frame_h != d->net_h || d->frame_w != d->net_w)
-        throw ArgError{"this build runs the detector at frame size == network input size (letterbox resize not built yet)"};
-    if (on_device) {
-        *canvas_stride = stride;
-        return frames;
+    const uint8_t* src = frames;
+    int src_stride = stride;
+    if (!on_device) {
+        FRB_CUDA(cudaMemcpy2DAsync(d->frames_dev, static_cast<size_t>(d->frame_w) * 3, frames, stride, static_cast<size_t>(d->frame_w) * 3,
+                                   static_cast<size_t>(batch) * d->frame_h, cudaMemcpyHostToDevice, st));
+        src = d->frames_dev;
+        src_stride = d->frame_w * 3;
     }
-    FRB_CUDA(cudaMemcpy2DAsync(d->frames_dev, static_cast<size_t>(d->frame_w) * 3, frames, stride, static_cast<size_t>(d->frame_w) * 3,
-                               static_cast<size_t>(batch) * d->frame_h, cudaMemcpyHostToDevice, st));
-    *canvas_stride = d->frame_w * 3;
-    return d->frames_dev;
+    if (d->frame_h == d->net_h && d->frame_w == d->net_w) {
+        *canvas_stride = src_stride;
+        return src;
+    }
+    // letterbox geometry exactly as :111-122 (float scales, truncation to int)
+    const float scale_h = static_cast<float>(d->net_h) / d->frame_h, scale_w = static_cast<float>(d->net_w) / d->frame_w;
+    int w, h, x, y;
+    if (scale_h > scale_w) {
+        w = d->net_w;
+        h = static_cast<int>(scale_w * d->frame_h);
+        x = 0;
+        y = (d->net_h - h) / 2;
+    } else {
+        w = static_cast<int>(scale_h * d->frame_w);
+        h = d->net_h;
+        x = (d->net_w - w) / 2;
+        y = 0;
+    }
+    if (!d->canvas_dev) d->canvas_dev = dalloc<uint8_t>(d, static_cast<size_t>(d->max_batch) * d->net_h * d->net_w * 3, false);
+    const long long px = static_cast<long long>(batch) * d->net_h * d->net_w;
+    det_letterbox_kernel<<<blocks_for(px, 256), 256, 0, st>>>(src, d->frame_h, d->frame_w, src_stride, batch, d->net_h, d->net_w, w, h, x, y,
+                                                             d->canvas_dev);
+    count_launch();
+    FRB_CUDA(cudaGetLastError());
+    *canvas_stride = d->net_w * 3;
+    return d->canvas_dev;
 }
 
 void copy_results(FrDetector* d, int batch, FrBbox* boxes, int* counts, float* landmarks, cudaStream_t st) {

@@ -139,3 +139,30 @@ def test_detector_errors(ckpt, tmp_path):
         with pytest.raises(frb200.FrError) as e:
             frb200.Detector(f, (640, 640), landmarks=True)
         assert e.value.code == frb200.FR_EFORMAT
+
+
+def test_letterboxed_frames_shipped_config(ckpt):
+    # the reference's shipped operating point (app/config.json:3-8): 640x480 frames into a 3x288x320 network. The GPU letterbox
+    # (bilinear resize + pad 128) must reproduce RetinaFace::preprocess (cv2 on the oracle side) and the boxes must map back.
+    full, sd, f = ckpt
+    det = frb200.Detector(f, (288, 320), frame_hw=(480, 640), max_batch=3, landmarks=full)
+    rng = np.random.default_rng(21)
+    # smooth-ish frames (upsampled noise) so that the resize is non-trivial
+    small = rng.integers(0, 256, (3, 60, 80, 3), dtype=np.uint8)
+    frames = np.ascontiguousarray(np.repeat(np.repeat(small, 8, axis=1), 8, axis=2))
+    frames = (frames.astype(np.int32) + rng.integers(-20, 21, frames.shape)).clip(0, 255).astype(np.uint8)
+    loc, conf, lm = det.raw(frames)
+    assert loc.shape[1] == ro.num_anchors(288, 320) == 3780
+    # network on the oracle's preprocessing output (cv2 resize): same tensors up to the resize's rounding
+    x = np.stack([ro.preprocess(fr, 288, 320) for fr in frames])
+    loc2, conf2, _ = det.net(x)
+    d = np.abs(conf - conf2).max()
+    print(f"letterbox: max|d conf| GPU-resize vs cv2-resize input = {d:.2e}")
+    assert d <= 2e-3 and np.abs(loc - loc2).max() <= 2e-2
+    boxes, counts, _ = det.run(frames)
+    for i in range(3):
+        want, _, _ = ro.postprocess(loc[i], conf[i], None, 288, 320, 480, 640, 0.4, 0.6, 4)
+        assert _boxes_list(boxes, counts, i) == [w[:4] for w in want]
+        for b in boxes[i, : counts[i]]:
+            assert 0 <= b["x1"] <= b["x2"] <= 479 and 0 <= b["y1"] <= b["y2"] <= 639
+    det.close()
