@@ -4,7 +4,10 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <array>
 #include <atomic>
+#include <cstdlib>
+#include <map>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -65,6 +68,50 @@ int guarded(F&& f) {
         return FR_ECUDA;
     }
 }
+
+// Launch-bound kernel sequences (the ~60-100 small launches of one network forward) are captured once per shape into a CUDA
+// graph and replayed. `body` enqueues the kernels on `st`; keys identify everything baked into the launch arguments.
+struct GraphCache {
+    struct Entry {
+        cudaGraphExec_t exec;
+        int launches;
+    };
+    std::map<std::array<uint64_t, 3>, Entry> entries;
+    bool enabled = std::getenv("FR_NO_GRAPHS") == nullptr;
+    template <class F>
+    void run(const std::array<uint64_t, 3>& key, cudaStream_t st, F&& body) {
+        auto it = entries.find(key);
+        if (!enabled || (it == entries.end() && entries.size() >= 16)) {
+            body();
+            return;
+        }
+        if (it == entries.end()) {
+            const uint64_t before = g_launches.load();
+            cudaGraph_t graph = nullptr;
+            FRB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try {
+                body();
+            } catch (...) {
+                cudaStreamEndCapture(st, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            FRB_CUDA(cudaStreamEndCapture(st, &graph));
+            Entry e{};
+            e.launches = static_cast<int>(g_launches.load() - before);
+            g_launches.store(before);  // capture launched nothing; every replay accounts for its kernels below
+            cudaError_t err = cudaGraphInstantiate(&e.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            FRB_CUDA(err);
+            it = entries.emplace(key, e).first;
+        }
+        FRB_CUDA(cudaGraphLaunch(it->second.exec, st));
+        count_launch(it->second.launches);
+    }
+    ~GraphCache() {
+        for (auto& kv : entries) cudaGraphExecDestroy(kv.second.exec);
+    }
+};
 
 // Select `device`, check it is sm_100, return its SM count.
 int use_device(int device);

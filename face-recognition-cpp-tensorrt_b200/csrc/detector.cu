@@ -71,6 +71,7 @@ struct FrDetector {
     int* counts = nullptr;
     float* out_landm = nullptr;
     int* out_ids = nullptr;
+    GraphCache graphs;
 };
 
 namespace {
@@ -316,6 +317,14 @@ void run_post(FrDetector* d, const float* loc, const float* conf, const float* l
     FRB_CUDA(cudaGetLastError());
 }
 
+// network (+ decode/NMS) replayed from a CUDA graph per (canvas pointer, stride, batch, with_post)
+void forward_graph(FrDetector* d, const uint8_t* canvas, int cs, int batch, bool with_post, cudaStream_t st) {
+    d->graphs.run({reinterpret_cast<uint64_t>(canvas), (static_cast<uint64_t>(cs) << 32) | static_cast<uint64_t>(batch), with_post ? 1ull : 0ull}, st, [&] {
+        run_net(d, canvas, cs, nullptr, batch, st);
+        if (with_post) run_post(d, d->loc, d->conf, d->landm, batch, st);
+    });
+}
+
 void check_det(const FrDetector* d, int batch) {
     if (!d) throw ArgError{"null detector"};
     if (batch < 1 || batch > d->max_batch) throw ArgError{"batch out of range (1..max_batch)"};
@@ -386,8 +395,7 @@ namespace frb {
 void detector_forward_dev(FrDetector* d, const uint8_t* frames_dev, int stride, int batch, cudaStream_t st) {
     int cs = 0;
     const uint8_t* canvas = stage_frames(d, frames_dev, stride, batch, true, &cs, st);
-    run_net(d, canvas, cs, nullptr, batch, st);
-    run_post(d, d->loc, d->conf, d->landm, batch, st);
+    forward_graph(d, canvas, cs, batch, true, st);
 }
 uint8_t* detector_frames_buffer(FrDetector* d) { return d->frames_dev; }
 const FrBbox* detector_boxes(const FrDetector* d) { return d->boxes; }
@@ -463,8 +471,7 @@ int fr_detector_run(FrDetector* d, const uint8_t* frames, int stride, int batch,
         DeviceGuard dg(d->device);
         int cs = 0;
         const uint8_t* canvas = stage_frames(d, frames, stride, batch, false, &cs, d->stream);
-        run_net(d, canvas, cs, nullptr, batch, d->stream);
-        run_post(d, d->loc, d->conf, d->landm, batch, d->stream);
+        forward_graph(d, canvas, cs, batch, true, d->stream);
         copy_results(d, batch, boxes, counts, landmarks, d->stream);
     });
 }
@@ -476,7 +483,7 @@ int fr_detector_raw(FrDetector* d, const uint8_t* frames, int stride, int batch,
         DeviceGuard dg(d->device);
         int cs = 0;
         const uint8_t* canvas = stage_frames(d, frames, stride, batch, false, &cs, d->stream);
-        run_net(d, canvas, cs, nullptr, batch, d->stream);
+        forward_graph(d, canvas, cs, batch, false, d->stream);
         copy_raw(d, batch, loc, conf, landm, d->stream);
     });
 }
@@ -523,8 +530,7 @@ int fr_detector_run_dev(FrDetector* d, const uint8_t* frames_dev, int stride, in
         cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
         int cs = 0;
         const uint8_t* canvas = stage_frames(d, frames_dev, stride, batch, true, &cs, st);
-        run_net(d, canvas, cs, nullptr, batch, st);
-        run_post(d, d->loc, d->conf, d->landm, batch, st);
+        forward_graph(d, canvas, cs, batch, true, st);
         FRB_CUDA(cudaMemcpyAsync(boxes_dev, d->boxes, sizeof(FrBbox) * batch * d->max_faces, cudaMemcpyDeviceToDevice, st));
         FRB_CUDA(cudaMemcpyAsync(counts_dev, d->counts, sizeof(int) * batch, cudaMemcpyDeviceToDevice, st));
         if (landmarks_dev)

@@ -86,6 +86,7 @@ struct FrEmbedder {
     std::vector<std::pair<const __half*, int>> unit_out;  // per unit: (y buffer, geometry index) for fr_embedder_trace
     int last_batch = 0;
     bool last_u8 = false;
+    GraphCache graphs;
 };
 
 namespace {
@@ -162,6 +163,12 @@ void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cud
         count_launch();
     }
     FRB_CUDA(cudaGetLastError());
+}
+
+// complete forward, replayed from a CUDA graph per (batch, input kind)
+void forward_all(FrEmbedder* e, int batch, bool u8_input, cudaStream_t st = nullptr) {
+    if (!st) st = e->stream;
+    e->graphs.run({static_cast<uint64_t>(batch), u8_input ? 1ull : 0ull, 0ull}, st, [&] { run_steps(e, batch, u8_input, kRunAll, st); });
 }
 
 void build_plan(FrEmbedder* e, const WeightFile& wf) {
@@ -407,7 +414,7 @@ int embedder_device(const FrEmbedder* e) { return e->device; }
 void embedder_forward_u8(FrEmbedder* e, int batch, cudaStream_t st) {
     e->last_batch = batch;
     e->last_u8 = true;
-    run_steps(e, batch, true, kRunAll, st);
+    forward_all(e, batch, true, st);
 }
 }  // namespace frb
 
@@ -459,7 +466,7 @@ int fr_embedder_run(FrEmbedder* e, const float* chw, int batch, float* out512) {
         FRB_CUDA(cudaMemcpyAsync(e->in_f32, chw, sizeof(float) * batch * 3 * 112 * 112, cudaMemcpyHostToDevice, e->stream));
         e->last_batch = batch;
         e->last_u8 = false;
-        run_steps(e, batch, false, kRunAll);
+        forward_all(e, batch, false);
         FRB_CUDA(cudaMemcpyAsync(out512, e->out_dev, sizeof(float) * batch * 512, cudaMemcpyDeviceToHost, e->stream));
         FRB_CUDA(cudaStreamSynchronize(e->stream));
     });
@@ -472,7 +479,7 @@ int fr_embedder_run_crops(FrEmbedder* e, const uint8_t* crops_bgr_u8, int batch,
         FRB_CUDA(cudaMemcpyAsync(e->in_u8, crops_bgr_u8, static_cast<size_t>(batch) * 112 * 112 * 3, cudaMemcpyHostToDevice, e->stream));
         e->last_batch = batch;
         e->last_u8 = true;
-        run_steps(e, batch, true, kRunAll);
+        forward_all(e, batch, true);
         FRB_CUDA(cudaMemcpyAsync(out512, e->out_dev, sizeof(float) * batch * 512, cudaMemcpyDeviceToHost, e->stream));
         FRB_CUDA(cudaStreamSynchronize(e->stream));
     });
@@ -493,7 +500,7 @@ int fr_embedder_run_dev(FrEmbedder* e, const float* chw_dev, int batch, float* o
         FRB_CUDA(cudaMemcpyAsync(e->in_f32, chw_dev, sizeof(float) * batch * 3 * 112 * 112, cudaMemcpyDeviceToDevice, e->stream));
         e->last_batch = batch;
         e->last_u8 = false;
-        run_steps(e, batch, false, kRunAll);
+        forward_all(e, batch, false);
         FRB_CUDA(cudaMemcpyAsync(out512_dev, e->out_dev, sizeof(float) * batch * 512, cudaMemcpyDeviceToDevice, e->stream));
         if (user) {
             FRB_CUDA(cudaEventRecord(ev, e->stream));
