@@ -25,7 +25,7 @@ namespace frb {
 
 constexpr int kConvBM = 128;
 constexpr int kConvThreads = 256;
-constexpr int kConvStages = 3;  // 3 x 32 KiB (BN = 128) leaves room for two CTAs per SM
+constexpr int kConvStages = 4;  // BN = 64: 4 x 24 KiB -> two CTAs per SM (one's epilogue overlaps the other's main loop)
 
 enum ConvOutMode { kOutNormal = 0, kOutPhaseSplit = 1 };
 enum ConvResMode { kResNone = 0, kResSame = 1, kResSubsample = 2, kResUpsample = 3 };
@@ -62,7 +62,8 @@ struct ConvCfg {
     static constexpr int kABytes = kConvBM * 128;
     static constexpr int kBBytes = BN * 128;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kSmemBytes = 1024 + kConvStages * kStageBytes + 256;
+    static constexpr int kParamBytes = 4 * BN * 4;  // bias, prelu, bn_s, bn_b of this CTA's channel slice (fp32)
+    static constexpr int kSmemBytes = 1024 + kConvStages * kStageBytes + 256 + kParamBytes;
     static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
@@ -78,6 +79,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* empty_bar = full_bar + kConvStages;
     uint64_t* acc_bar = empty_bar + kConvStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(smem + kConvStages * Cfg::kStageBytes + 256);
+    float* s_prelu = s_bias + BN;
+    float* s_bns = s_prelu + BN;
+    float* s_bnb = s_bns + BN;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -101,6 +106,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (warp >= 4) {  // epilogue parameters of this CTA's channel slice -> shared memory (the epilogue never touches global for them)
+        for (int i = threadIdx.x - 128; i < BN; i += 128) {
+            const int n = blockIdx.y * BN + i;
+            s_bias[i] = prm.bias ? __ldg(prm.bias + n) : 0.f;
+            s_prelu[i] = prm.prelu ? __ldg(prm.prelu + n) : 1.f;
+            s_bns[i] = prm.out_bn ? __ldg(prm.bn_s + n) : 1.f;
+            s_bnb[i] = prm.out_bn ? __ldg(prm.bn_b + n) : 0.f;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -195,10 +209,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 o_res = static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
             }
         }
+        // the residual row of this position is fetched while the tensor pipe is still busy with the main loop
+        uint4 resv[BN / 8];
+        if (valid && prm.res_mode != kResNone) {
+            const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * ldr + n0);
+#pragma unroll
+            for (int j = 0; j < BN / 8; ++j) resv[j] = __ldg(rp + j);
+        }
         mbar_wait(acc_bar, 0);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-#pragma unroll 1
+#pragma unroll
         for (int cc = 0; cc < BN; cc += 16) {
             uint32_t raw[16];
             tmem_ld_32x32b_x16(taddr + cc, raw);
@@ -214,21 +235,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 continue;
             }
-            if (prm.bias) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += __ldg(prm.bias + n + j);
-            }
+            for (int j = 0; j < 16; ++j) v[j] += s_bias[cc + j];
             if (prm.prelu) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * __ldg(prm.prelu + n + j);
+                for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * s_prelu[cc + j];
             }
             if (prm.relu) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (prm.res_mode != kResNone) {
-                const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * ldr + n);
-                const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                const uint4 r0 = resv[cc / 8], r1 = resv[cc / 8 + 1];
                 const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
                 const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll
@@ -261,8 +279,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float2 y = __half22float2(hp[j]);
-                    hb[j] = __floats2half2_rn(fmaf(y.x, __ldg(prm.bn_s + n + 2 * j), __ldg(prm.bn_b + n + 2 * j)),
-                                              fmaf(y.y, __ldg(prm.bn_s + n + 2 * j + 1), __ldg(prm.bn_b + n + 2 * j + 1)));
+                    hb[j] = __floats2half2_rn(fmaf(y.x, s_bns[cc + 2 * j], s_bnb[cc + 2 * j]), fmaf(y.y, s_bns[cc + 2 * j + 1], s_bnb[cc + 2 * j + 1]));
                 }
                 uint4* dst = reinterpret_cast<uint4*>(prm.out_bn + o_main * ldo + n);
                 dst[0] = pb[0];

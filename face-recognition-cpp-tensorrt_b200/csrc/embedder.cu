@@ -38,7 +38,9 @@ struct DevBuf {
 };
 
 struct GemmStep {
-    CUtensorMap ta{}, tb{};
+    CUtensorMap ta{}, tb{};   // tb: weight rows in boxes of `bn`
+    CUtensorMap tb64{};       // same weights in boxes of 64 rows: used when 128-wide tiles would leave SMs idle
+    bool has64 = false;
     ConvGemmParams prm{};
     int bn = 128;
     int out_geo = 0;     // geometry index of the OUTPUT grid (P = batch * hpwp(out_geo)); -1: FC (P = batch)
@@ -145,6 +147,13 @@ void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cud
                 g.prm.W = batch;
                 g.prm.H = 1;
             }
+            // 128-wide channel tiles only when they still give every SM two CTAs' worth of work; otherwise 64-wide tiles (two CTAs
+            // fit per SM, so one CTA's epilogue overlaps another's main loop)
+            const long long tiles128 = static_cast<long long>((P + kConvBM - 1) / kConvBM) * (g.prm.cout / 128);
+            if (g.bn == 128 && g.has64 && tiles128 < 2LL * e->sms) {
+                g.bn = 64;
+                g.tb = g.tb64;
+            }
             if (g.bn == 64) launch_gemm<64>(g, P, st);
             else launch_gemm<128>(g, P, st);
         } else {
@@ -194,7 +203,7 @@ void build_plan(FrEmbedder* e, const WeightFile& wf) {
         int cin, d, stride;
         float *bn1_s, *bn1_b, *prelu, *b2, *bs = nullptr, *fc1 = nullptr, *fc2 = nullptr;
         __half *w1, *w2, *ws = nullptr;
-        CUtensorMap t1, t2, ts;
+        CUtensorMap t1, t2, ts, t1n, t2n, tsn;  // *n: 64-row boxes
     };
     std::vector<UnitW> uw;
     {
@@ -215,10 +224,13 @@ void build_plan(FrEmbedder* e, const WeightFile& wf) {
                 const int bn = u.d == 64 ? 64 : 128;
                 u.t1 = make_tmap_2d_f16(u.w1, u.d, 9ull * u.cin, bn, 64);
                 u.t2 = make_tmap_2d_f16(u.w2, u.d, 9ull * u.d, bn, 64);
+                u.t1n = make_tmap_2d_f16(u.w1, u.d, 9ull * u.cin, 64, 64);
+                u.t2n = make_tmap_2d_f16(u.w2, u.d, 9ull * u.d, 64, 64);
                 if (u.cin != u.d) {
                     u.ws = f16(q + "sc.w", static_cast<int64_t>(u.d) * u.cin);
                     u.bs = f32(q + "sc.b", u.d);
                     u.ts = make_tmap_2d_f16(u.ws, u.d, u.cin, bn, 64);
+                    u.tsn = make_tmap_2d_f16(u.ws, u.d, u.cin, 64, 64);
                 }
                 if (se) {
                     u.fc1 = f32(q + "se.fc1", static_cast<int64_t>(u.d / 16) * u.d);
@@ -280,6 +292,8 @@ void build_plan(FrEmbedder* e, const WeightFile& wf) {
                 s.unit = ui;
                 s.g.ta = sb[stage].ysub.tmap;
                 s.g.tb = u.ts;
+                s.g.tb64 = u.tsn;
+                s.g.has64 = true;
                 s.g.bn = bn;
                 s.g.out_geo = stage;
                 s.g.prm = base_prm(stage, u.cin, 1, u.d);
@@ -293,6 +307,8 @@ void build_plan(FrEmbedder* e, const WeightFile& wf) {
                 s.unit = ui;
                 s.g.ta = in_yb->tmap;
                 s.g.tb = u.t1;
+                s.g.tb64 = u.t1n;
+                s.g.has64 = true;
                 s.g.bn = bn;
                 s.g.out_geo = in_geo;
                 s.g.prm = base_prm(in_geo, u.cin, 9, u.d);
@@ -331,6 +347,8 @@ void build_plan(FrEmbedder* e, const WeightFile& wf) {
                 s.unit = ui;
                 s.g.ta = first ? sb[stage].tphase.tmap : sb[stage].t.tmap;
                 s.g.tb = u.t2;
+                s.g.tb64 = u.t2n;
+                s.g.has64 = true;
                 s.g.bn = bn;
                 s.g.out_geo = stage;
                 s.g.prm = base_prm(stage, u.d, 9, u.d);
