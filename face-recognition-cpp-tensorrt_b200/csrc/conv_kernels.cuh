@@ -25,7 +25,12 @@ namespace frb {
 
 constexpr int kConvBM = 128;
 constexpr int kConvThreads = 256;
-constexpr int kConvStages = 4;  // BN = 64: 4 x 24 KiB -> two CTAs per SM (one's epilogue overlaps the other's main loop)
+// pipeline depth per tile width: two CTAs must fit per SM so that one CTA's epilogue overlaps the other's main loop
+// (BN = 128: 3 x 32 KiB, BN <= 64: 4 x <= 24 KiB)
+template <int BN>
+struct ConvStages {
+    static constexpr int value = BN >= 128 ? 3 : 4;
+};
 
 enum ConvOutMode { kOutNormal = 0, kOutPhaseSplit = 1 };
 enum ConvResMode { kResNone = 0, kResSame = 1, kResSubsample = 2, kResUpsample = 3 };
@@ -59,6 +64,7 @@ struct ConvGemmParams {
 
 template <int BN>
 struct ConvCfg {
+    static constexpr int kConvStages = ConvStages<BN>::value;
     static constexpr int kABytes = kConvBM * 128;
     static constexpr int kBBytes = BN * 128;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -72,6 +78,7 @@ __global__ void __launch_bounds__(kConvThreads)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ ConvGemmParams prm) {
     using Cfg = ConvCfg<BN>;
+    constexpr int kConvStages = Cfg::kConvStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
