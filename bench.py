@@ -205,7 +205,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: fused peer-memory exchange+merge kernel (default) or NCCL all-gather + merge kernel")
+    ap.add_argument("--scan", default="f16", choices=["f16", "f8"],
+                    help="scan copy precision: f16 (default, provably exact top-k) or f8 (opt-in e4m3 copy, exact fp32 re-score)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
+    ap.add_argument("--no-fp8", action="store_true", help="skip the informational fp8-scan measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the detect->embed->search faces/sec section")
     ap.add_argument("--ramp-s", type=float, default=1.0, help="untimed busy period before the timed region (clock ramp)")
     args = ap.parse_args()
@@ -240,6 +243,8 @@ def main():
     lo, hi = sharding.shard_bounds(N, n_gpus, rank)
     gal = frb200.Gallery.synthetic(hi - lo, seed=GALLERY_SEED, device=local, row_offset=lo)
     gal.set_path(frb200.FR_PATH_TENSOR)
+    if args.scan == "f8":
+        gal.set_scan(frb200.FR_SCAN_F8)
 
     # queries: planted on known global rows (same on every rank), so expected identities are known without a host gallery
     rng = np.random.default_rng(QUERY_SEED)
@@ -395,6 +400,32 @@ def main():
 
     hbm_peak, tf_burst, tf_sust, peak_src = peaks()
     st = gal.last_stats()
+    # informational: the same step with the opt-in e4m3 scan copy (every rank takes part; eager launches, events around the kernel)
+    fp8_info = None
+    if args.scan == "f16" and not args.no_fp8:
+        try:
+            gal.set_scan(frb200.FR_SCAN_F8)
+            for _ in range(args.warmup):
+                search_step()
+            barrier()
+            gal.set_timing(True)
+            ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev6.record(stream)
+            for _ in range(args.steps):
+                search_step()
+            ev7.record(stream)
+            barrier()
+            f8_ms = max_over_ranks(ev6.elapsed_time(ev7)) / args.steps
+            f8_scan_ms, f8_n = gal.scan_time()
+            gal.set_timing(False)
+            f8_ok = bool(np.array_equal(out_i.cpu().numpy()[:, 0], planted))
+            f8_stats = gal.last_stats()
+            fp8_info = {"value": Q / (f8_ms * 1e-3), "unit": UNIT, "ms_per_step": f8_ms, "kernel_ms": f8_scan_ms / max(f8_n, 1),
+                        "top1_exact": f8_ok, "hbm_frac": (f8_stats.scan_bytes / (f8_scan_ms / max(f8_n, 1) * 1e-3) / 1e9 / hbm_peak) if f8_n else None,
+                        "note": "opt-in FR_SCAN_F8: e4m3 scan copy (512 B/row), exact fp32 re-score; eager launches"}
+            gal.set_scan(frb200.FR_SCAN_F16)
+        except Exception as e:
+            fp8_info = {"error": f"{type(e).__name__}: {e}"}
     scan_ms_avg = scan_ms / max(scan_n, 1)
     achieved = st.scan_bytes / (scan_ms_avg * 1e-3) / 1e9 if scan_n else None
     tflops = st.flops / (scan_ms_avg * 1e-3) / 1e12 if scan_n else None
@@ -402,7 +433,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 scan / f32 re-score",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": ("f8 (e4m3)" if args.scan == "f8" else "f16") + " scan / f32 re-score",
             "data": "synthetic",
             "config": {"workload": f"gallery-sharded cosine-sim search: batch={Q} queries vs {N}x512 gallery, top-{K}, "
                                    f"{n_gpus} GPU(s), " + ("single shard" if n_gpus == 1 else ("fused NVLink peer-memory exchange+merge kernel" if exchange is not None else "NCCL all-gather of per-shard top-k + merge kernel")),
@@ -413,6 +444,7 @@ def main():
             "gpu_launches": int(launches),
             "cuda_graph": graph is not None, "cuda_graph_error": graph_note, "eager_ms_per_step": eager_ms_per_step,
             "clocks": clocks,
+            "fp8_scan": fp8_info,
             "parity": {"top1_exact": parity_ok, "max_abs_dscore": float(np.abs(got_s - want_score).max())},
             "roofline": {"bound": "hbm", "kernel": "cosine_topk_coarse", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,

@@ -59,6 +59,19 @@ CUtensorMap make_tmap_2d_f16(const void* base, uint64_t rows, uint64_t cols, uin
     return m;
 }
 
+CUtensorMap make_tmap_2d_u8(const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled(2d u8) failed with CUresult " + std::to_string(static_cast<int>(r))};
+    return m;
+}
+
 CUtensorMap make_tmap_nhwc_f16(const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, uint32_t bn, uint32_t bh, uint32_t bw,
                                uint32_t bc) {
     CUtensorMap m;

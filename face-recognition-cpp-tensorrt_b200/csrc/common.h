@@ -131,6 +131,8 @@ struct DeviceGuard {
 
 // 2-D row-major 16-bit tensor [rows, cols] -> TMA map with box [box_rows, box_cols], 128-byte swizzle.
 CUtensorMap make_tmap_2d_f16(const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
+// 2-D row-major byte tensor [rows, cols] -> TMA map with box [box_rows, box_cols <= 128], 128-byte swizzle (fp8 scan copy).
+CUtensorMap make_tmap_2d_u8(const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 // 4-D NHWC 16-bit tensor [n, h, w, c] -> TMA map with box [bn, bh, bw, bc], 128-byte swizzle, zero OOB fill.
 CUtensorMap make_tmap_nhwc_f16(const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, uint32_t bn, uint32_t bh, uint32_t bw,
                                uint32_t bc);

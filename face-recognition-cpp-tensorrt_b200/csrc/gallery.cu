@@ -23,8 +23,11 @@ struct FrGallery {
     int64_t row_offset = 0;
     float* rows_f32 = nullptr;
     __half* rows_f16 = nullptr;
+    uint8_t* rows_f8 = nullptr;       // optional e4m3 scan copy (FR_SCAN_F8), 512 B / row
     float* gmax = nullptr;
     CUtensorMap tmap{};
+    CUtensorMap tmap8{};
+    int scan = FR_SCAN_F16;
     cudaStream_t stream = nullptr;
     // scratch, sized for one chunk of 256 queries
     float* q_dev = nullptr;          // 256 x 512
@@ -65,10 +68,14 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
     static bool attr_done[16] = {};
     if (!attr_done[g->device & 15]) {
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1, false>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1, false>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2, false>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2, false>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1, true>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1, true>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2, true>::kSmemBytes));
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2, true>::kSmemBytes));
         attr_done[g->device & 15] = true;
     }
 }
@@ -105,7 +112,7 @@ void finish_rows(FrGallery* g, bool write_f16) {
     FRB_CUDA(cudaStreamSynchronize(g->stream));
 }
 
-template <int CG, int KSEL>
+template <int CG, int KSEL, bool F8>
 void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tiles, cudaStream_t st) {
     std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
     if (g->timing) {
@@ -121,7 +128,7 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(units * CG);
     cfg.blockDim = dim3(kSearchThreads);
-    cfg.dynamicSmemBytes = CoarseCfg<CG>::kSmemBytes;
+    cfg.dynamicSmemBytes = CoarseCfg<CG, F8>::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -130,7 +137,7 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL>, g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles,
+    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL, F8>, F8 ? g->tmap8 : g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles,
                                 static_cast<const float*>(g->gmax), g->cand_s, g->cand_i, g->flags));
     count_launch();
     if (ev) FRB_CUDA(cudaEventRecord(ev->second, st));
@@ -183,22 +190,33 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     const int cg = nq > kQRows ? 2 : 1;
     const int kc = k == 1 ? 8 : 16;
     int units;
+    const bool f8 = g->scan == FR_SCAN_F8;
     if (cg == 2) {
         units = std::min(g->sms / 2, tiles);
-        if (k == 1) launch_coarse<2, 1>(g, q_dev, nq, units, tiles, st);
-        else launch_coarse<2, 8>(g, q_dev, nq, units, tiles, st);
+        if (f8) {
+            if (k == 1) launch_coarse<2, 1, true>(g, q_dev, nq, units, tiles, st);
+            else launch_coarse<2, 8, true>(g, q_dev, nq, units, tiles, st);
+        } else {
+            if (k == 1) launch_coarse<2, 1, false>(g, q_dev, nq, units, tiles, st);
+            else launch_coarse<2, 8, false>(g, q_dev, nq, units, tiles, st);
+        }
     } else {
         units = std::min(g->sms, tiles);
-        if (k == 1) launch_coarse<1, 1>(g, q_dev, nq, units, tiles, st);
-        else launch_coarse<1, 8>(g, q_dev, nq, units, tiles, st);
+        if (f8) {
+            if (k == 1) launch_coarse<1, 1, true>(g, q_dev, nq, units, tiles, st);
+            else launch_coarse<1, 8, true>(g, q_dev, nq, units, tiles, st);
+        } else {
+            if (k == 1) launch_coarse<1, 1, false>(g, q_dev, nq, units, tiles, st);
+            else launch_coarse<1, 8, false>(g, q_dev, nq, units, tiles, st);
+        }
     }
-    topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->gmax, k,
+    topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->gmax, f8 ? kCoarseEpsF8 : kCoarseEps, k,
                                                    g->row_offset, scores_dev, idx_dev, g->flags);
     count_launch();
     FRB_CUDA(cudaGetLastError());
     // queries whose candidate set may be incomplete (flagged by the re-rank) are recomputed exactly; no-op otherwise
     launch_exact(g, q_dev, nq, k, g->flags, scores_dev, idx_dev, st);
-    g->stats.scan_bytes = g->n * kDim * 2;
+    g->stats.scan_bytes = g->n * kDim * (f8 ? 1 : 2);
     g->stats.flops = 2LL * (cg * kQRows) * g->n * kDim;
     g->stats.launches = 4;
     g->stats.ctas = units * cg;
@@ -285,6 +303,7 @@ void fr_gallery_destroy(FrGallery* g) {
     if (g->stream) cudaStreamSynchronize(g->stream);
     cudaFree(g->rows_f32);
     cudaFree(g->rows_f16);
+    cudaFree(g->rows_f8);
     cudaFree(g->gmax);
     cudaFree(g->q_dev);
     cudaFree(g->cand_s);
@@ -311,6 +330,27 @@ int fr_gallery_set_path(FrGallery* g, int path) {
         if (!g) throw ArgError{"null gallery"};
         if (path != FR_PATH_AUTO && path != FR_PATH_EXACT && path != FR_PATH_TENSOR) throw ArgError{"unknown path"};
         g->path = path;
+    });
+}
+
+int fr_gallery_set_scan(FrGallery* g, int scan) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        if (scan != FR_SCAN_F16 && scan != FR_SCAN_F8) throw ArgError{"unknown scan precision"};
+        DeviceGuard dg(g->device);
+        if (scan == FR_SCAN_F8 && !g->rows_f8 && g->n > 0) {
+            float gmax = 0.f;
+            FRB_CUDA(cudaMemcpy(&gmax, g->gmax, sizeof(float), cudaMemcpyDeviceToHost));
+            if (gmax > 1.001f) throw StateError{"FR_SCAN_F8 needs L2-normalised rows (largest row norm > 1)"};
+            FRB_CUDA(cudaMalloc(&g->rows_f8, static_cast<size_t>(g->n) * kDim));
+            const int blocks = static_cast<int>(std::min<int64_t>((g->n + 7) / 8, g->sms * 16LL));
+            make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f8, g->n);
+            count_launch();
+            FRB_CUDA(cudaGetLastError());
+            FRB_CUDA(cudaStreamSynchronize(g->stream));
+            g->tmap8 = make_tmap_2d_u8(g->rows_f8, static_cast<uint64_t>(g->n), kDim, 128, 128);
+        }
+        g->scan = scan;
     });
 }
 

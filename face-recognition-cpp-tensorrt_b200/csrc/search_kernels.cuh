@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -22,7 +23,7 @@
 namespace frb {
 
 constexpr int kDim = 512;          // rec_outputDim, app/config.json:16
-constexpr int kKBlocks = 8;        // 512 / 64 : one 128-byte swizzle span of fp16 per k-block
+constexpr int kKBlocks = 8;        // fp16 scan: 512 / 64 : one 128-byte swizzle span per k-block (fp8 scan: 512 / 128 = 4)
 constexpr int kTileRows = 256;     // gallery rows per accumulator tile (UMMA N)
 constexpr int kQRows = 128;        // queries per CTA (UMMA M per CTA = TMEM lanes)
 constexpr int kTopkMax = 8;        // FR_TOPK_MAX
@@ -37,11 +38,19 @@ constexpr int kLdCols = 16;                          // accumulator columns per 
 // accumulation, bounded through Cauchy-Schwarz. Candidates within 2 eps of the k-th best coarse score are re-scored exactly.
 constexpr float kCoarseEps = 1.25e-3f;
 
-template <int CG>
+// fp8 (e4m3) scan copy: rows and queries are multiplied by kF8Scale before the conversion (unit-norm components ~0.044 land in
+// e4m3's normal range), accumulators are kF8Scale^2 x the cosine. The fp8 rounding error has no useful provable bound; the margin
+// uses kCoarseEpsF8 ~ 8 sigma of the measured error model (sigma = 2.3e-3 for unit vectors): exact up to that tail probability.
+constexpr float kF8Scale = 256.f;
+constexpr float kCoarseEpsF8 = 2.0e-2f;
+template <int CG, bool F8 = false>
 struct CoarseCfg {
-    static constexpr int kStageBytes = (kTileRows / CG) * 128;   // bytes this CTA loads per k-block
-    static constexpr int kStages = kRingBytes / kStageBytes;     // 3 (single CTA) or 6 (CTA pair)
-    static constexpr int kSmemBytes = 1024 /*align slack*/ + kQBytes + kRingBytes + 256 /*barriers*/;
+    static constexpr int kKB = F8 ? 4 : 8;                         // k-blocks of 128 bytes per row
+    static constexpr int kQSmem = kKB * kQTileBytes;               // 128 KiB (fp16) / 64 KiB (fp8)
+    static constexpr int kRing = F8 ? 160 * 1024 : kRingBytes;     // the fp8 query block leaves room for a deeper ring
+    static constexpr int kStageBytes = (kTileRows / CG) * 128;     // bytes this CTA loads per k-block
+    static constexpr int kStages = kRing / kStageBytes;            // fp16: 3 / 6 (single CTA / pair); fp8: 5 / 10
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kQSmem + kRing + 256 /*barriers*/;
 };
 // candidate list length per epilogue thread: KSEL = 1 (top-1 search) keeps 8, KSEL = 8 (k <= 8) keeps 16
 template <int KSEL>
@@ -79,20 +88,21 @@ __device__ __forceinline__ void topk_insert(float (&s)[KC], int (&ix)[KC], float
 // A thread keeps a row iff its coarse score exceeds max(KC-th best, KSEL-th best - 2 eps |q| gmax): every row that can
 // still reach the exact top-KSEL survives unless more than KC such rows exist (detected in topk_rerank_kernel).
 // ----------------------------------------------------------------------------------------------------------
-template <int CG, int KSEL>
+template <int CG, int KSEL, bool F8>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ q, int nq, long long n_rows, int num_tiles,
                    const float* __restrict__ gmax_ptr, float* __restrict__ cand_s, int* __restrict__ cand_i,
                    int* __restrict__ flag_list) {
-    using Cfg = CoarseCfg<CG>;
+    using Cfg = CoarseCfg<CG, F8>;
+    constexpr int kKB = Cfg::kKB;
     if (blockIdx.x == 0 && threadIdx.x == 0) flag_list[0] = 0;  // list of queries the re-rank hands to the exact scan
     constexpr int KC = ListCfg<KSEL>::kKC;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* q_smem = smem;
-    uint8_t* ring = smem + kQBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + kRingBytes);  // [kStages]  (used in the leader CTA)
+    uint8_t* ring = smem + Cfg::kQSmem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + Cfg::kRing);  // [kStages]  (used in the leader CTA)
     uint64_t* empty_bar = full_bar + Cfg::kStages;                        // [kStages]
     uint64_t* tfull_bar = empty_bar + Cfg::kStages;                       // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;                                 // [2] accumulator drained (leader CTA)
@@ -121,23 +131,37 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
         else tmem_alloc<512>(tmem_slot);
     }
 
-    // ---- stage this CTA's 128 queries: f32 global -> fp16, K-major, 128-byte swizzled (the layout TMA would write)
+    // ---- stage this CTA's 128 queries: f32 global -> fp16 (or scaled e4m3), K-major, 128-byte swizzled (the layout TMA would write)
     {
         const int q_first = static_cast<int>(cta_rank) * kQRows;
-        for (int g = threadIdx.x; g < kQRows * 64; g += kSearchThreads) {
-            const int r = g >> 6;       // query row inside the CTA
-            const int ch = g & 63;      // 16-byte (8 x fp16) chunk along K
+        constexpr int kChunksPerRow = kKB * 8;  // 16-byte chunks along K
+        for (int g = threadIdx.x; g < kQRows * kChunksPerRow; g += kSearchThreads) {
+            const int r = g / kChunksPerRow;   // query row inside the CTA
+            const int ch = g % kChunksPerRow;
             const int kb = ch >> 3, c = ch & 7;
             uint4 packed = make_uint4(0u, 0u, 0u, 0u);
             if (q_first + r < nq) {
-                const float4* src = reinterpret_cast<const float4*>(q + static_cast<size_t>(q_first + r) * kDim + ch * 8);
-                const float4 a = __ldg(src), b = __ldg(src + 1);
-                __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-                __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
-                packed.x = *reinterpret_cast<uint32_t*>(&h0);
-                packed.y = *reinterpret_cast<uint32_t*>(&h1);
-                packed.z = *reinterpret_cast<uint32_t*>(&h2);
-                packed.w = *reinterpret_cast<uint32_t*>(&h3);
+                if (F8) {
+                    const float4* src = reinterpret_cast<const float4*>(q + static_cast<size_t>(q_first + r) * kDim + ch * 16);
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 a = __ldg(src + j);
+                        const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a.x * kF8Scale, a.y * kF8Scale), __NV_SATFINITE, __NV_E4M3);
+                        const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a.z * kF8Scale, a.w * kF8Scale), __NV_SATFINITE, __NV_E4M3);
+                        w[j] = lo | (hi << 16);
+                    }
+                    packed = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {
+                    const float4* src = reinterpret_cast<const float4*>(q + static_cast<size_t>(q_first + r) * kDim + ch * 8);
+                    const float4 a = __ldg(src), b = __ldg(src + 1);
+                    __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+                    __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+                    packed.x = *reinterpret_cast<uint32_t*>(&h0);
+                    packed.y = *reinterpret_cast<uint32_t*>(&h1);
+                    packed.z = *reinterpret_cast<uint32_t*>(&h2);
+                    packed.w = *reinterpret_cast<uint32_t*>(&h3);
+                }
             }
             *reinterpret_cast<uint4*>(q_smem + kb * kQTileBytes + r * 128 + ((c ^ (r & 7)) << 4)) = packed;
         }
@@ -157,17 +181,17 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             const uint32_t leader_full0 = (CG == 2) ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
             for (int t = unit; t < num_tiles; t += num_units) {
                 const int row0 = t * kTileRows;
-                for (int kb = 0; kb < kKBlocks; ++kb) {
+                for (int kb = 0; kb < kKB; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* dst = ring + stage * Cfg::kStageBytes;
                     if (CG == 1) {
                         mbar_expect_tx(&full_bar[stage], 2 * kHalfTileBytes);
-                        tma_load_2d(dst, &tmap, &full_bar[stage], kb * 64, row0, kEvictFirst);
-                        tma_load_2d(dst + kHalfTileBytes, &tmap, &full_bar[stage], kb * 64, row0 + 128, kEvictFirst);
+                        tma_load_2d(dst, &tmap, &full_bar[stage], kb * (F8 ? 128 : 64), row0, kEvictFirst);
+                        tma_load_2d(dst + kHalfTileBytes, &tmap, &full_bar[stage], kb * (F8 ? 128 : 64), row0 + 128, kEvictFirst);
                     } else {
                         // the leader's barrier collects the bytes of both CTAs' halves
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kHalfTileBytes);
-                        tma_load_2d_pair(dst, &tmap, leader_full0 + stage * 8, kb * 64, row0 + static_cast<int>(cta_rank) * 128,
+                        tma_load_2d_pair(dst, &tmap, leader_full0 + stage * 8, kb * (F8 ? 128 : 64), row0 + static_cast<int>(cta_rank) * 128,
                                          kEvictFirst);
                     }
                     if (++stage == Cfg::kStages) {
@@ -188,17 +212,22 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * kTileRows;
-                for (int kb = 0; kb < kKBlocks; ++kb) {
+                for (int kb = 0; kb < kKB; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(q_smem + kb * kQTileBytes);
                     const uint32_t b_addr = smem_u32(ring + stage * Cfg::kStageBytes);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 4 x (K = 16) inside the 128-byte swizzle span
+                    for (int k = 0; k < 4; ++k) {  // 4 MMAs (K = 16 fp16 / 32 fp8 = 32 bytes each) inside the 128-byte swizzle span
                         const uint64_t da = umma_desc_sw128(a_addr + k * 32);
                         const uint64_t db = umma_desc_sw128(b_addr + k * 32);
-                        if (CG == 2) umma_f16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0);
-                        else umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+                        if (F8) {
+                            if (CG == 2) umma_f8_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0);
+                            else umma_f8_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+                        } else {
+                            if (CG == 2) umma_f16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0);
+                            else umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+                        }
                     }
                     if (CG == 2) umma_commit_pair(&empty_bar[stage], 0x3);  // frees the slot in both CTAs
                     else umma_commit(&empty_bar[stage]);
@@ -229,7 +258,8 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 ss = fmaf(v.z, v.z, ss);
                 ss = fmaf(v.w, v.w, ss);
             }
-            margin = 2.f * kCoarseEps * sqrtf(ss) * __ldg(gmax_ptr);
+            // fp8: the list holds raw accumulators (kF8Scale^2 x cosine), so the margin is scaled the same way
+            margin = 2.f * (F8 ? kCoarseEpsF8 * kF8Scale * kF8Scale : kCoarseEps) * sqrtf(ss) * __ldg(gmax_ptr);
         }
         float best_s[KC];
         int best_i[KC];
@@ -301,7 +331,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
         const size_t o = ((static_cast<size_t>(unit) * 2 + half) * (CG * kQRows) + qrow) * KC;
 #pragma unroll
         for (int j = 0; j < KC; ++j) {
-            cand_s[o + j] = best_s[j];
+            cand_s[o + j] = F8 ? best_s[j] * (1.f / (kF8Scale * kF8Scale)) : best_s[j];
             cand_i[o + j] = best_i[j];
         }
     }
@@ -405,7 +435,7 @@ constexpr int kRescoreMax = 64;               // rows re-scored exactly per quer
 __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* __restrict__ cand_s, const int* __restrict__ cand_i,
                                                                   int lists, int q_stride, int kc, const float* __restrict__ q,
                                                                   const float* __restrict__ rows, const float* __restrict__ gmax_ptr,
-                                                                  int k, long long row_offset, float* __restrict__ out_s,
+                                                                  float eps, int k, long long row_offset, float* __restrict__ out_s,
                                                                   long long* __restrict__ out_i, int* __restrict__ flag_list) {
     __shared__ float cs[kHeadMax];
     __shared__ long long ci[kHeadMax];
@@ -441,7 +471,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
     __syncthreads();
     block_select(cs, ci, head, k, sel_s, sel_i, red_s, red_i, red_p);
     const float ck = sel_s[k - 1];  // -inf when fewer than k rows exist
-    const float thr = ck - 2.f * kCoarseEps * sqrtf(qnorm2) * __ldg(gmax_ptr);
+    const float thr = ck - 2.f * eps * sqrtf(qnorm2) * __ldg(gmax_ptr);
     // phase 2: every candidate with coarse >= thr is re-scored
     const int total = lists * kc;
     for (int p = threadIdx.x; p < total; p += blockDim.x) {
@@ -649,6 +679,22 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(float* __restrict__ row
             const size_t o = static_cast<size_t>(r) * kDim + lane + 32 * i;
             rows32[o] = f;
             rows16[o] = __float2half_rn(f);
+        }
+    }
+}
+
+// e4m3 scan copy (rows x kF8Scale). One warp per row.
+__global__ void __launch_bounds__(256) make_f8_copy_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, long long n) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps) {
+        float4 a[4];
+        load512(src + static_cast<size_t>(r) * kDim, lane, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a[i].x * kF8Scale, a[i].y * kF8Scale), __NV_SATFINITE, __NV_E4M3);
+            const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a[i].z * kF8Scale, a[i].w * kF8Scale), __NV_SATFINITE, __NV_E4M3);
+            reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r) * kDim)[lane + 32 * i] = lo | (hi << 16);
         }
     }
 }

@@ -16,6 +16,7 @@ LIB_PATH = PKG / "lib" / "libfr_b200.so"
 FR_OK, FR_EINVAL, FR_ENODEVICE, FR_ECUDA, FR_ENOENT, FR_EFORMAT, FR_ESTATE = 0, -1, -2, -3, -4, -5, -6
 FR_TOPK_MAX = 8
 FR_PATH_AUTO, FR_PATH_EXACT, FR_PATH_TENSOR = 0, 1, 2
+FR_SCAN_F16, FR_SCAN_F8 = 0, 1
 
 
 class FrError(RuntimeError):
@@ -134,6 +135,10 @@ class Gallery:
 
     def set_path(self, path: int) -> None:
         check(lib().fr_gallery_set_path(self._h, path))
+
+    def set_scan(self, scan: int) -> None:
+        lib().fr_gallery_set_scan.argtypes = [C.c_void_p, C.c_int]
+        check(lib().fr_gallery_set_scan(self._h, scan))
 
     def read_rows(self, first: int, count: int) -> np.ndarray:
         out = np.empty((count, 512), np.float32)

@@ -98,6 +98,13 @@ int fr_topk_merge_dev(const float *scores_parts_dev, const int64_t *idx_parts_de
 #define FR_PATH_EXACT 1
 #define FR_PATH_TENSOR 2
 int fr_gallery_set_path(FrGallery *g, int path);
+/* Precision of the scan copy the fused kernel streams. FR_SCAN_F16 (default): 1 KiB/row, provable error bound -> the result is the
+ * exact fp32 top-k unconditionally. FR_SCAN_F8 (opt-in, L2-normalised rows only): e4m3, 512 B/row, half the HBM traffic and twice
+ * the tensor rate; candidates within 0.04 of the k-th best coarse score are re-scored in exact fp32, which is exact unless a row's
+ * fp8 rounding error exceeds ~8 sigma of its model (no provable bound exists for fp8). Scores returned are exact fp32 either way. */
+#define FR_SCAN_F16 0
+#define FR_SCAN_F8 1
+int fr_gallery_set_scan(FrGallery *g, int scan);
 
 /* Fused exchange + merge over NVLink peer memory (replaces "all-gather, then fr_topk_merge_dev"): one kernel per rank stores its
  * nq x k results into every peer's mailbox, publishes per-query flags, waits for the peers and merges. One FrExchange per rank

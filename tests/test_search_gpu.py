@@ -278,3 +278,34 @@ def test_fused_exchange_merge_protocol(world):
         assert fi[0, 0] == 17 and fi[0, 1] == n - 5
     for o in shards + [full] + group:
         o.close()
+
+
+@pytest.mark.parametrize("n,nq,k", [(1000, 1, 1), (150_001, 256, 1), (33_333, 129, 4), (70_000, 64, 8)])
+def test_fp8_scan_copy_topk(n, nq, k):
+    # opt-in e4m3 scan copy (FR_SCAN_F8): the coarse pass is fp8, the returned scores / order come from the exact fp32 re-score
+    rng = np.random.default_rng(n + nq + k)
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    G[n - 2] = G[3]
+    planted = rng.integers(0, n, nq)
+    planted[0] = 3
+    q = so.planted_queries(G[planted], noise=0.75, seed=n)
+    q[0] = G[3]
+    g = frb200.Gallery.from_rows(G, row_offset=7)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(frb200.FR_SCAN_F8)
+    s, i = g.topk(q, k)
+    _check_topk(s, i, so.sims(G, q), k, row_offset=7)
+    assert np.array_equal(i[:, 0], planted + 7)
+    st = g.last_stats()
+    assert st.scan_bytes == n * 512
+    # same answers as the provable fp16 scan, bit for bit
+    g.set_scan(frb200.FR_SCAN_F16)
+    s2, i2 = g.topk(q, k)
+    assert np.array_equal(i, i2) and np.array_equal(s.view(np.uint32), s2.view(np.uint32))
+    g.close()
+    # rows that are not L2-normalised are refused
+    g2 = frb200.Gallery.from_rows(2.0 * G[:100])
+    with pytest.raises(frb200.FrError) as e:
+        g2.set_scan(frb200.FR_SCAN_F8)
+    assert e.value.code == frb200.FR_ESTATE
+    g2.close()
