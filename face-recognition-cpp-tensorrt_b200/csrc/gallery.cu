@@ -33,6 +33,7 @@ struct FrGallery {
     float* q_dev = nullptr;          // 256 x 512
     float* cand_s = nullptr;         // [lists <= 296][256][16]
     int* cand_i = nullptr;
+    int* gbest = nullptr;            // 256: best coarse score per query shared by the scan's epilogue threads (0 between searches)
     int* flags = nullptr;            // [0] = count, [1..256] = queries handed to the exact scan
     float* part_s = nullptr;         // exact scan partials [256][slices][8]
     long long* part_i = nullptr;
@@ -60,6 +61,8 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMalloc(&g->cand_s, sizeof(float) * kMaxLists * kChunkQ * 16));
     FRB_CUDA(cudaMalloc(&g->cand_i, sizeof(int) * kMaxLists * kChunkQ * 16));
     FRB_CUDA(cudaMalloc(&g->flags, sizeof(int) * (kChunkQ + 1)));
+    FRB_CUDA(cudaMalloc(&g->gbest, sizeof(int) * kChunkQ));
+    FRB_CUDA(cudaMemsetAsync(g->gbest, 0, sizeof(int) * kChunkQ, g->stream));
     FRB_CUDA(cudaMalloc(&g->part_s, sizeof(float) * kChunkQ * kScanSlicesMax * kTopkMax));
     FRB_CUDA(cudaMalloc(&g->part_i, sizeof(long long) * kChunkQ * kScanSlicesMax * kTopkMax));
     FRB_CUDA(cudaMalloc(&g->res_s, sizeof(float) * kChunkQ * FR_TOPK_MAX));
@@ -138,7 +141,7 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL, F8>, F8 ? g->tmap8 : g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles,
-                                static_cast<const float*>(g->gmax), g->cand_s, g->cand_i, g->flags));
+                                static_cast<const float*>(g->gmax), g->cand_s, g->cand_i, g->flags, g->gbest));
     count_launch();
     if (ev) FRB_CUDA(cudaEventRecord(ev->second, st));
 }
@@ -211,7 +214,7 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
         }
     }
     topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->gmax, f8 ? kCoarseEpsF8 : kCoarseEps, k,
-                                                   g->row_offset, scores_dev, idx_dev, g->flags);
+                                                   g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
     count_launch();
     FRB_CUDA(cudaGetLastError());
     // queries whose candidate set may be incomplete (flagged by the re-rank) are recomputed exactly; no-op otherwise
@@ -309,6 +312,7 @@ void fr_gallery_destroy(FrGallery* g) {
     cudaFree(g->cand_s);
     cudaFree(g->cand_i);
     cudaFree(g->flags);
+    cudaFree(g->gbest);
     cudaFree(g->part_s);
     cudaFree(g->part_i);
     cudaFree(g->res_s);

@@ -92,7 +92,7 @@ template <int CG, int KSEL, bool F8>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ q, int nq, long long n_rows, int num_tiles,
                    const float* __restrict__ gmax_ptr, float* __restrict__ cand_s, int* __restrict__ cand_i,
-                   int* __restrict__ flag_list) {
+                   int* __restrict__ flag_list, int* __restrict__ gbest) {
     using Cfg = CoarseCfg<CG, F8>;
     constexpr int kKB = Cfg::kKB;
     if (blockIdx.x == 0 && threadIdx.x == 0) flag_list[0] = 0;  // list of queries the re-rank hands to the exact scan
@@ -269,6 +269,11 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             best_i[j] = -1;
         }
         float thr = -INFINITY;
+        // top-1 searches share the best coarse score seen so far for each query between ALL epilogue threads of the GPU (gbest, cosine
+        // units, as int bits of a positive float; reset by the re-rank kernel): any row's score bounds the final best from below, so
+        // rows more than the margin below it can never be needed. It turns the per-thread list threshold into a global one.
+        constexpr float kRawScale = F8 ? kF8Scale * kF8Scale : 1.f;
+        float published = 0.f;
         const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
         constexpr int kChunks = (kTileRows / 2) / kLdCols;  // 8 loads of 16 columns per tile half
 
@@ -309,6 +314,10 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             const int valid = (n_rows - row0 >= kTileRows) ? kTileRows : static_cast<int>(n_rows - row0);
             const int row_base = static_cast<int>(row0);
             const int cbase = half * (kTileRows / 2);
+            if (KSEL == 1 && qrow < nq) {
+                const float gb = __int_as_float(*reinterpret_cast<volatile int*>(gbest + qrow));
+                if (gb > 0.f) thr = fmaxf(thr, gb * kRawScale - margin);
+            }
             // software pipeline: the load of chunk c+1 is in flight while chunk c is consumed
             uint32_t ra[kLdCols], rb[kLdCols];
             tmem_ld_32x32b_x16(taddr, ra);
@@ -323,6 +332,10 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             }
             tc_fence_before();
             __syncwarp();
+            if (KSEL == 1 && qrow < nq && best_s[0] > published) {
+                published = best_s[0];
+                atomicMax(gbest + qrow, __float_as_int(best_s[0] * (1.f / kRawScale)));  // non-negative floats order like their bits
+            }
             if (lane == 0) {
                 if (CG == 2) mbar_arrive_cluster(tempty_leader0 + buf * 8);
                 else mbar_arrive(&tempty_bar[buf]);
@@ -436,7 +449,8 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
                                                                   int lists, int q_stride, int kc, const float* __restrict__ q,
                                                                   const float* __restrict__ rows, const float* __restrict__ gmax_ptr,
                                                                   float eps, int k, long long row_offset, float* __restrict__ out_s,
-                                                                  long long* __restrict__ out_i, int* __restrict__ flag_list) {
+                                                                  long long* __restrict__ out_i, int* __restrict__ flag_list,
+                                                                  int* __restrict__ gbest) {
     __shared__ float cs[kHeadMax];
     __shared__ long long ci[kHeadMax];
     __shared__ float sel_s[kTopkMax];
@@ -505,6 +519,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
         out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
     }
     if (threadIdx.x == 0 && overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
+    if (threadIdx.x == 0) gbest[qi] = 0;  // ready for the next search (0 = nothing published)
 }
 
 // exact fp32 scan. flag_list == nullptr: all nq queries; else the flag_list[0] queries listed in flag_list[1..].
