@@ -106,7 +106,8 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
     uint64_t* empty_bar = full_bar + Cfg::kStages;                        // [kStages]
     uint64_t* tfull_bar = empty_bar + Cfg::kStages;                       // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;                                 // [2] accumulator drained (leader CTA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* q_bar = tempty_bar + 2;                                     // queries staged in every CTA of the unit (leader CTA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -124,6 +125,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             mbar_init(&tfull_bar[b], 1);
             mbar_init(&tempty_bar[b], CG * kEpiWarps);  // one arrive per epilogue warp of every CTA of the unit
         }
+        mbar_init(q_bar, CG * 11);  // one arrive per staging warp (warps 1-11) of every CTA of the unit
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -131,11 +133,18 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
         else tmem_alloc<512>(tmem_slot);
     }
 
-    // ---- stage this CTA's 128 queries: f32 global -> fp16 (or scaled e4m3), K-major, 128-byte swizzled (the layout TMA would write)
-    {
+    // barriers and TMEM are ready in every CTA of the unit before anything is signalled across CTAs
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all();
+    else __syncthreads();
+    tc_fence_after();
+
+    // ---- warps 1-11 stage this CTA's 128 queries: f32 global -> fp16 (or scaled e4m3), K-major, 128-byte swizzled (the layout TMA
+    //      would write), while warp 0 already streams the first gallery stages
+    if (warp != 0) {
         const int q_first = static_cast<int>(cta_rank) * kQRows;
         constexpr int kChunksPerRow = kKB * 8;  // 16-byte chunks along K
-        for (int g = threadIdx.x; g < kQRows * kChunksPerRow; g += kSearchThreads) {
+        for (int g = threadIdx.x - 32; g < kQRows * kChunksPerRow; g += kSearchThreads - 32) {
             const int r = g / kChunksPerRow;   // query row inside the CTA
             const int ch = g % kChunksPerRow;
             const int kb = ch >> 3, c = ch & 7;
@@ -166,12 +175,12 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             *reinterpret_cast<uint4*>(q_smem + kb * kQTileBytes + r * 128 + ((c ^ (r & 7)) << 4)) = packed;
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(q_bar), 0));
+            else mbar_arrive(q_bar);
+        }
     }
-
-    tc_fence_before();
-    if (CG == 2) cluster_sync_all();
-    else __syncthreads();
-    tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -207,6 +216,8 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             constexpr uint32_t idesc = umma_idesc(kQRows * CG, kTileRows, 0, 0);
             uint32_t stage = 0, phase = 0;
             int it = 0;
+            mbar_wait(q_bar, 0);  // query operand staged in both CTAs
+            tc_fence_after();
             for (int t = unit; t < num_tiles; t += num_units, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
