@@ -7,6 +7,7 @@
 //   writes y, BN_next(y), y[::2,::2]) }  ->  folded Linear as split-K GEMM  ->  partial reduce + bias + L2 normalise.
 // Every GEMM is conv_gemm_kernel (tcgen05, csrc/conv_kernels.cuh). Activations are fp16 in the shared-halo flat layout.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -118,12 +119,26 @@ DevBuf make_buf(FrEmbedder* e, size_t rows, int C) {
     return b;
 }
 
+// FR_NO_HALO=1 falls back to per-tap activation loads; FR_HALO_BASEOFF=0 leaves the descriptor's base-offset field zero
+const bool g_use_halo = std::getenv("FR_NO_HALO") == nullptr;
+const int g_halo_baseoff = std::getenv("FR_HALO_BASEOFF") ? std::atoi(std::getenv("FR_HALO_BASEOFF")) : 1;
+
 template <int BN>
 void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
     ConvGemmParams prm = s.prm;
     prm.P = P;
     dim3 grid((P + kConvBM - 1) / kConvBM, prm.cout / BN, s.splits);
-    conv_gemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
+    if (g_use_halo && prm.taps == 9 && !prm.tap_phase && s.splits == 1) {
+        // 3x3 stride-1 conv: one halo tile per 64-channel block feeds all nine taps (conv3x3_halo_kernel)
+        prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
+        prm.halo_bufs = prm.cin_blocks > 1 ? 2 : 1;
+        prm.halo_base_offset = g_halo_baseoff;
+        const int smem = 1024 + prm.halo_bufs * prm.halo_chunks * ConvCfg<BN>::kABytes + ConvCfg<BN>::kConvStages * ConvCfg<BN>::kBBytes + 256 +
+                         ConvCfg<BN>::kParamBytes;
+        conv3x3_halo_kernel<BN><<<grid, kConvThreads, smem, st>>>(s.ta, s.tb, prm);
+    } else {
+        conv_gemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
+    }
     count_launch();
 }
 
@@ -453,6 +468,8 @@ int fr_embedder_create(const char* weights_path, int max_batch, int device, FrEm
             FRB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             build_plan(e.get(), wf);
         } catch (...) {
             fr_embedder_destroy(e.release());
