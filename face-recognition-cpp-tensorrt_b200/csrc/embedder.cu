@@ -119,9 +119,12 @@ DevBuf make_buf(FrEmbedder* e, size_t rows, int C) {
     return b;
 }
 
-// FR_NO_HALO=1 falls back to per-tap activation loads; FR_HALO_BASEOFF=0 leaves the descriptor's base-offset field zero
-const bool g_use_halo = std::getenv("FR_NO_HALO") == nullptr;
-const int g_halo_baseoff = std::getenv("FR_HALO_BASEOFF") ? std::atoi(std::getenv("FR_HALO_BASEOFF")) : 1;
+// FR_HALO=1 switches the stride-1 3x3 convs to conv3x3_halo_kernel (one halo tile per channel block instead of nine per-tap loads).
+// Measured on B200 (IR-SE-50): 1.55 vs 1.64 ms at batch 32, but 8.65 vs 7.54 ms at batch 256, so it is not the default.
+// The tap operands start at 128-byte-row offsets inside the 1024-byte swizzle atom; the hardware swizzles on absolute shared-memory
+// address bits, so the descriptor's base-offset field must stay 0 (setting it to (addr >> 7) & 7 breaks parity: measured).
+const bool g_use_halo = std::getenv("FR_HALO") != nullptr && std::atoi(std::getenv("FR_HALO")) != 0;
+const int g_halo_baseoff = 0;
 
 template <int BN>
 void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
