@@ -34,6 +34,8 @@ struct FrGallery {
     float* cand_s = nullptr;         // [lists <= 296][256][16]
     int* cand_i = nullptr;
     int* gbest = nullptr;            // 256: best coarse score per query shared by the scan's epilogue threads (0 between searches)
+    uint2* app_buf = nullptr;        // append epilogue: [lists <= 296][256][kAppCap] (coarse score bits, local row), allocated on first use
+    int* app_cnt = nullptr;          // [lists][256] entries appended
     int* flags = nullptr;            // [0] = count, [1..256] = queries handed to the exact scan
     float* part_s = nullptr;         // exact scan partials [256][slices][8]
     long long* part_i = nullptr;
@@ -69,18 +71,6 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMalloc(&g->res_i, sizeof(long long) * kChunkQ * FR_TOPK_MAX));
     FRB_CUDA(cudaMalloc(&g->gmax, sizeof(float)));
     FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
-    static bool attr_done[16] = {};
-    if (!attr_done[g->device & 15]) {
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1, false>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1, false>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2, false>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2, false>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1, true>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<1, true>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2, true>::kSmemBytes));
-        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<2, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<2, true>::kSmemBytes));
-        attr_done[g->device & 15] = true;
-    }
 }
 
 FrGallery* new_gallery(int64_t n, int dim, int device, int64_t row_offset) {
@@ -115,7 +105,18 @@ void finish_rows(FrGallery* g, bool write_f16) {
     FRB_CUDA(cudaStreamSynchronize(g->stream));
 }
 
-template <int CG, int KSEL, bool F8>
+// FR_F8_EPS overrides the fp8 margin constant (experiments); FR_SEARCH_APPEND: 0 = sorted register lists everywhere,
+// 1 (default) = append epilogue for top-1 searches on the fp8 scan copy, 2 = also on the fp16 scan copy
+float f8_eps() {
+    static const float v = std::getenv("FR_F8_EPS") ? static_cast<float>(std::atof(std::getenv("FR_F8_EPS"))) : kCoarseEpsF8;
+    return v;
+}
+int append_mode() {
+    static const int v = std::getenv("FR_SEARCH_APPEND") ? std::atoi(std::getenv("FR_SEARCH_APPEND")) : 1;
+    return v;
+}
+
+template <int CG, int KSEL, bool F8, bool APP = false>
 void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tiles, cudaStream_t st) {
     std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
     if (g->timing) {
@@ -133,6 +134,12 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     cfg.blockDim = dim3(kSearchThreads);
     cfg.dynamicSmemBytes = CoarseCfg<CG, F8>::kSmemBytes;
     cfg.stream = st;
+    static bool attr_done[16][2][2][2][2] = {};
+    bool& done = attr_done[g->device & 15][CG - 1][KSEL == 1][F8][APP];
+    if (!done) {
+        FRB_CUDA(cudaFuncSetAttribute(cosine_topk_coarse<CG, KSEL, F8, APP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CoarseCfg<CG, F8>::kSmemBytes));
+        done = true;
+    }
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
@@ -140,8 +147,9 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL, F8>, F8 ? g->tmap8 : g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles,
-                                static_cast<const float*>(g->gmax), g->cand_s, g->cand_i, g->flags, g->gbest));
+    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL, F8, APP>, F8 ? g->tmap8 : g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles,
+                                static_cast<const float*>(g->gmax), F8 ? f8_eps() : kCoarseEps, g->cand_s, g->cand_i, g->flags, g->gbest,
+                                g->app_buf, g->app_cnt));
     count_launch();
     if (ev) FRB_CUDA(cudaEventRecord(ev->second, st));
 }
@@ -194,27 +202,41 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     const int kc = k == 1 ? 8 : 16;
     int units;
     const bool f8 = g->scan == FR_SCAN_F8;
+    const bool app = k == 1 && (append_mode() >= 2 || (append_mode() == 1 && f8));
+    if (app && !g->app_buf) {
+        // not reached while a stream capture is open: callers warm a search up before capturing it (cudaMalloc is not capturable)
+        FRB_CUDA(cudaMalloc(&g->app_buf, sizeof(uint2) * kMaxLists * kChunkQ * kAppCap));
+        FRB_CUDA(cudaMalloc(&g->app_cnt, sizeof(int) * kMaxLists * kChunkQ));
+    }
     if (cg == 2) {
         units = std::min(g->sms / 2, tiles);
         if (f8) {
-            if (k == 1) launch_coarse<2, 1, true>(g, q_dev, nq, units, tiles, st);
+            if (app) launch_coarse<2, 1, true, true>(g, q_dev, nq, units, tiles, st);
+            else if (k == 1) launch_coarse<2, 1, true>(g, q_dev, nq, units, tiles, st);
             else launch_coarse<2, 8, true>(g, q_dev, nq, units, tiles, st);
         } else {
-            if (k == 1) launch_coarse<2, 1, false>(g, q_dev, nq, units, tiles, st);
+            if (app) launch_coarse<2, 1, false, true>(g, q_dev, nq, units, tiles, st);
+            else if (k == 1) launch_coarse<2, 1, false>(g, q_dev, nq, units, tiles, st);
             else launch_coarse<2, 8, false>(g, q_dev, nq, units, tiles, st);
         }
     } else {
         units = std::min(g->sms, tiles);
         if (f8) {
-            if (k == 1) launch_coarse<1, 1, true>(g, q_dev, nq, units, tiles, st);
+            if (app) launch_coarse<1, 1, true, true>(g, q_dev, nq, units, tiles, st);
+            else if (k == 1) launch_coarse<1, 1, true>(g, q_dev, nq, units, tiles, st);
             else launch_coarse<1, 8, true>(g, q_dev, nq, units, tiles, st);
         } else {
-            if (k == 1) launch_coarse<1, 1, false>(g, q_dev, nq, units, tiles, st);
+            if (app) launch_coarse<1, 1, false, true>(g, q_dev, nq, units, tiles, st);
+            else if (k == 1) launch_coarse<1, 1, false>(g, q_dev, nq, units, tiles, st);
             else launch_coarse<1, 8, false>(g, q_dev, nq, units, tiles, st);
         }
     }
-    topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->gmax, f8 ? kCoarseEpsF8 : kCoarseEps, k,
-                                                   g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
+    if (app)
+        append_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->app_buf, g->app_cnt, units * 2, cg * kQRows, q_dev, g->rows_f32, g->gmax,
+                                                         f8 ? f8_eps() : kCoarseEps, g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
+    else
+        topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->gmax,
+                                                       f8 ? f8_eps() : kCoarseEps, k, g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
     count_launch();
     FRB_CUDA(cudaGetLastError());
     // queries whose candidate set may be incomplete (flagged by the re-rank) are recomputed exactly; no-op otherwise
@@ -313,6 +335,8 @@ void fr_gallery_destroy(FrGallery* g) {
     cudaFree(g->cand_i);
     cudaFree(g->flags);
     cudaFree(g->gbest);
+    cudaFree(g->app_buf);
+    cudaFree(g->app_cnt);
     cudaFree(g->part_s);
     cudaFree(g->part_i);
     cudaFree(g->res_s);
@@ -472,6 +496,15 @@ int fr_gallery_scan_time(FrGallery* g, double* total_ms, int* launches) {
         *total_ms = sum;
         *launches = static_cast<int>(g->ev_used);
         g->ev_used = 0;
+    });
+}
+
+int fr_gallery_last_flagged(FrGallery* g, int* out) {
+    return guarded([&] {
+        if (!g || !out) throw ArgError{"null argument"};
+        DeviceGuard dg(g->device);
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+        FRB_CUDA(cudaMemcpy(out, g->flags, sizeof(int), cudaMemcpyDeviceToHost));
     });
 }
 

@@ -42,7 +42,15 @@ constexpr float kCoarseEps = 1.25e-3f;
 // e4m3's normal range), accumulators are kF8Scale^2 x the cosine. The fp8 rounding error has no useful provable bound; the margin
 // uses kCoarseEpsF8 ~ 8 sigma of the measured error model (sigma = 2.3e-3 for unit vectors): exact up to that tail probability.
 constexpr float kF8Scale = 256.f;
-constexpr float kCoarseEpsF8 = 2.0e-2f;
+// measured error model of the e4m3 scan (unit vectors, tools/f8_error_model.py): sigma = 1.65e-3 for unrelated pairs, 2.2e-3 for a
+// matched pair (cos 0.8); the test "true best's coarse score >= best coarse score - margin" involves the sum of two such errors
+// (sigma <= 2.8e-3), and margin = 2 * kCoarseEpsF8 = 2.5e-2 is 8.9 sigma of it.
+constexpr float kCoarseEpsF8 = 1.25e-2f;
+// "append" epilogue (top-1 searches on the fp8 scan copy): instead of a sorted register list every epilogue thread appends the
+// rows that pass its running threshold to a private buffer in global memory; the wide fp8 margin makes passes frequent (a few per
+// thousand rows), and an append is a predicated 8-byte store where a sorted insert is a divergent 8-deep compare-swap chain.
+constexpr int kAppCap = 128;          // entries per (unit, column half, query); more than that hands the query to the exact scan
+constexpr int kAppRescoreMax = 1024;  // rows re-scored exactly per query in append mode
 template <int CG, bool F8 = false>
 struct CoarseCfg {
     static constexpr int kKB = F8 ? 4 : 8;                         // k-blocks of 128 bytes per row
@@ -60,6 +68,12 @@ struct ListCfg {
 
 __device__ __forceinline__ bool better(float sa, long long ia, float sb, long long ib) {
     return sa > sb || (sa == sb && ia < ib);
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // one FMNMX3
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 
 // insert (v, id) into a descending list held in registers; ties keep the earlier (lower row) entry first
@@ -88,11 +102,12 @@ __device__ __forceinline__ void topk_insert(float (&s)[KC], int (&ix)[KC], float
 // A thread keeps a row iff its coarse score exceeds max(KC-th best, KSEL-th best - 2 eps |q| gmax): every row that can
 // still reach the exact top-KSEL survives unless more than KC such rows exist (detected in topk_rerank_kernel).
 // ----------------------------------------------------------------------------------------------------------
-template <int CG, int KSEL, bool F8>
+template <int CG, int KSEL, bool F8, bool APP = false>
 __global__ void __launch_bounds__(kSearchThreads, 1)
 cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ q, int nq, long long n_rows, int num_tiles,
-                   const float* __restrict__ gmax_ptr, float* __restrict__ cand_s, int* __restrict__ cand_i,
-                   int* __restrict__ flag_list, int* __restrict__ gbest) {
+                   const float* __restrict__ gmax_ptr, float eps, float* __restrict__ cand_s, int* __restrict__ cand_i,
+                   int* __restrict__ flag_list, int* __restrict__ gbest, uint2* __restrict__ app_buf, int* __restrict__ app_cnt) {
+    static_assert(!APP || KSEL == 1, "the append epilogue serves top-1 searches");
     using Cfg = CoarseCfg<CG, F8>;
     constexpr int kKB = Cfg::kKB;
     if (blockIdx.x == 0 && threadIdx.x == 0) flag_list[0] = 0;  // list of queries the re-rank hands to the exact scan
@@ -270,8 +285,110 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 ss = fmaf(v.w, v.w, ss);
             }
             // fp8: the list holds raw accumulators (kF8Scale^2 x cosine), so the margin is scaled the same way
-            margin = 2.f * (F8 ? kCoarseEpsF8 * kF8Scale * kF8Scale : kCoarseEps) * sqrtf(ss) * __ldg(gmax_ptr);
+            margin = 2.f * eps * (F8 ? kF8Scale * kF8Scale : 1.f) * sqrtf(ss) * __ldg(gmax_ptr);
         }
+        if constexpr (APP) {
+            // ---------- append epilogue (see kAppCap): thread state = running best, threshold, entry count
+            constexpr float kRaw = F8 ? kF8Scale * kF8Scale : 1.f;
+            constexpr float kInvRaw = 1.f / kRaw;
+            constexpr int kChunksA = (kTileRows / 2) / kLdCols;
+            const bool live = qrow < nq;
+            const size_t list = (static_cast<size_t>(unit) * 2 + half) * (CG * kQRows) + qrow;
+            uint2* mybuf = app_buf + list * kAppCap;
+            float best = -INFINITY, thr = live ? -INFINITY : INFINITY, published = 0.f;
+            int cnt = 0;
+            const uint32_t tempty_leader = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
+            volatile int* gb_ptr = reinterpret_cast<volatile int*>(gbest + (live ? qrow : 0));
+
+            auto chunk_max = [&](const uint32_t (&raw)[kLdCols], int col0, int valid, float (&v)[kLdCols]) -> float {
+#pragma unroll
+                for (int j = 0; j < kLdCols; ++j) v[j] = __uint_as_float(raw[j]);
+                if (valid < kTileRows) {
+#pragma unroll
+                    for (int j = 0; j < kLdCols; ++j)
+                        if (col0 + j >= valid) v[j] = -INFINITY;
+                }
+                const float a = fmax3(v[0], v[1], v[2]), b = fmax3(v[3], v[4], v[5]), c = fmax3(v[6], v[7], v[8]);
+                const float d = fmax3(v[9], v[10], v[11]), e = fmax3(v[12], v[13], v[14]);
+                return fmax3(fmax3(a, b, c), fmax3(d, e, v[15]), -INFINITY);
+            };
+            auto consume_app = [&](const uint32_t (&raw)[kLdCols], int col0, int valid, int row_base) {
+                float v[kLdCols];
+                const float m = chunk_max(raw, col0, valid, v);
+                if (m > thr) {
+#pragma unroll
+                    for (int j = 0; j < kLdCols; ++j) {
+                        if (v[j] > thr) {
+                            if (cnt < kAppCap) mybuf[cnt] = make_uint2(__float_as_uint(v[j] * kInvRaw), static_cast<uint32_t>(row_base + col0 + j));
+                            ++cnt;
+                        }
+                    }
+                    best = fmaxf(best, m);
+                    thr = fmaxf(thr, best - margin);
+                }
+            };
+
+            int it = 0;
+            for (int t = unit; t < num_tiles; t += num_units, ++it) {
+                const int buf = it & 1;
+                // the shared best of this query, fetched now and consumed after the tile: the L2 round trip hides behind the tile
+                const int gb_bits = *gb_ptr;
+                mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * kTileRows + half * (kTileRows / 2);
+                const long long row0 = static_cast<long long>(t) * kTileRows;
+                const int valid = (n_rows - row0 >= kTileRows) ? kTileRows : static_cast<int>(n_rows - row0);
+                const int row_base = static_cast<int>(row0);
+                const int cbase = half * (kTileRows / 2);
+                uint32_t ra[kLdCols], rb[kLdCols];
+                if (it == 0) {
+                    // first tile: a max-only pass seeds the threshold (and the shared best) before anything is appended; without it
+                    // the first chunks would append every row they see
+                    float tm = -INFINITY;
+                    float v[kLdCols];
+                    tmem_ld_32x32b_x16(taddr, ra);
+#pragma unroll 1
+                    for (int c = 0; c < kChunksA; c += 2) {
+                        tmem_ld_wait_x16(ra);
+                        tmem_ld_32x32b_x16(taddr + (c + 1) * kLdCols, rb);
+                        tm = fmaxf(tm, chunk_max(ra, cbase + c * kLdCols, valid, v));
+                        tmem_ld_wait_x16(rb);
+                        if (c + 2 < kChunksA) tmem_ld_32x32b_x16(taddr + (c + 2) * kLdCols, ra);
+                        tm = fmaxf(tm, chunk_max(rb, cbase + (c + 1) * kLdCols, valid, v));
+                    }
+                    if (live) {
+                        // strictly below the tile's best, so that the append pass keeps it
+                        thr = fmaxf(thr, fminf(tm - margin, tm - fabsf(tm) * 1e-6f - 1e-30f));
+                        if (tm > 0.f) atomicMax(gbest + qrow, __float_as_int(tm * kInvRaw));
+                    }
+                }
+                tmem_ld_32x32b_x16(taddr, ra);
+#pragma unroll 1
+                for (int c = 0; c < kChunksA; c += 2) {
+                    tmem_ld_wait_x16(ra);
+                    tmem_ld_32x32b_x16(taddr + (c + 1) * kLdCols, rb);
+                    consume_app(ra, cbase + c * kLdCols, valid, row_base);
+                    tmem_ld_wait_x16(rb);
+                    if (c + 2 < kChunksA) tmem_ld_32x32b_x16(taddr + (c + 2) * kLdCols, ra);
+                    consume_app(rb, cbase + (c + 1) * kLdCols, valid, row_base);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(tempty_leader + buf * 8);
+                    else mbar_arrive(&tempty_bar[buf]);
+                }
+                if (live) {
+                    if (best > published && best > 0.f) {
+                        published = best;
+                        atomicMax(gbest + qrow, __float_as_int(best * kInvRaw));  // non-negative floats order like their bits
+                    }
+                    const float gb = __int_as_float(gb_bits);
+                    if (gb > 0.f) thr = fmaxf(thr, gb * kRaw - margin);
+                }
+            }
+            app_cnt[list] = live ? cnt : 0;
+        } else {
         float best_s[KC];
         int best_i[KC];
 #pragma unroll
@@ -358,6 +475,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             cand_s[o + j] = F8 ? best_s[j] * (1.f / (kF8Scale * kF8Scale)) : best_s[j];
             cand_i[o + j] = best_i[j];
         }
+        }  // !APP
     }
 
     tc_fence_before();
@@ -531,6 +649,95 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
     }
     if (threadIdx.x == 0 && overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
     if (threadIdx.x == 0) gbest[qi] = 0;  // ready for the next search (0 = nothing published)
+}
+
+// Re-rank for the append epilogue (top-1). One block per query: the best coarse score over all appended entries, then every entry
+// within the margin of it is re-scored in exact fp32 and the best by (score desc, row asc) is the result. A list that overflowed
+// (count > kAppCap) or more than kAppRescoreMax in-margin rows flag the query for the exact scan.
+__global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2* __restrict__ app_buf, const int* __restrict__ app_cnt,
+                                                                    int lists, int q_stride, const float* __restrict__ q,
+                                                                    const float* __restrict__ rows, const float* __restrict__ gmax_ptr,
+                                                                    float eps, long long row_offset, float* __restrict__ out_s,
+                                                                    long long* __restrict__ out_i, int* __restrict__ flag_list,
+                                                                    int* __restrict__ gbest) {
+    __shared__ float rs[kAppRescoreMax];
+    __shared__ long long ri[kAppRescoreMax];
+    __shared__ float sel_s[kTopkMax];
+    __shared__ long long sel_i[kTopkMax];
+    __shared__ float red_s[32];
+    __shared__ long long red_i[32];
+    __shared__ int red_p[32];
+    __shared__ int n_resc, overflow;
+    __shared__ float qnorm2, ck_sh;
+    const int qi = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        n_resc = 0;
+        overflow = 0;
+    }
+    float4 qa[4];
+    load512(q + static_cast<size_t>(qi) * kDim, lane, qa);
+    if (warp == 0) {
+        const float n2 = dot512(qa, qa);
+        if (lane == 0) qnorm2 = n2;
+    }
+    __syncthreads();
+    // pass A: best coarse score
+    float mx = -INFINITY;
+    bool over = false;
+    for (int l = threadIdx.x; l < lists; l += blockDim.x) {
+        const size_t li = static_cast<size_t>(l) * q_stride + qi;
+        int c = app_cnt[li];
+        if (c > kAppCap) {
+            over = true;
+            c = kAppCap;
+        }
+        const uint2* e = app_buf + li * kAppCap;
+        for (int j = 0; j < c; ++j) mx = fmaxf(mx, __uint_as_float(e[j].x));
+    }
+    if (over) overflow = 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red_s[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red_s[0];
+        for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red_s[w]);
+        ck_sh = m;
+    }
+    __syncthreads();
+    const float thr = ck_sh - 2.f * eps * sqrtf(qnorm2) * __ldg(gmax_ptr);
+    // pass B: rows to re-score
+    for (int l = threadIdx.x; l < lists; l += blockDim.x) {
+        const size_t li = static_cast<size_t>(l) * q_stride + qi;
+        const int c = min(app_cnt[li], kAppCap);
+        const uint2* e = app_buf + li * kAppCap;
+        for (int j = 0; j < c; ++j) {
+            const uint2 en = e[j];
+            if (__uint_as_float(en.x) >= thr) {
+                const int slot = atomicAdd(&n_resc, 1);
+                if (slot < kAppRescoreMax) ri[slot] = static_cast<long long>(en.y);
+            }
+        }
+    }
+    __syncthreads();
+    const int nr = min(n_resc, kAppRescoreMax);
+    if (n_resc > kAppRescoreMax && threadIdx.x == 0) overflow = 1;
+    for (int c = warp; c < nr; c += (blockDim.x >> 5)) {
+        float4 b[4];
+        load512(rows + static_cast<size_t>(ri[c]) * kDim, lane, b);
+        const float s = dot512(qa, b);
+        if (lane == 0) rs[c] = s;
+    }
+    __syncthreads();
+    block_select(rs, ri, nr, 1, sel_s, sel_i, red_s, red_i, red_p);
+    if (threadIdx.x == 0) {
+        const long long id = sel_i[0];
+        out_s[qi] = sel_s[0];
+        out_i[qi] = id >= 0 ? id + row_offset : -1;
+        if (overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
+        gbest[qi] = 0;  // ready for the next search
+    }
 }
 
 // exact fp32 scan. flag_list == nullptr: all nq queries; else the flag_list[0] queries listed in flag_list[1..].

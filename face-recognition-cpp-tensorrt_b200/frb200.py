@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         L.fr_gallery_topk_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.fr_topk_merge_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fr_gallery_last_stats.argtypes = [C.c_void_p, C.POINTER(FrSearchStats)]
+        L.fr_gallery_last_flagged.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.fr_gallery_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.fr_gallery_scan_time.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         _lib = L
@@ -176,6 +177,12 @@ class Gallery:
         ms, n = C.c_double(), C.c_int()
         check(lib().fr_gallery_scan_time(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def last_flagged(self) -> int:
+        """queries of the last tensor-path search that were recomputed by the exact scan (0 normally)"""
+        n = C.c_int()
+        check(lib().fr_gallery_last_flagged(self._h, C.byref(n)))
+        return n.value
 
     def last_stats(self) -> FrSearchStats:
         st = FrSearchStats()

@@ -131,6 +131,10 @@ typedef struct FrSearchStats {
     int ctas;           /* CTAs of the fused kernel */
 } FrSearchStats;
 int fr_gallery_last_stats(const FrGallery *g, FrSearchStats *out);
+/* diagnostic: how many queries of the last fr_gallery_topk* call on the tensor path the re-rank handed to the exact fp32 scan
+ * (candidate set possibly incomplete). Waits for the gallery's own stream; after a *_dev call on a caller stream, synchronise
+ * that stream first. 0 in the normal case. */
+int fr_gallery_last_flagged(FrGallery *g, int *out);
 /* bench.py's live roofline measurement: when enabled, every launch of the fused scan kernel is bracketed by CUDA events on
  * the stream it is launched on; fr_gallery_scan_time waits for them, returns their summed duration and count, and resets. */
 int fr_gallery_set_timing(FrGallery *g, int enable);

@@ -309,3 +309,48 @@ def test_fp8_scan_copy_topk(n, nq, k):
         g2.set_scan(frb200.FR_SCAN_F8)
     assert e.value.code == frb200.FR_ESTATE
     g2.close()
+
+
+def test_fp8_scan_unknown_queries_and_near_ties():
+    # the hard case for the e4m3 coarse pass: queries WITHOUT a match (hundreds of impostors inside the fp8 margin of the best one)
+    # and a cluster of near-duplicates of the match. Top-1 must still equal the exact fp32 answer, without the exact-scan fallback
+    # for the unknown queries (append epilogue + wide re-score).
+    rng = np.random.default_rng(808)
+    n = 200_000
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    base = G[4242].copy()
+    where = rng.choice(n, 40, replace=False)
+    G[where] = so.l2_normalise(base[None, :] + 2e-3 * rng.standard_normal((40, 512)).astype(np.float32) / np.sqrt(512))
+    q = so.l2_normalise(rng.standard_normal((256, 512))).astype(np.float32)
+    q[7] = base
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(frb200.FR_SCAN_F8)
+    s, i = g.topk(q, 1)
+    flagged = g.last_flagged()
+    sim = so.sims(G, q)
+    _check_topk(s, i, sim, 1)
+    assert i[7, 0] in set(where.tolist()) | {4242}
+    assert flagged == 0, f"{flagged} queries fell back to the exact scan"
+    # k > 1 on the fp8 copy keeps the sorted-list epilogue; same contract
+    s4, i4 = g.topk(q[:64], 4)
+    _check_topk(s4, i4, sim[:64], 4)
+    g.close()
+
+
+def test_fp8_scan_everything_inside_margin_falls_back_exactly():
+    # all rows identical up to 1e-4 noise: every row is inside the margin of the best, the append lists overflow, and the flagged
+    # exact scan must still return the fp32 answer (lowest row among exact ties)
+    rng = np.random.default_rng(5)
+    n = 60_000
+    base = so.l2_normalise(rng.standard_normal((1, 512)))
+    G = so.l2_normalise(base + 1e-4 * rng.standard_normal((n, 512)).astype(np.float32) / np.sqrt(512))
+    G[100] = G[50]
+    q = np.concatenate([G[50][None, :], so.l2_normalise(rng.standard_normal((2, 512)))]).astype(np.float32)
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(frb200.FR_SCAN_F8)
+    s, i = g.topk(q, 1)
+    _check_topk(s, i, so.sims(G, q), 1)
+    assert g.last_flagged() >= 1
+    g.close()
