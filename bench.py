@@ -487,6 +487,14 @@ def main():
                                                            if args.scan == "f8" else " (bf16 sustained)"),
                                 "flops_per_launch": int(st.flops)},
         }
+        probe_file = ROOT / "profiles" / "r01_hbm_read_probe.jsonl"
+        if probe_file.exists() and achieved:
+            try:  # read-only streaming probe (tools/hbm_read_peak.cu) on the same GPU type: the copy-derived peak above undersells reads
+                best = max(json.loads(l)["GBps"] for l in probe_file.read_text().splitlines() if l.startswith("{") and "D2D" not in l)
+                line["roofline"]["read_only_probe_gbs"] = best
+                line["roofline"]["frac_of_read_only_probe"] = achieved / best
+            except Exception:
+                pass
         traffic_file = ROOT / "profiles" / "traffic.json"
         if traffic_file.exists():
             try:

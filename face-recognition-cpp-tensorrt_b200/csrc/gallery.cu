@@ -25,12 +25,16 @@ struct FrGallery {
     __half* rows_f16 = nullptr;
     uint8_t* rows_f8 = nullptr;       // optional e4m3 scan copy (FR_SCAN_F8), 512 B / row
     float* gmax = nullptr;
+    float* g4max = nullptr;           // largest sum of fourth powers of a row (set with the e4m3 copy): scales the fp8 margin
     CUtensorMap tmap{};
     CUtensorMap tmap8{};
     int scan = FR_SCAN_F16;
     cudaStream_t stream = nullptr;
     // scratch, sized for one chunk of 256 queries
     float* q_dev = nullptr;          // 256 x 512
+    void* q_img = nullptr;           // 256 x 512 fp16 (or e4m3): the scan's query operand, written by prep_queries_kernel per search
+    float* q_margin = nullptr;       // 256: 2 eps |q| gmax in accumulator units
+    CUtensorMap tmq16{}, tmq8{};     // two views of q_img
     float* cand_s = nullptr;         // [lists <= 296][256][16]
     int* cand_i = nullptr;
     int* gbest = nullptr;            // 256: best coarse score per query shared by the scan's epilogue threads (0 between searches)
@@ -60,6 +64,10 @@ constexpr int64_t kExactMaxRows = 2048;  // FR_PATH_AUTO: below this the exact s
 void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     FRB_CUDA(cudaMalloc(&g->q_dev, sizeof(float) * kChunkQ * kDim));
+    FRB_CUDA(cudaMalloc(&g->q_img, sizeof(__half) * kChunkQ * kDim));
+    FRB_CUDA(cudaMalloc(&g->q_margin, sizeof(float) * kChunkQ));
+    g->tmq16 = make_tmap_2d_f16(g->q_img, kChunkQ, kDim, 128, 64);
+    g->tmq8 = make_tmap_2d_u8(g->q_img, kChunkQ, kDim, 128, 128);
     FRB_CUDA(cudaMalloc(&g->cand_s, sizeof(float) * kMaxLists * kChunkQ * 16));
     FRB_CUDA(cudaMalloc(&g->cand_i, sizeof(int) * kMaxLists * kChunkQ * 16));
     FRB_CUDA(cudaMalloc(&g->flags, sizeof(int) * (kChunkQ + 1)));
@@ -71,6 +79,8 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMalloc(&g->res_i, sizeof(long long) * kChunkQ * FR_TOPK_MAX));
     FRB_CUDA(cudaMalloc(&g->gmax, sizeof(float)));
     FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
+    FRB_CUDA(cudaMalloc(&g->g4max, sizeof(float)));
+    FRB_CUDA(cudaMemsetAsync(g->g4max, 0, sizeof(float), g->stream));
 }
 
 FrGallery* new_gallery(int64_t n, int dim, int device, int64_t row_offset) {
@@ -105,10 +115,10 @@ void finish_rows(FrGallery* g, bool write_f16) {
     FRB_CUDA(cudaStreamSynchronize(g->stream));
 }
 
-// FR_F8_EPS overrides the fp8 margin constant (experiments); FR_SEARCH_APPEND: 0 = sorted register lists everywhere,
-// 1 = append epilogue for top-1 searches on the fp8 scan copy only, 2 (default) = for top-1 searches on either scan copy
-float f8_eps() {
-    static const float v = std::getenv("FR_F8_EPS") ? static_cast<float>(std::atof(std::getenv("FR_F8_EPS"))) : kCoarseEpsF8;
+// FR_F8_Z overrides the fp8 margin's number of standard deviations (experiments); FR_SEARCH_APPEND: 0 = sorted register lists
+// everywhere, 1 = append epilogue for top-1 searches on the fp8 scan copy only, 2 (default) = for top-1 searches on either scan copy
+float f8_z() {
+    static const float v = std::getenv("FR_F8_Z") ? static_cast<float>(std::atof(std::getenv("FR_F8_Z"))) : kF8Z;
     return v;
 }
 int append_mode() {
@@ -118,6 +128,8 @@ int append_mode() {
 
 template <int CG, int KSEL, bool F8, bool APP = false>
 void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tiles, cudaStream_t st) {
+    prep_queries_kernel<F8><<<kChunkQ / 8, 256, 0, st>>>(q_dev, nq, g->gmax, g->g4max, F8 ? f8_z() : kCoarseEps, g->q_img, g->q_margin);
+    count_launch();
     std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
     if (g->timing) {
         if (g->ev_used == g->ev_pool.size()) {
@@ -147,9 +159,9 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL, F8, APP>, F8 ? g->tmap8 : g->tmap, q_dev, nq, static_cast<long long>(g->n), tiles,
-                                static_cast<const float*>(g->gmax), F8 ? f8_eps() : kCoarseEps, g->cand_s, g->cand_i, g->flags, g->gbest,
-                                g->app_buf, g->app_cnt));
+    FRB_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_coarse<CG, KSEL, F8, APP>, F8 ? g->tmap8 : g->tmap, F8 ? g->tmq8 : g->tmq16,
+                                static_cast<const float*>(g->q_margin), nq, static_cast<long long>(g->n), tiles, g->cand_s, g->cand_i, g->flags,
+                                g->gbest, g->app_buf, g->app_cnt));
     count_launch();
     if (ev) FRB_CUDA(cudaEventRecord(ev->second, st));
 }
@@ -232,18 +244,18 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
         }
     }
     if (app)
-        append_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->app_buf, g->app_cnt, units * 2, cg * kQRows, q_dev, g->rows_f32, g->gmax,
-                                                         f8 ? f8_eps() : kCoarseEps, g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
+        append_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->app_buf, g->app_cnt, units * 2, cg * kQRows, q_dev, g->rows_f32, g->q_margin,
+                                                         f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
     else
-        topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->gmax,
-                                                       f8 ? f8_eps() : kCoarseEps, k, g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
+        topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->q_margin,
+                                                       f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, k, g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
     count_launch();
     FRB_CUDA(cudaGetLastError());
     // queries whose candidate set may be incomplete (flagged by the re-rank) are recomputed exactly; no-op otherwise
     launch_exact(g, q_dev, nq, k, g->flags, scores_dev, idx_dev, st);
     g->stats.scan_bytes = g->n * kDim * (f8 ? 1 : 2);
     g->stats.flops = 2LL * (cg * kQRows) * g->n * kDim;
-    g->stats.launches = 4;
+    g->stats.launches = 5;
     g->stats.ctas = units * cg;
 }
 
@@ -330,7 +342,10 @@ void fr_gallery_destroy(FrGallery* g) {
     cudaFree(g->rows_f16);
     cudaFree(g->rows_f8);
     cudaFree(g->gmax);
+    cudaFree(g->g4max);
     cudaFree(g->q_dev);
+    cudaFree(g->q_img);
+    cudaFree(g->q_margin);
     cudaFree(g->cand_s);
     cudaFree(g->cand_i);
     cudaFree(g->flags);
@@ -374,7 +389,7 @@ int fr_gallery_set_scan(FrGallery* g, int scan) {
             //  difference, 1.010 vs 1.015 ms per 10 M-row scan; the plain matrix stays)
             FRB_CUDA(cudaMalloc(&g->rows_f8, static_cast<size_t>(g->n) * kDim));
             const int blocks = static_cast<int>(std::min<int64_t>((g->n + 7) / 8, g->sms * 16LL));
-            make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f8, g->n);
+            make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f8, g->n, g->g4max);
             count_launch();
             FRB_CUDA(cudaGetLastError());
             FRB_CUDA(cudaStreamSynchronize(g->stream));

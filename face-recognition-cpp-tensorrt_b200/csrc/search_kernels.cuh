@@ -39,13 +39,16 @@ constexpr int kLdCols = 16;                          // accumulator columns per 
 constexpr float kCoarseEps = 1.25e-3f;
 
 // fp8 (e4m3) scan copy: rows and queries are multiplied by kF8Scale before the conversion (unit-norm components ~0.044 land in
-// e4m3's normal range), accumulators are kF8Scale^2 x the cosine. The fp8 rounding error has no useful provable bound; the margin
-// uses kCoarseEpsF8 ~ 8 sigma of the measured error model (sigma = 2.3e-3 for unit vectors): exact up to that tail probability.
+// e4m3's normal range), accumulators are kF8Scale^2 x the cosine. The worst-case rounding bound (2^-4 per operand through
+// Cauchy-Schwarz) is useless, so the margin is statistical: the error of one coarse score is a sum of 512 independent rounding errors
+// with standard deviation  kF8Delta * sqrt(sum q_i^2 g_i^2)  <=  kF8Delta * |q|_4 * |g|_4  (Cauchy-Schwarz on the squares; equality for a
+// matched pair), kF8Delta = 0.0373 = the rms relative error of an e4m3 x e4m3 product (tools/f8_error_model.py: 1.65e-3 measured for
+// unrelated unit vectors, 2.5e-3 for matched pairs, bound 2.85e-3). "The true best's coarse score >= the best coarse score - margin"
+// involves two such errors, so  margin = kF8Z * sqrt(2) * kF8Delta * |q|_4 * max_rows |g|_4 : kF8Z = 6.5 standard deviations of the
+// BOUND (8.7 of the measured sum for Gaussian-like embeddings), ~2.6e-2 for isotropic unit vectors, wider for heavy-tailed ones.
 constexpr float kF8Scale = 256.f;
-// measured error model of the e4m3 scan (unit vectors, tools/f8_error_model.py): sigma = 1.65e-3 for unrelated pairs, 2.2e-3 for a
-// matched pair (cos 0.8); the test "true best's coarse score >= best coarse score - margin" involves the sum of two such errors
-// (sigma <= 2.8e-3), and margin = 2 * kCoarseEpsF8 = 2.5e-2 is 8.9 sigma of it.
-constexpr float kCoarseEpsF8 = 1.25e-2f;
+constexpr float kF8Delta = 0.0373f;
+constexpr float kF8Z = 6.5f;
 // "append" epilogue (top-1 searches on the fp8 scan copy): instead of a sorted register list every epilogue thread appends the
 // rows that pass its running threshold to a private buffer in global memory; the wide fp8 margin makes passes frequent (a few per
 // thousand rows), and an append is a predicated 8-byte store where a sorted insert is a divergent 8-deep compare-swap chain.
@@ -104,8 +107,8 @@ __device__ __forceinline__ void topk_insert(float (&s)[KC], int (&ix)[KC], float
 // ----------------------------------------------------------------------------------------------------------
 template <int CG, int KSEL, bool F8, bool APP = false>
 __global__ void __launch_bounds__(kSearchThreads, 1)
-cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ q, int nq, long long n_rows, int num_tiles,
-                   const float* __restrict__ gmax_ptr, float eps, float* __restrict__ cand_s, int* __restrict__ cand_i,
+cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapq, const float* __restrict__ q_margin,
+                   int nq, long long n_rows, int num_tiles, float* __restrict__ cand_s, int* __restrict__ cand_i,
                    int* __restrict__ flag_list, int* __restrict__ gbest, uint2* __restrict__ app_buf, int* __restrict__ app_cnt) {
     static_assert(!APP || KSEL == 1, "the append epilogue serves top-1 searches");
     using Cfg = CoarseCfg<CG, F8>;
@@ -130,7 +133,10 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
     const int unit = blockIdx.x / CG;
     const int num_units = gridDim.x / CG;
 
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap);
+        tma_prefetch_desc(&tmapq);
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -140,7 +146,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
             mbar_init(&tfull_bar[b], 1);
             mbar_init(&tempty_bar[b], CG * kEpiWarps);  // one arrive per epilogue warp of every CTA of the unit
         }
-        mbar_init(q_bar, CG * 11);  // one arrive per staging warp (warps 1-11) of every CTA of the unit
+        mbar_init(q_bar, 1);  // the leader's expect_tx arrival; both CTAs' query loads complete_tx on it
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -154,48 +160,6 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
     else __syncthreads();
     tc_fence_after();
 
-    // ---- warps 1-11 stage this CTA's 128 queries: f32 global -> fp16 (or scaled e4m3), K-major, 128-byte swizzled (the layout TMA
-    //      would write), while warp 0 already streams the first gallery stages
-    if (warp != 0) {
-        const int q_first = static_cast<int>(cta_rank) * kQRows;
-        constexpr int kChunksPerRow = kKB * 8;  // 16-byte chunks along K
-        for (int g = threadIdx.x - 32; g < kQRows * kChunksPerRow; g += kSearchThreads - 32) {
-            const int r = g / kChunksPerRow;   // query row inside the CTA
-            const int ch = g % kChunksPerRow;
-            const int kb = ch >> 3, c = ch & 7;
-            uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-            if (q_first + r < nq) {
-                if (F8) {
-                    const float4* src = reinterpret_cast<const float4*>(q + static_cast<size_t>(q_first + r) * kDim + ch * 16);
-                    uint32_t w[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 a = __ldg(src + j);
-                        const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a.x * kF8Scale, a.y * kF8Scale), __NV_SATFINITE, __NV_E4M3);
-                        const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a.z * kF8Scale, a.w * kF8Scale), __NV_SATFINITE, __NV_E4M3);
-                        w[j] = lo | (hi << 16);
-                    }
-                    packed = make_uint4(w[0], w[1], w[2], w[3]);
-                } else {
-                    const float4* src = reinterpret_cast<const float4*>(q + static_cast<size_t>(q_first + r) * kDim + ch * 8);
-                    const float4 a = __ldg(src), b = __ldg(src + 1);
-                    __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-                    __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
-                    packed.x = *reinterpret_cast<uint32_t*>(&h0);
-                    packed.y = *reinterpret_cast<uint32_t*>(&h1);
-                    packed.z = *reinterpret_cast<uint32_t*>(&h2);
-                    packed.w = *reinterpret_cast<uint32_t*>(&h3);
-                }
-            }
-            *reinterpret_cast<uint4*>(q_smem + kb * kQTileBytes + r * 128 + ((c ^ (r & 7)) << 4)) = packed;
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) {
-            if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(q_bar), 0));
-            else mbar_arrive(q_bar);
-        }
-    }
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -203,6 +167,14 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             const uint32_t leader_full0 = (CG == 2) ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
+            // this CTA's 128 queries: the operand image prep_queries_kernel wrote (fp16 / scaled e4m3, row-major 256 x 512), one
+            // 128-row x 128-byte box per k-block, 128-byte swizzled by TMA like the gallery tiles
+            if (cta_rank == 0) mbar_expect_tx(q_bar, CG * Cfg::kQSmem);
+            for (int kb = 0; kb < kKB; ++kb) {
+                if (CG == 1) tma_load_2d(q_smem + kb * kQTileBytes, &tmapq, q_bar, kb * (F8 ? 128 : 64), 0, kEvictLast);
+                else tma_load_2d_pair(q_smem + kb * kQTileBytes, &tmapq, mapa_u32(smem_u32(q_bar), 0), kb * (F8 ? 128 : 64),
+                                      static_cast<int>(cta_rank) * kQRows, kEvictLast);
+            }
             for (int t = unit; t < num_tiles; t += num_units) {
                 const int row0 = t * kTileRows;
                 for (int kb = 0; kb < kKB; ++kb) {
@@ -271,22 +243,8 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const float* __rest
         const int ew = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
         const int half = (warp - 4) >> 2;  // accumulator column half
         const int qrow = static_cast<int>(cta_rank) * kQRows + ew * 32 + lane;
-        // margin = 2 eps |q| gmax, |q| from the fp32 query (read while the first tile is still in the tensor pipe)
-        float margin = 0.f;
-        if (qrow < nq) {
-            const float4* qp = reinterpret_cast<const float4*>(q + static_cast<size_t>(qrow) * kDim);
-            float ss = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < kDim / 4; ++i) {
-                const float4 v = __ldg(qp + i);
-                ss = fmaf(v.x, v.x, ss);
-                ss = fmaf(v.y, v.y, ss);
-                ss = fmaf(v.z, v.z, ss);
-                ss = fmaf(v.w, v.w, ss);
-            }
-            // fp8: the list holds raw accumulators (kF8Scale^2 x cosine), so the margin is scaled the same way
-            margin = 2.f * eps * (F8 ? kF8Scale * kF8Scale : 1.f) * sqrtf(ss) * __ldg(gmax_ptr);
-        }
+        // margin = 2 eps |q| gmax in accumulator units (prep_queries_kernel); 0 for the padding rows beyond nq
+        const float margin = qrow < nq ? __ldg(q_margin + qrow) : 0.f;
         if constexpr (APP) {
             // ---------- append epilogue (see kAppCap): thread state = running best, threshold, entry count
             constexpr float kRaw = F8 ? kF8Scale * kF8Scale : 1.f;
@@ -576,8 +534,8 @@ constexpr int kRescoreMax = 64;               // rows re-scored exactly per quer
 // out_s: nq x k, out_i: nq x k (row_offset + local row), padded with (-inf, -1).
 __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* __restrict__ cand_s, const int* __restrict__ cand_i,
                                                                   int lists, int q_stride, int kc, const float* __restrict__ q,
-                                                                  const float* __restrict__ rows, const float* __restrict__ gmax_ptr,
-                                                                  float eps, int k, long long row_offset, float* __restrict__ out_s,
+                                                                  const float* __restrict__ rows, const float* __restrict__ q_margin,
+                                                                  float inv_raw, int k, long long row_offset, float* __restrict__ out_s,
                                                                   long long* __restrict__ out_i, int* __restrict__ flag_list,
                                                                   int* __restrict__ gbest) {
     __shared__ float cs[kHeadMax];
@@ -590,7 +548,6 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
     __shared__ float rs[kRescoreMax];
     __shared__ long long ri[kRescoreMax];
     __shared__ int n_resc, overflow;
-    __shared__ float qnorm2;
     const int qi = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -607,14 +564,10 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
     }
     float4 qa[4];
     load512(q + static_cast<size_t>(qi) * kDim, lane, qa);
-    if (warp == 0) {
-        const float n2 = dot512(qa, qa);
-        if (lane == 0) qnorm2 = n2;
-    }
     __syncthreads();
     block_select(cs, ci, head, k, sel_s, sel_i, red_s, red_i, red_p);
     const float ck = sel_s[k - 1];  // -inf when fewer than k rows exist
-    const float thr = ck - 2.f * eps * sqrtf(qnorm2) * __ldg(gmax_ptr);
+    const float thr = ck - __ldg(q_margin + qi) * inv_raw;  // the scan's margin (prep_queries_kernel), in cosine units
     // phase 2: every candidate with coarse >= thr is re-scored
     const int total = lists * kc;
     for (int p = threadIdx.x; p < total; p += blockDim.x) {
@@ -651,24 +604,25 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
     if (threadIdx.x == 0) gbest[qi] = 0;  // ready for the next search (0 = nothing published)
 }
 
-// Re-rank for the append epilogue (top-1). One block per query: the best coarse score over all appended entries, then every entry
-// within the margin of it is re-scored in exact fp32 and the best by (score desc, row asc) is the result. A list that overflowed
-// (count > kAppCap) or more than kAppRescoreMax in-margin rows flag the query for the exact scan.
+// Re-rank for the append epilogue (top-1). One block per query: the best coarse score (the scan's shared per-query best, or a pass
+// over the entries when nothing positive was published), then every appended entry within the margin of it is re-scored in exact
+// fp32 and the best by (score desc, row asc) is the result. The lists x (count <= kAppCap) entries are walked as ONE flat index
+// range (prefix sums of the counts in shared memory, binary search per element), so the loads of a thread are independent.
+// A list that overflowed (count > kAppCap) or more than kAppRescoreMax in-margin rows flag the query for the exact scan.
 __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2* __restrict__ app_buf, const int* __restrict__ app_cnt,
                                                                     int lists, int q_stride, const float* __restrict__ q,
-                                                                    const float* __restrict__ rows, const float* __restrict__ gmax_ptr,
-                                                                    float eps, long long row_offset, float* __restrict__ out_s,
+                                                                    const float* __restrict__ rows, const float* __restrict__ q_margin,
+                                                                    float inv_raw, long long row_offset, float* __restrict__ out_s,
                                                                     long long* __restrict__ out_i, int* __restrict__ flag_list,
                                                                     int* __restrict__ gbest) {
+    constexpr int kListsMax = 2 * 148;
     __shared__ float rs[kAppRescoreMax];
-    __shared__ long long ri[kAppRescoreMax];
-    __shared__ float sel_s[kTopkMax];
-    __shared__ long long sel_i[kTopkMax];
-    __shared__ float red_s[32];
-    __shared__ long long red_i[32];
-    __shared__ int red_p[32];
+    __shared__ int ri[kAppRescoreMax];
+    __shared__ int s_off[kListsMax + 1];  // exclusive prefix sums of the (clamped) counts
+    __shared__ int warp_tot[kSelThreads / 32];
+    __shared__ float red_s[kSelThreads / 32];
+    __shared__ int red_i[kSelThreads / 32];
     __shared__ int n_resc, overflow;
-    __shared__ float qnorm2, ck_sh;
     const int qi = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -677,64 +631,114 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
     }
     float4 qa[4];
     load512(q + static_cast<size_t>(qi) * kDim, lane, qa);
-    if (warp == 0) {
-        const float n2 = dot512(qa, qa);
-        if (lane == 0) qnorm2 = n2;
-    }
     __syncthreads();
-    // pass A: best coarse score
-    float mx = -INFINITY;
-    bool over = false;
-    for (int l = threadIdx.x; l < lists; l += blockDim.x) {
-        const size_t li = static_cast<size_t>(l) * q_stride + qi;
-        int c = app_cnt[li];
-        if (c > kAppCap) {
-            over = true;
-            c = kAppCap;
-        }
-        const uint2* e = app_buf + li * kAppCap;
-        for (int j = 0; j < c; ++j) mx = fmaxf(mx, __uint_as_float(e[j].x));
-    }
-    if (over) overflow = 1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) red_s[warp] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float m = red_s[0];
-        for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red_s[w]);
-        ck_sh = m;
-    }
-    __syncthreads();
-    const float thr = ck_sh - 2.f * eps * sqrtf(qnorm2) * __ldg(gmax_ptr);
-    // pass B: rows to re-score
-    for (int l = threadIdx.x; l < lists; l += blockDim.x) {
-        const size_t li = static_cast<size_t>(l) * q_stride + qi;
-        const int c = min(app_cnt[li], kAppCap);
-        const uint2* e = app_buf + li * kAppCap;
-        for (int j = 0; j < c; ++j) {
-            const uint2 en = e[j];
-            if (__uint_as_float(en.x) >= thr) {
-                const int slot = atomicAdd(&n_resc, 1);
-                if (slot < kAppRescoreMax) ri[slot] = static_cast<long long>(en.y);
+    // counts -> prefix sums (lists <= 296: at most two per thread, processed in two rounds of a block scan)
+    int base = 0;
+    for (int l0 = 0; l0 < lists; l0 += kSelThreads) {
+        const int l = l0 + threadIdx.x;
+        int c = 0;
+        if (l < lists) {
+            c = app_cnt[static_cast<size_t>(l) * q_stride + qi];
+            if (c > kAppCap) {
+                overflow = 1;
+                c = kAppCap;
             }
+        }
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+        if (l < lists) s_off[l] = base + wbase + inc - c;
+        int round_total = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) round_total += warp_tot[w];
+        base += round_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_off[lists] = base;
+    __syncthreads();
+    const int total = base;
+    auto entry_of = [&](int e) -> uint2 {
+        int lo = 0, hi = lists;  // largest l with s_off[l] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= e) lo = mid;
+            else hi = mid;
+        }
+        return __ldg(app_buf + (static_cast<size_t>(lo) * q_stride + qi) * kAppCap + (e - s_off[lo]));
+    };
+    float ck = __int_as_float(gbest[qi]);  // cosine units; 0 = nothing positive was published
+    if (!(ck > 0.f)) {
+        float mx = -INFINITY;
+        for (int e = threadIdx.x; e < total; e += kSelThreads) mx = fmaxf(mx, __uint_as_float(entry_of(e).x));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red_s[warp] = mx;
+        __syncthreads();
+        mx = red_s[0];
+        for (int w = 1; w < kSelThreads / 32; ++w) mx = fmaxf(mx, red_s[w]);
+        ck = mx;
+        __syncthreads();
+    }
+    const float thr = ck - __ldg(q_margin + qi) * inv_raw;  // the scan's margin (prep_queries_kernel), in cosine units
+    for (int e = threadIdx.x; e < total; e += kSelThreads) {
+        const uint2 en = entry_of(e);
+        if (__uint_as_float(en.x) >= thr) {
+            const int slot = atomicAdd(&n_resc, 1);
+            if (slot < kAppRescoreMax) ri[slot] = static_cast<int>(en.y);
         }
     }
     __syncthreads();
     const int nr = min(n_resc, kAppRescoreMax);
     if (n_resc > kAppRescoreMax && threadIdx.x == 0) overflow = 1;
-    for (int c = warp; c < nr; c += (blockDim.x >> 5)) {
+    for (int c = warp; c < nr; c += kSelThreads / 32) {
         float4 b[4];
         load512(rows + static_cast<size_t>(ri[c]) * kDim, lane, b);
-        const float s = dot512(qa, b);
-        if (lane == 0) rs[c] = s;
+        const float sc = dot512(qa, b);
+        if (lane == 0) rs[c] = sc;
     }
     __syncthreads();
-    block_select(rs, ri, nr, 1, sel_s, sel_i, red_s, red_i, red_p);
+    // best by (exact score desc, row asc)
+    float bs = -INFINITY;
+    int bi = -1;
+    for (int c = threadIdx.x; c < nr; c += kSelThreads) {
+        const float sc = rs[c];
+        const int id = ri[c];
+        if (bi < 0 || sc > bs || (sc == bs && id < bi)) {
+            bs = sc;
+            bi = id;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
+            bs = os;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        red_s[warp] = bs;
+        red_i[warp] = bi;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const long long id = sel_i[0];
-        out_s[qi] = sel_s[0];
-        out_i[qi] = id >= 0 ? id + row_offset : -1;
+        for (int w = 1; w < kSelThreads / 32; ++w) {
+            const float os = red_s[w];
+            const int oi = red_i[w];
+            if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
+                bs = os;
+                bi = oi;
+            }
+        }
+        out_s[qi] = bi >= 0 ? bs : -INFINITY;
+        out_i[qi] = bi >= 0 ? bi + row_offset : -1;
         if (overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
         gbest[qi] = 0;  // ready for the next search
     }
@@ -916,13 +920,63 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(float* __restrict__ row
     }
 }
 
+// Query operand of the fused scan: 256 rows (nq real ones, then zeros) x 512 as fp16, or e4m3 scaled by kF8Scale, row-major, plus the
+// per-query margin 2 eps |q| gmax in accumulator units. One warp per row; runs once per search, so that the scan's CTAs fetch their
+// operand with TMA instead of each converting the fp32 queries themselves.
+template <bool F8>
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int nq, const float* __restrict__ gmax_ptr,
+                                                           const float* __restrict__ g4max_ptr, float scale, void* __restrict__ q_img,
+                                                           float* __restrict__ q_margin) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= 2 * kQRows) return;
+    float4 a[4];
+    if (r < nq) load512(q + static_cast<size_t>(r) * kDim, lane, a);
+    else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float m;
+    if (F8) {  // scale = kF8Z (or its override): margin = scale * sqrt(2) * kF8Delta * (sum q^4 * max_rows sum g^4)^(1/4), in accumulator units
+        float4 a2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a2[i] = make_float4(a[i].x * a[i].x, a[i].y * a[i].y, a[i].z * a[i].z, a[i].w * a[i].w);
+        const float q4 = dot512(a2, a2);
+        m = scale * 1.41421356f * kF8Delta * sqrtf(sqrtf(q4 * __ldg(g4max_ptr))) * (kF8Scale * kF8Scale);
+    } else {   // scale = kCoarseEps: provable margin 2 eps |q| gmax
+        m = 2.f * scale * sqrtf(dot512(a, a)) * __ldg(gmax_ptr);
+    }
+    if (lane == 0) q_margin[r] = r < nq ? m : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (F8) {
+            const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a[i].x * kF8Scale, a[i].y * kF8Scale), __NV_SATFINITE, __NV_E4M3);
+            const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a[i].z * kF8Scale, a[i].w * kF8Scale), __NV_SATFINITE, __NV_E4M3);
+            reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(q_img) + static_cast<size_t>(r) * kDim)[lane + 32 * i] = lo | (hi << 16);
+        } else {
+            __half2 lo = __floats2half2_rn(a[i].x, a[i].y), hi = __floats2half2_rn(a[i].z, a[i].w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(static_cast<__half*>(q_img) + static_cast<size_t>(r) * kDim)[lane + 32 * i] = o;
+        }
+    }
+}
+
 // e4m3 scan copy (rows x kF8Scale). One warp per row.
-__global__ void __launch_bounds__(256) make_f8_copy_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, long long n) {
+// Also the largest sum of fourth powers of a row (g4max, as the bits of a non-negative float): the fp8 margin scales with it.
+__global__ void __launch_bounds__(256) make_f8_copy_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, long long n,
+                                                           float* __restrict__ g4max) {
     const int lane = threadIdx.x & 31;
     const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    float w4 = 0.f;
     for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps) {
         float4 a[4];
         load512(src + static_cast<size_t>(r) * kDim, lane, a);
+        float4 a2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a2[i] = make_float4(a[i].x * a[i].x, a[i].y * a[i].y, a[i].z * a[i].z, a[i].w * a[i].w);
+        w4 = fmaxf(w4, dot512(a2, a2));
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a[i].x * kF8Scale, a[i].y * kF8Scale), __NV_SATFINITE, __NV_E4M3);
@@ -930,6 +984,7 @@ __global__ void __launch_bounds__(256) make_f8_copy_kernel(const float* __restri
             reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r) * kDim)[lane + 32 * i] = lo | (hi << 16);
         }
     }
+    if (lane == 0 && w4 > 0.f) atomicMax(reinterpret_cast<int*>(g4max), __float_as_int(w4));
 }
 
 // scan copy + largest row norm (the margin of the coarse pass scales with it). One warp per row.
