@@ -29,6 +29,11 @@ import threading
 import time
 from pathlib import Path
 
+if "reference" in sys.argv[1:] or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    # the CPU baselines use every host core: torchrun exports OMP_NUM_THREADS=1, and BLAS sizes its pool when numpy is imported
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
@@ -92,17 +97,32 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baselines are meant to use every host core, so lift the BLAS / OpenMP pool
+    limits at run time (threadpoolctl for numpy's BLAS, torch.set_num_threads for torch)"""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    try:
+        import torch
+
+        torch.set_num_threads(n)
+        n = torch.get_num_threads()
+    except Exception:
+        pass
+    return n
+
+
 def cpu_search_sample(nq: int, sample_rows: int, total_rows: int, reps: int, warm: int):
     """oracle port on the host cores: sims = Q @ G^T (fp32 sgemm) then first-max argmax; returns (queries/s scaled to
     total_rows, seconds per sample pass, threads)"""
     from oracle import search_oracle as so
 
-    try:
-        import torch
-
-        threads = torch.get_num_threads()
-    except Exception:
-        threads = os.cpu_count() or 1
+    threads = use_all_host_threads()
     rng = np.random.default_rng(GALLERY_SEED)
     G = rng.standard_normal((sample_rows, 512), dtype=np.float32)
     G /= np.linalg.norm(G, axis=1, keepdims=True)
