@@ -28,6 +28,19 @@ class MatMul {
     void search(float *embeds, int embedCount, int topk, float *scores, int64_t *rows) {
         frCheck(fr_gallery_topk(gallery, embeds, embedCount, topk, scores, rows));
     }
+    // gallery lifecycle without a re-upload (not in the reference, which re-stages and re-uploads everything per enrolment,
+    // src/app.cpp:131-217,354-365): append rows after the last one / delete a row by moving the last row into its slot
+    void append(float *embeds, int count) {
+        if (!gallery) frCheck(fr_gallery_create(nullptr, 0, k ? k : 512, device, 0, &gallery));
+        frCheck(fr_gallery_append(gallery, embeds, count));
+        m += count;
+    }
+    int64_t remove(int row) {
+        int64_t moved = -1;
+        frCheck(fr_gallery_remove(gallery, row, &moved));
+        m -= 1;
+        return moved;
+    }
     FrGallery *handle() const { return gallery; }
     int device = 0;
 

@@ -20,6 +20,7 @@ struct FrGallery {
     int device = 0;
     int sms = 0;
     int64_t n = 0;
+    int64_t capacity = 0;            // rows the device buffers can hold (>= n); grown by fr_gallery_reserve / fr_gallery_append
     int64_t row_offset = 0;
     float* rows_f32 = nullptr;
     __half* rows_f16 = nullptr;
@@ -90,6 +91,7 @@ FrGallery* new_gallery(int64_t n, int dim, int device, int64_t row_offset) {
     g->sms = use_device(device);
     g->device = device;
     g->n = n;
+    g->capacity = n;
     g->row_offset = row_offset;
     try {
         alloc_common(g);
@@ -113,6 +115,45 @@ void finish_rows(FrGallery* g, bool write_f16) {
     count_launch();
     FRB_CUDA(cudaGetLastError());
     FRB_CUDA(cudaStreamSynchronize(g->stream));
+}
+
+// tensor maps follow the row count (rows past n are TMA zero fill) and the buffers' base addresses
+void refresh_tmaps(FrGallery* g) {
+    if (g->n > 0 && g->rows_f16) g->tmap = make_tmap_2d_f16(g->rows_f16, static_cast<uint64_t>(g->n), kDim, 128, 64);
+    if (g->n > 0 && g->rows_f8) g->tmap8 = make_tmap_2d_u8(g->rows_f8, static_cast<uint64_t>(g->n), kDim, 128, 128);
+}
+
+// grow the resident copies to `capacity` rows, preserving the first n
+void grow_rows(FrGallery* g, int64_t capacity) {
+    if (capacity <= g->capacity) return;
+    if (capacity >= (int64_t(1) << 31) - kTileRows) throw ArgError{"row count out of range for one shard"};
+    float* f32 = nullptr;
+    __half* f16 = nullptr;
+    uint8_t* f8 = nullptr;
+    try {
+        FRB_CUDA(cudaMalloc(&f32, sizeof(float) * capacity * kDim));
+        FRB_CUDA(cudaMalloc(&f16, sizeof(__half) * capacity * kDim));
+        if (g->rows_f8 || g->scan == FR_SCAN_F8) FRB_CUDA(cudaMalloc(&f8, static_cast<size_t>(capacity) * kDim));
+        if (g->n > 0) {
+            FRB_CUDA(cudaMemcpyAsync(f32, g->rows_f32, sizeof(float) * g->n * kDim, cudaMemcpyDeviceToDevice, g->stream));
+            FRB_CUDA(cudaMemcpyAsync(f16, g->rows_f16, sizeof(__half) * g->n * kDim, cudaMemcpyDeviceToDevice, g->stream));
+            if (f8 && g->rows_f8) FRB_CUDA(cudaMemcpyAsync(f8, g->rows_f8, static_cast<size_t>(g->n) * kDim, cudaMemcpyDeviceToDevice, g->stream));
+        }
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+    } catch (...) {
+        cudaFree(f32);
+        cudaFree(f16);
+        cudaFree(f8);
+        throw;
+    }
+    cudaFree(g->rows_f32);
+    cudaFree(g->rows_f16);
+    cudaFree(g->rows_f8);
+    g->rows_f32 = f32;
+    g->rows_f16 = f16;
+    g->rows_f8 = f8;
+    g->capacity = capacity;
+    refresh_tmaps(g);
 }
 
 // FR_F8_Z overrides the fp8 margin's number of standard deviations (experiments); FR_SEARCH_APPEND: 0 = sorted register lists
@@ -381,21 +422,99 @@ int fr_gallery_set_scan(FrGallery* g, int scan) {
         if (!g) throw ArgError{"null gallery"};
         if (scan != FR_SCAN_F16 && scan != FR_SCAN_F8) throw ArgError{"unknown scan precision"};
         DeviceGuard dg(g->device);
-        if (scan == FR_SCAN_F8 && !g->rows_f8 && g->n > 0) {
+        if (scan == FR_SCAN_F8 && !g->rows_f8 && g->capacity > 0) {
             float gmax = 0.f;
             FRB_CUDA(cudaMemcpy(&gmax, g->gmax, sizeof(float), cudaMemcpyDeviceToHost));
             if (gmax > 1.001f) throw StateError{"FR_SCAN_F8 needs L2-normalised rows (largest row norm > 1)"};
             // (a block-tiled copy, one contiguous 16 KiB chunk per TMA box, was measured against this row-major one on B200: no
             //  difference, 1.010 vs 1.015 ms per 10 M-row scan; the plain matrix stays)
-            FRB_CUDA(cudaMalloc(&g->rows_f8, static_cast<size_t>(g->n) * kDim));
-            const int blocks = static_cast<int>(std::min<int64_t>((g->n + 7) / 8, g->sms * 16LL));
-            make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f8, g->n, g->g4max);
-            count_launch();
-            FRB_CUDA(cudaGetLastError());
-            FRB_CUDA(cudaStreamSynchronize(g->stream));
-            g->tmap8 = make_tmap_2d_u8(g->rows_f8, static_cast<uint64_t>(g->n), kDim, 128, 128);
+            FRB_CUDA(cudaMalloc(&g->rows_f8, static_cast<size_t>(g->capacity) * kDim));
+            if (g->n > 0) {
+                const int blocks = static_cast<int>(std::min<int64_t>((g->n + 7) / 8, g->sms * 16LL));
+                make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f8, g->n, g->g4max);
+                count_launch();
+                FRB_CUDA(cudaGetLastError());
+                FRB_CUDA(cudaStreamSynchronize(g->stream));
+                g->tmap8 = make_tmap_2d_u8(g->rows_f8, static_cast<uint64_t>(g->n), kDim, 128, 128);
+            }
         }
         g->scan = scan;
+    });
+}
+
+int64_t fr_gallery_capacity(const FrGallery* g) { return g ? g->capacity : -1; }
+
+int fr_gallery_reserve(FrGallery* g, int64_t capacity) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        if (capacity < 0) throw ArgError{"negative capacity"};
+        DeviceGuard dg(g->device);
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+        grow_rows(g, capacity);
+    });
+}
+
+int fr_gallery_append(FrGallery* g, const float* rows, int64_t n) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        if (n < 0 || (n > 0 && !rows)) throw ArgError{"bad rows / n"};
+        if (n == 0) return;
+        DeviceGuard dg(g->device);
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+        if (g->rows_f8 || g->scan == FR_SCAN_F8) {  // the e4m3 copy scales by 256 and saturates at 448: only L2-normalised rows may enter it
+            for (int64_t r = 0; r < n; ++r) {
+                double ss = 0;
+                for (int i = 0; i < kDim; ++i) ss += static_cast<double>(rows[r * kDim + i]) * rows[r * kDim + i];
+                if (ss > 1.001 * 1.001) throw StateError{"FR_SCAN_F8 needs L2-normalised rows (appended row norm > 1)"};
+            }
+        }
+        if (g->n + n > g->capacity) grow_rows(g, std::max<int64_t>(g->n + n, g->capacity + g->capacity / 2 + 1024));
+        float* dst = g->rows_f32 + g->n * kDim;
+        FRB_CUDA(cudaMemcpyAsync(dst, rows, sizeof(float) * n * kDim, cudaMemcpyHostToDevice, g->stream));
+        const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, g->sms * 16LL));
+        // scan copies of the new rows only; gmax / g4max are running maxima (atomicMax), so they stay upper bounds
+        make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f16 + g->n * kDim, n, g->gmax);
+        count_launch();
+        if (g->rows_f8) {
+            make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f8 + g->n * kDim, n, g->g4max);
+            count_launch();
+        }
+        FRB_CUDA(cudaGetLastError());
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+        g->n += n;
+        refresh_tmaps(g);
+    });
+}
+
+int fr_gallery_remove(FrGallery* g, int64_t row, int64_t* moved_from) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        if (row < 0 || row >= g->n) throw ArgError{"row out of range"};
+        DeviceGuard dg(g->device);
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+        const int64_t last = g->n - 1;
+        if (row != last) {
+            FRB_CUDA(cudaMemcpyAsync(g->rows_f32 + row * kDim, g->rows_f32 + last * kDim, sizeof(float) * kDim, cudaMemcpyDeviceToDevice, g->stream));
+            FRB_CUDA(cudaMemcpyAsync(g->rows_f16 + row * kDim, g->rows_f16 + last * kDim, sizeof(__half) * kDim, cudaMemcpyDeviceToDevice, g->stream));
+            if (g->rows_f8)
+                FRB_CUDA(cudaMemcpyAsync(g->rows_f8 + row * kDim, g->rows_f8 + last * kDim, kDim, cudaMemcpyDeviceToDevice, g->stream));
+            FRB_CUDA(cudaStreamSynchronize(g->stream));
+        }
+        if (moved_from) *moved_from = last;
+        g->n = last;  // gmax / g4max keep the removed row's contribution: still upper bounds, the margins only get wider
+        refresh_tmaps(g);
+    });
+}
+
+int fr_gallery_clear(FrGallery* g) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        DeviceGuard dg(g->device);
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+        g->n = 0;
+        FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
+        FRB_CUDA(cudaMemsetAsync(g->g4max, 0, sizeof(float), g->stream));
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
     });
 }
 

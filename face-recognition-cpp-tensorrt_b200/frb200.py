@@ -62,6 +62,12 @@ def lib() -> C.CDLL:
         L.fr_topk_merge_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fr_gallery_last_stats.argtypes = [C.c_void_p, C.POINTER(FrSearchStats)]
         L.fr_gallery_last_flagged.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.fr_gallery_reserve.argtypes = [C.c_void_p, C.c_int64]
+        L.fr_gallery_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.fr_gallery_remove.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.fr_gallery_clear.argtypes = [C.c_void_p]
+        L.fr_gallery_capacity.argtypes = [C.c_void_p]
+        L.fr_gallery_capacity.restype = C.c_int64
         L.fr_gallery_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.fr_gallery_scan_time.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         _lib = L
@@ -133,6 +139,29 @@ class Gallery:
     @property
     def rows(self) -> int:
         return int(lib().fr_gallery_rows(self._h))
+
+    @property
+    def capacity(self) -> int:
+        return int(lib().fr_gallery_capacity(self._h))
+
+    # gallery lifecycle without a re-upload (addEmbedding / resetEmbeddings / reload of the reference)
+    def reserve(self, capacity: int) -> None:
+        check(lib().fr_gallery_reserve(self._h, capacity))
+
+    def append(self, rows) -> None:
+        rows = _f32(rows)
+        if rows.ndim == 1:
+            rows = rows[None, :]
+        check(lib().fr_gallery_append(self._h, _ptr(rows), rows.shape[0]))
+
+    def remove(self, row: int) -> int:
+        """deletes local row `row`; returns the index the row that now sits in its slot had before (the old last row)"""
+        moved = C.c_int64()
+        check(lib().fr_gallery_remove(self._h, row, C.byref(moved)))
+        return moved.value
+
+    def clear(self) -> None:
+        check(lib().fr_gallery_clear(self._h))
 
     def set_path(self, path: int) -> None:
         check(lib().fr_gallery_set_path(self._h, path))

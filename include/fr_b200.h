@@ -73,6 +73,22 @@ int64_t fr_gallery_rows(const FrGallery *g);
 /* copy rows [first, first+count) (f32) back to the host — test hook */
 int fr_gallery_read_rows(FrGallery *g, int64_t first, int64_t count, float *out_rows);
 
+/* Gallery lifecycle without a full re-upload. The reference re-stages every embedding on the host and re-uploads the
+ * whole matrix for each enrolment or /reload (ArcFaceIR50::addEmbedding / initKnownEmbeds / resetEmbeddings / initMatMul,
+ * src/arcface.cpp:150-164,233-236; src/app.cpp:131-217,354-365; src/db.cpp:316-346), leaking the previous copies. Here the resident
+ * copies (f32 master, fp16 scan copy, e4m3 scan copy when enabled, norm bounds) are maintained incrementally. Not concurrent with
+ * searches on the same handle; every call waits for the handle's stream.
+ *   reserve  grow the device buffers to hold `capacity` rows (content preserved); append grows geometrically by itself
+ *   append   add n rows (host f32, n x 512) after the last row; their local indices are [rows, rows + n)
+ *   remove   delete local row `row` by moving the LAST row into its slot (*moved_from = index the moved row had, == row when the
+ *            last row itself was deleted); the caller applies the same move to its row -> userId table (classNames)
+ *   clear    drop all rows, keep the buffers (resetEmbeddings) */
+int fr_gallery_reserve(FrGallery *g, int64_t capacity);
+int fr_gallery_append(FrGallery *g, const float *rows, int64_t n);
+int fr_gallery_remove(FrGallery *g, int64_t row, int64_t *moved_from);
+int fr_gallery_clear(FrGallery *g);
+int64_t fr_gallery_capacity(const FrGallery *g);
+
 /* MatMul::calculate (src/matmul.cpp:36-77): out[i*n_rows + j] = <q_i, row_j>, exact fp32
  * (CUDA_R_32F / CUBLAS_COMPUTE_32F, src/matmul.h:24-25). q: nq x dim host f32; out: nq x n_rows host f32. */
 int fr_gallery_sims(FrGallery *g, const float *q, int nq, float *out);
@@ -100,8 +116,10 @@ int fr_topk_merge_dev(const float *scores_parts_dev, const int64_t *idx_parts_de
 int fr_gallery_set_path(FrGallery *g, int path);
 /* Precision of the scan copy the fused kernel streams. FR_SCAN_F16 (default): 1 KiB/row, provable error bound -> the result is the
  * exact fp32 top-k unconditionally. FR_SCAN_F8 (opt-in, L2-normalised rows only): e4m3, 512 B/row, half the HBM traffic and twice
- * the tensor rate; candidates within 0.04 of the k-th best coarse score are re-scored in exact fp32, which is exact unless a row's
- * fp8 rounding error exceeds ~8 sigma of its model (no provable bound exists for fp8). Scores returned are exact fp32 either way. */
+ * the tensor rate; rows whose coarse score is within margin = 6.5 * sqrt(2) * 0.0373 * |q|_4 * max_rows |g|_4 of the best coarse score
+ * (about 0.03 for isotropic unit vectors) are re-scored in exact fp32: exact unless the rounding errors of two scores exceed 6.5 sigma
+ * of the bound on their standard deviation (no useful provable bound exists for fp8; csrc/search_kernels.cuh, tools/f8_error_model.py).
+ * Scores returned are exact fp32 either way. */
 #define FR_SCAN_F16 0
 #define FR_SCAN_F8 1
 int fr_gallery_set_scan(FrGallery *g, int scan);

@@ -354,3 +354,71 @@ def test_fp8_scan_everything_inside_margin_falls_back_exactly():
     _check_topk(s, i, so.sims(G, q), 1)
     assert g.last_flagged() >= 1
     g.close()
+
+
+@pytest.mark.parametrize("scan", [frb200.FR_SCAN_F16, frb200.FR_SCAN_F8])
+def test_gallery_lifecycle_append_remove_clear(scan):
+    # enrolment / deletion / reload without a full re-upload. After every step the resident gallery must answer
+    # exactly like a gallery created from scratch with the same rows (scan copies and margin bounds maintained incrementally).
+    rng = np.random.default_rng(77)
+    G = so.l2_normalise(rng.standard_normal((9000, 512)))
+    model = G[:5000].copy()                     # host model of the resident rows
+    g = frb200.Gallery.from_rows(model)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(scan)
+
+    def check(nq=37, k=3):
+        planted = rng.integers(0, len(model), nq)
+        q = so.planted_queries(model[planted], noise=0.75, seed=int(rng.integers(1 << 30)))
+        assert g.rows == len(model) and g.capacity >= g.rows
+        s1, i1 = g.topk(q, 1)
+        sk, ik = g.topk(q, k)
+        sim = so.sims(model, q)
+        _check_topk(s1, i1, sim, 1)
+        _check_topk(sk, ik, sim, k)
+        assert np.array_equal(i1[:, 0], planted)
+        assert np.array_equal(g.read_rows(0, len(model)).view(np.uint32), model.view(np.uint32))
+
+    check()
+    g.append(G[5000:5001])                      # one enrolment (grows the buffers)
+    model = np.concatenate([model, G[5000:5001]])
+    check()
+    g.append(G[5001:8000])                      # bulk enrolment
+    model = np.concatenate([model, G[5001:8000]])
+    check()
+    g.reserve(20_000)
+    assert g.capacity >= 20_000
+    check()
+    for row in (0, 4321, len(model) - 1, 17):   # deletions: the last row moves into the slot
+        moved = g.remove(row)
+        assert moved == len(model) - 1
+        model[row] = model[moved]
+        model = model[:-1]
+        check()
+    g.clear()
+    assert g.rows == 0
+    with pytest.raises(frb200.FrError) as e:
+        g.topk(G[:2], 1)
+    assert e.value.code == frb200.FR_ESTATE
+    g.append(G[8000:9000])                      # reload after resetEmbeddings
+    model = G[8000:9000].copy()
+    check(k=2)
+    if scan == frb200.FR_SCAN_F8:               # rows that are not L2-normalised cannot enter the e4m3 copy
+        with pytest.raises(frb200.FrError):
+            g.append(2.0 * G[:3])
+        assert g.rows == 1000
+    g.close()
+
+
+def test_gallery_starts_empty_then_appends():
+    rng = np.random.default_rng(3)
+    G = so.l2_normalise(rng.standard_normal((3000, 512)))
+    g = frb200.Gallery.from_rows(np.zeros((0, 512), np.float32))
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(frb200.FR_SCAN_F8)
+    g.append(G)
+    q = so.planted_queries(G[[5, 2999, 1234]], noise=0.5, seed=1)
+    s, i = g.topk(q, 1)
+    _check_topk(s, i, so.sims(G, q), 1)
+    assert i[:, 0].tolist() == [5, 2999, 1234]
+    g.close()
