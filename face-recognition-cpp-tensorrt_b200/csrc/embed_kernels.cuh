@@ -34,8 +34,10 @@ __global__ void __launch_bounds__(128) arcface_stem_kernel(const void* __restric
         sbb[threadIdx.x] = bn_b ? bn_b[threadIdx.x] : 0.f;
     }
     __syncthreads();
-    const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (pix >= static_cast<long long>(batch) * S * S) return;
+    // grid-stride over the pixels: the 6.9 KiB of weights staged above are amortised over several pixels per thread
+    const long long total = static_cast<long long>(batch) * S * S;
+    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int img = static_cast<int>(pix / (S * S));
     const int rc = static_cast<int>(pix - static_cast<long long>(img) * S * S);
     const int r = rc / S, c = rc % S;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(128) arcface_stem_kernel(const void* __restric
             d1[0] = pb[0];
             d1[1] = pb[1];
         }
+    }
     }
 }
 

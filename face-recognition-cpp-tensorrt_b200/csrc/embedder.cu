@@ -148,7 +148,7 @@ void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
 void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cudaStream_t st = nullptr) {
     if (!st) st = e->stream;
     const long long pixels = static_cast<long long>(batch) * 112 * 112;
-    const int blocks = static_cast<int>((pixels + 127) / 128);
+    const int blocks = static_cast<int>(std::min<long long>((pixels + 127) / 128, 148LL * 16));  // grid-stride inside the kernel
     if (u8_input)
         arcface_stem_kernel<true><<<blocks, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
                                                           e->stem_y.p, e->stem_yb.p);
