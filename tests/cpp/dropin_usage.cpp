@@ -99,6 +99,19 @@ int main(int argc, char **argv) {
     recognizer.initMatMul();
     std::tie(names, best) = recognizer.getOutputs(recognizer.featureMatching());
     if (names[0] != "only") return 28;
+    // enrolment without a reload: append / remove on the resident gallery through the MatMul extension
+    {
+        MatMul mm;
+        mm.init(e0.data(), 1, 512);
+        mm.append(emb1, 1);
+        float s2[2];
+        int64_t r2[2];
+        mm.search(emb1, 1, 2, s2, r2);
+        if (r2[0] != 1 || std::fabs(s2[0] - 1.f) > 1e-4) return 29;
+        if (mm.remove(0) != 1) return 30;  // the last row (emb1) moved into slot 0
+        mm.search(emb1, 1, 1, s2, r2);
+        if (r2[0] != 0) return 31;
+    }
     std::printf("DROPIN OK: %zu faces, first box (%d,%d,%d,%d) score %.4f, top-1 %s %.4f\n", outputBbox.size(), outputBbox[0].x1, outputBbox[0].y1,
                 outputBbox[0].x2, outputBbox[0].y2, outputBbox[0].score, names2[0].c_str(), best2[0]);
     return 0;

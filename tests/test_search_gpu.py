@@ -389,7 +389,8 @@ def test_gallery_lifecycle_append_remove_clear(scan):
     g.reserve(20_000)
     assert g.capacity >= 20_000
     check()
-    for row in (0, 4321, len(model) - 1, 17):   # deletions: the last row moves into the slot
+    for pick in (0, 4321, -1, 17):              # deletions (-1 = the last row itself): the last row moves into the slot
+        row = pick if pick >= 0 else len(model) - 1
         moved = g.remove(row)
         assert moved == len(model) - 1
         model[row] = model[moved]
