@@ -36,13 +36,13 @@ __device__ __forceinline__ unsigned int ld_flag_system(const unsigned int* p) {
     return v;
 }
 
-// the call sequence number lives in device memory so that a CUDA graph of the step can be replayed: a 1-thread kernel advances
-// it (stream-ordered) before the exchange kernel of the same call reads it
-__global__ void exchange_tick_kernel(unsigned int* epoch) { *epoch += 1; }
+// The call sequence number lives in device memory so that a CUDA graph of the step can be replayed. Every block of a call reads
+// epoch_state[0] + 1 when it starts; the block that finishes last (ticket counter epoch_state[1]) stores the new value, i.e. after
+// every block of the call has read the old one and before the next call (stream order) starts.
 
 // grid = nq blocks of 64 threads. local_s / local_i: this rank's nq x k results (global row ids).
 __global__ void __launch_bounds__(64) exchange_merge_kernel(XPeers peers, int world, int rank, int nq_max, int k_max, int nq, int k,
-                                                            const unsigned int* __restrict__ epoch_ptr, const float* __restrict__ local_s,
+                                                            unsigned int* epoch_state, const float* __restrict__ local_s,
                                                             const long long* __restrict__ local_i, float* __restrict__ out_s,
                                                             long long* __restrict__ out_i) {
     __shared__ float cs[16 * kTopkMax];
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(64) exchange_merge_kernel(XPeers peers, int wo
     __shared__ long long red_i[32];
     __shared__ int red_p[32];
     const int q = blockIdx.x;
-    const unsigned int epoch = *epoch_ptr;
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(epoch_state) + 1u;
     const int par = epoch & 1;
     const size_t slot = ((static_cast<size_t>(par) * world + rank) * nq_max + q) * k_max;  // my slot in every mailbox
     // (a) push: thread t -> (peer t / k, entry t % k)
@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(64) exchange_merge_kernel(XPeers peers, int wo
         out_s[static_cast<size_t>(q) * k + threadIdx.x] = sel_s[threadIdx.x];
         out_i[static_cast<size_t>(q) * k + threadIdx.x] = sel_i[threadIdx.x];
     }
+    if (threadIdx.x == 0 && atomicAdd(epoch_state + 1, 1u) == gridDim.x - 1) {
+        epoch_state[1] = 0u;
+        epoch_state[0] = epoch;
+    }
 }
 
 }  // namespace
@@ -125,8 +129,8 @@ int fr_exchange_create(int device, int world, int rank, int nq_max, int k_max, F
         x->flag_bytes = sizeof(unsigned int) * 2 * world * nq_max;
         FRB_CUDA(cudaMalloc(&x->base, x->entry_bytes + x->flag_bytes));
         FRB_CUDA(cudaMemset(x->base, 0, x->entry_bytes + x->flag_bytes));
-        FRB_CUDA(cudaMalloc(&x->epoch_dev, sizeof(unsigned int)));
-        FRB_CUDA(cudaMemset(x->epoch_dev, 0, sizeof(unsigned int)));
+        FRB_CUDA(cudaMalloc(&x->epoch_dev, 2 * sizeof(unsigned int)));  // [0] calls completed, [1] finished-block ticket of the running call
+        FRB_CUDA(cudaMemset(x->epoch_dev, 0, 2 * sizeof(unsigned int)));
         FRB_CUDA(cudaDeviceSynchronize());
         *out = x.release();
     });
@@ -191,12 +195,11 @@ int fr_exchange_merge_dev(FrExchange* x, const float* local_scores_dev, const in
         if (!x->connected) throw StateError{"exchange not connected"};
         if (nq < 1 || nq > x->nq_max || k < 1 || k > x->k_max) throw ArgError{"nq/k exceed the exchange's capacity"};
         DeviceGuard dg(x->device);
-        exchange_tick_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(x->epoch_dev);
         exchange_merge_kernel<<<nq, 64, 0, static_cast<cudaStream_t>(stream)>>>(x->peers, x->world, x->rank, x->nq_max, x->k_max, nq, k, x->epoch_dev,
                                                                                local_scores_dev,
                                                                                reinterpret_cast<const long long*>(local_idx_dev), scores_dev,
                                                                                reinterpret_cast<long long*>(idx_dev));
-        count_launch(2);
+        count_launch();
         FRB_CUDA(cudaGetLastError());
     });
 }

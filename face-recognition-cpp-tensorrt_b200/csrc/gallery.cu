@@ -42,6 +42,7 @@ struct FrGallery {
     uint2* app_buf = nullptr;        // append epilogue: [lists <= 296][256][kAppCap] (coarse score bits, local row), allocated on first use
     int* app_cnt = nullptr;          // [lists][256] entries appended
     int* flags = nullptr;            // [0] = count, [1..256] = queries handed to the exact scan
+    unsigned int* scan_ticket = nullptr;  // finished-block counter of the exact-scan fix-up (0 between launches)
     float* part_s = nullptr;         // exact scan partials [256][slices][8]
     long long* part_i = nullptr;
     float* res_s = nullptr;          // 256 x FR_TOPK_MAX
@@ -72,6 +73,8 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMalloc(&g->cand_s, sizeof(float) * kMaxLists * kChunkQ * 16));
     FRB_CUDA(cudaMalloc(&g->cand_i, sizeof(int) * kMaxLists * kChunkQ * 16));
     FRB_CUDA(cudaMalloc(&g->flags, sizeof(int) * (kChunkQ + 1)));
+    FRB_CUDA(cudaMalloc(&g->scan_ticket, sizeof(unsigned int)));
+    FRB_CUDA(cudaMemsetAsync(g->scan_ticket, 0, sizeof(unsigned int), g->stream));
     FRB_CUDA(cudaMalloc(&g->gbest, sizeof(int) * kChunkQ));
     FRB_CUDA(cudaMemsetAsync(g->gbest, 0, sizeof(int) * kChunkQ, g->stream));
     FRB_CUDA(cudaMalloc(&g->part_s, sizeof(float) * kChunkQ * kScanSlicesMax * kTopkMax));
@@ -231,10 +234,13 @@ void launch_exact(FrGallery* g, const float* q_dev, int nq, int k, const int* fl
     const int slices = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->n + 7) / 8, std::min(kScanSlicesMax, 2 * g->sms))));
     // flagged-query fix-up: one pass of blocks that loop over the (normally empty) list; exact path: spread the queries too
     const int qsplit = flags ? 1 : std::min(nq, 64);
-    exact_scan_kernel<<<dim3(slices, qsplit), kScanThreads, 0, st>>>(g->rows_f32, g->n, q_dev, nq, flags, g->part_s, g->part_i);
-    exact_merge_kernel<<<flags ? 8 : std::min(nq, 148), kSelThreads, 0, st>>>(g->part_s, g->part_i, slices, nq, flags, k, g->row_offset,
-                                                                          scores_dev, idx_dev);
-    count_launch(2);
+    exact_scan_kernel<<<dim3(slices, qsplit), kScanThreads, 0, st>>>(g->rows_f32, g->n, q_dev, nq, flags, g->part_s, g->part_i, k, g->row_offset,
+                                                                     scores_dev, idx_dev, g->scan_ticket);
+    count_launch();
+    if (!flags) {  // all queries: the merge is spread over its own grid; the fix-up's last block merges in the same launch
+        exact_merge_kernel<<<std::min(nq, 148), kSelThreads, 0, st>>>(g->part_s, g->part_i, slices, nq, flags, k, g->row_offset, scores_dev, idx_dev);
+        count_launch();
+    }
     FRB_CUDA(cudaGetLastError());
 }
 
@@ -296,7 +302,7 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     launch_exact(g, q_dev, nq, k, g->flags, scores_dev, idx_dev, st);
     g->stats.scan_bytes = g->n * kDim * (f8 ? 1 : 2);
     g->stats.flops = 2LL * (cg * kQRows) * g->n * kDim;
-    g->stats.launches = 5;
+    g->stats.launches = 4;
     g->stats.ctas = units * cg;
 }
 
@@ -390,6 +396,7 @@ void fr_gallery_destroy(FrGallery* g) {
     cudaFree(g->cand_s);
     cudaFree(g->cand_i);
     cudaFree(g->flags);
+    cudaFree(g->scan_ticket);
     cudaFree(g->gbest);
     cudaFree(g->app_buf);
     cudaFree(g->app_cnt);

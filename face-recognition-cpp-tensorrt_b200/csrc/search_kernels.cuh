@@ -1,13 +1,16 @@
 // Device code of the cosine-similarity search:
-//   cosine_topk_coarse<CG,KSEL>  fused  Q x 512 · (N x 512)^T  on tcgen05 tensor cores (fp16 in, fp32 accumulate in TMEM)
-//                                + running candidate list per query in registers; the similarity matrix is never written.
-//   topk_rerank_kernel           merges the per-CTA candidate lists, keeps every row whose coarse score is within the
-//                                provable fp16 error margin of the k-th best, re-scores those in exact fp32 from the fp32 master
-//                                rows and orders them by (score desc, row asc). Queries whose candidate set could be
-//                                incomplete are flagged and recomputed by the exact scan.
+//   prep_queries_kernel<F8>      the scan's query operand (fp16 or scaled e4m3, row-major) + the per-query margin, once per search.
+//   cosine_topk_coarse<CG,KSEL,F8,APP>  fused  Q x 512 · (N x 512)^T  on tcgen05 tensor cores (fp16 or e4m3 in, fp32 accumulate in
+//                                TMEM) + a running candidate set per query; the similarity matrix is never written.
+//                                APP (top-1): predicated appends to per-thread buffers behind a shared per-query threshold;
+//                                otherwise (k > 1): sorted candidate lists in registers.
+//   append_rerank_kernel / topk_rerank_kernel   keep every candidate whose coarse score is within the margin of the (k-th) best,
+//                                re-score those in exact fp32 from the fp32 master rows and order them by (score desc, row asc).
+//                                Queries whose candidate set could be incomplete are flagged and recomputed by the exact scan.
 //   exact_scan_kernel / exact_merge_kernel   exact fp32 scan (small galleries, flagged queries, FR_PATH_EXACT).
 //   sims_kernel                  exact fp32 dense similarities (MatMul::calculate, /root/reference src/matmul.cpp:36-77).
 //   topk_merge_kernel            merge of per-shard (score, idx) lists after the cross-GPU all-gather.
+//   make_scan_copy_kernel / make_f8_copy_kernel   the resident scan copies and the norm bounds the margins scale with.
 // Ordering everywhere: (score descending, row index ascending) — for k = 1 this is std::max_element's "first maximum"
 // (ArcFaceIR50::getOutputs, /root/reference src/arcface.cpp:210).
 #pragma once
@@ -747,11 +750,16 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
 // exact fp32 scan. flag_list == nullptr: all nq queries; else the flag_list[0] queries listed in flag_list[1..].
 // grid (slices, qsplit), 256 threads: block (s, y) handles queries y, y + qsplit, ...; warp w of slice s scores rows
 // s*8+w, s*8+w + 8*slices, ... and keeps its top-k; the block merges its 8 warps.  part_s / part_i: [nq][slices][kTopkMax]
+// Fix-up mode (flag_list != nullptr, grid.y == 1): nothing flagged -> every block returns at once; otherwise the block that finishes
+// last (ticket) also merges the slices of the flagged queries into out_s / out_i, so the fix-up is ONE launch per search.
 constexpr int kScanThreads = 256;
+constexpr int kScanSlicesMax = 148 * 2;
 __global__ void __launch_bounds__(kScanThreads) exact_scan_kernel(const float* __restrict__ rows, long long n, const float* __restrict__ q,
-                                                                  int nq, const int* __restrict__ flag_list, float* __restrict__ part_s,
-                                                                  long long* __restrict__ part_i) {
+                                                                  int nq, const int* __restrict__ flag_list, float* part_s, long long* part_i,
+                                                                  int k, long long row_offset, float* __restrict__ out_s,
+                                                                  long long* __restrict__ out_i, unsigned int* __restrict__ ticket) {
     const int total = flag_list ? flag_list[0] : nq;
+    if (total == 0) return;
     for (int f = blockIdx.y; f < total; f += gridDim.y) {
     const int qi = flag_list ? flag_list[1 + f] : f;
     __shared__ float cs[8 * kTopkMax];
@@ -794,9 +802,43 @@ __global__ void __launch_bounds__(kScanThreads) exact_scan_kernel(const float* _
     }
     __syncthreads();
     }
+    if (!flag_list) return;
+    // fix-up mode: last block merges
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (is_last) *ticket = 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    __shared__ float ms[kScanSlicesMax * kTopkMax];
+    __shared__ long long mi[kScanSlicesMax * kTopkMax];
+    __shared__ float msel_s[kTopkMax];
+    __shared__ long long msel_i[kTopkMax];
+    __shared__ float mred_s[32];
+    __shared__ long long mred_i[32];
+    __shared__ int mred_p[32];
+    const int slices = gridDim.x, count = slices * kTopkMax;
+    for (int f = 0; f < total; ++f) {
+        const int qi = flag_list[1 + f];
+        for (int p = threadIdx.x; p < count; p += blockDim.x) {
+            ms[p] = __ldcg(part_s + static_cast<size_t>(qi) * count + p);
+            mi[p] = __ldcg(part_i + static_cast<size_t>(qi) * count + p);
+        }
+        __syncthreads();
+        block_select(ms, mi, count, k, msel_s, msel_i, mred_s, mred_i, mred_p);
+        if (threadIdx.x < k) {
+            const long long id = msel_i[threadIdx.x];
+            out_s[static_cast<size_t>(qi) * k + threadIdx.x] = msel_s[threadIdx.x];
+            out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
+        }
+        __syncthreads();
+    }
 }
-// second half of the exact scan: merge the slices of each flagged query and write the final nq x k result
-constexpr int kScanSlicesMax = 148 * 2;
+// second half of the exact scan (FR_PATH_EXACT: all queries): merge the slices of each query and write the final nq x k result
 __global__ void __launch_bounds__(kSelThreads) exact_merge_kernel(const float* __restrict__ part_s, const long long* __restrict__ part_i,
                                                                   int slices, int nq, const int* __restrict__ flag_list, int k,
                                                                   long long row_offset, float* __restrict__ out_s,
