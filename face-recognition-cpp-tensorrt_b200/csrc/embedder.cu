@@ -119,11 +119,13 @@ DevBuf make_buf(FrEmbedder* e, size_t rows, int C) {
     return b;
 }
 
-// FR_HALO=1 switches the stride-1 3x3 convs to conv3x3_halo_kernel (one halo tile per channel block instead of nine per-tap loads).
-// Measured on B200 (IR-SE-50): 1.55 vs 1.64 ms at batch 32, but 8.65 vs 7.54 ms at batch 256, so it is not the default.
+// conv3x3_halo_kernel (one halo tile per channel block instead of nine per-tap loads) policy, FR_HALO: 0 = never, 1 = only the
+// 64-input-channel layers (one channel block: the layers that are most L2-bound per tap, and the halo tile + weight ring still let two
+// CTAs share an SM), 2 = every stride-1 3x3 conv. Measured on B200 (IR-SE-50) for FR_HALO=2: 1.55 vs 1.64 ms at batch 32 but 8.65 vs
+// 7.54 ms at batch 256 (with two halo buffers only one CTA fits per SM on the 128..512-channel layers).
 // The tap operands start at 128-byte-row offsets inside the 1024-byte swizzle atom; the hardware swizzles on absolute shared-memory
 // address bits, so the descriptor's base-offset field must stay 0 (setting it to (addr >> 7) & 7 breaks parity: measured).
-const bool g_use_halo = std::getenv("FR_HALO") != nullptr && std::atoi(std::getenv("FR_HALO")) != 0;
+const int g_halo_level = std::getenv("FR_HALO") ? std::atoi(std::getenv("FR_HALO")) : 0;
 const int g_halo_baseoff = 0;
 
 template <int BN>
@@ -131,7 +133,7 @@ void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
     ConvGemmParams prm = s.prm;
     prm.P = P;
     dim3 grid((P + kConvBM - 1) / kConvBM, prm.cout / BN, s.splits);
-    if (g_use_halo && prm.taps == 9 && !prm.tap_phase && s.splits == 1) {
+    if (prm.taps == 9 && !prm.tap_phase && s.splits == 1 && (g_halo_level >= 2 || (g_halo_level == 1 && prm.cin_blocks == 1))) {
         // 3x3 stride-1 conv: one halo tile per 64-channel block feeds all nine taps (conv3x3_halo_kernel)
         prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
         prm.halo_bufs = prm.cin_blocks > 1 ? 2 : 1;
