@@ -119,13 +119,14 @@ DevBuf make_buf(FrEmbedder* e, size_t rows, int C) {
     return b;
 }
 
-// conv3x3_halo_kernel (one halo tile per channel block instead of nine per-tap loads) policy, FR_HALO: 0 = never, 1 = only the
+// conv3x3_halo_kernel (one halo tile per channel block instead of nine per-tap loads) policy, FR_HALO: 0 = never, 1 (default) = only the
 // 64-input-channel layers (one channel block: the layers that are most L2-bound per tap, and the halo tile + weight ring still let two
 // CTAs share an SM), 2 = every stride-1 3x3 conv. Measured on B200 (IR-SE-50) for FR_HALO=2: 1.55 vs 1.64 ms at batch 32 but 8.65 vs
-// 7.54 ms at batch 256 (with two halo buffers only one CTA fits per SM on the 128..512-channel layers).
+// 7.54 ms at batch 256 (with two halo buffers only one CTA fits per SM on the 128..512-channel layers); FR_HALO=1: 1.576 vs 1.601 ms
+// at batch 32 and 7.43 vs 7.52 ms at batch 256 (gpurun_out/halo_policy.txt, two interleaved runs each).
 // The tap operands start at 128-byte-row offsets inside the 1024-byte swizzle atom; the hardware swizzles on absolute shared-memory
 // address bits, so the descriptor's base-offset field must stay 0 (setting it to (addr >> 7) & 7 breaks parity: measured).
-const int g_halo_level = std::getenv("FR_HALO") ? std::atoi(std::getenv("FR_HALO")) : 0;
+const int g_halo_level = std::getenv("FR_HALO") ? std::atoi(std::getenv("FR_HALO")) : 1;
 const int g_halo_baseoff = 0;
 
 template <int BN>
