@@ -119,7 +119,9 @@ int fr_gallery_set_path(FrGallery *g, int path);
  * the tensor rate; rows whose coarse score is within margin = 6.5 * sqrt(2) * 0.0373 * |q|_4 * max_rows |g|_4 of the best coarse score
  * (about 0.03 for isotropic unit vectors) are re-scored in exact fp32: exact unless the rounding errors of two scores exceed 6.5 sigma
  * of the bound on their standard deviation (no useful provable bound exists for fp8; csrc/search_kernels.cuh, tools/f8_error_model.py).
- * Scores returned are exact fp32 either way. */
+ * Scores returned are exact fp32 either way. Top-1 searches (the reference's getOutputs) use the append epilogue and stay fast for
+ * queries without a match; k > 1 on the e4m3 copy keeps the sorted-list epilogue, whose 16-entry lists overflow under the wide
+ * margin when nothing matches — such queries are recomputed by the exact fp32 scan (correct, slow): prefer FR_SCAN_F16 for k > 1. */
 #define FR_SCAN_F16 0
 #define FR_SCAN_F8 1
 int fr_gallery_set_scan(FrGallery *g, int scan);
