@@ -145,7 +145,7 @@ void fr_exchange_destroy(FrExchange *x);
 
 /* roofline bookkeeping for bench.py: algorithmic bytes/flops of the dominant kernel of the last topk call */
 typedef struct FrSearchStats {
-    int64_t scan_bytes; /* bytes of the resident scan copy streamed (n_rows * dim * 2) */
+    int64_t scan_bytes; /* bytes of the resident scan copy streamed (n_rows * dim * 2 for the fp16 copy, * 1 for the e4m3 copy) */
     int64_t flops;      /* 2 * nq_padded * n_rows * dim */
     int launches;       /* kernels launched by the last call */
     int ctas;           /* CTAs of the fused kernel */
