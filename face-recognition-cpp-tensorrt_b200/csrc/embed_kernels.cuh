@@ -13,8 +13,113 @@ namespace frb {
 // Input: either the tensor ArcFaceIR50::preprocessFaces produces (f32 planar R,G,B, (x-127.5)*0.0078125, src/arcface.cpp:118-125)
 // or the u8 BGR HWC crop itself (the same arithmetic is applied on the fly).
 // Output (shared-halo flat NHWC, H = W = 112): y and y_bn = y * bn_s + bn_b (unit 0's pre-activation BN).
-// One thread per pixel, 64 output channels in four groups of 16.
+// One thread per PAIR of horizontally adjacent pixels, 64 output channels in four groups of 16: every weight vector fetched from
+// shared memory (LDS.128, broadcast) feeds eight FMAs instead of four, and the pair shares 6 of its 9 input columns. Each output is
+// the same bias + 27-term FMA chain in the same order as a one-pixel-per-thread kernel (bit-identical results).
 // ---------------------------------------------------------------------------------------------------------------
+template <bool kU8>
+__global__ void __launch_bounds__(128) arcface_stem_pair_kernel(const void* __restrict__ in, int batch, const float* __restrict__ w /*[64][27]*/,
+                                                           const float* __restrict__ bias, const float* __restrict__ prelu,
+                                                           const float* __restrict__ bn_s, const float* __restrict__ bn_b,
+                                                           __half* __restrict__ y, __half* __restrict__ y_bn) {
+    constexpr int S = 112, Wp = S + 1, HpWp = Wp * Wp, kPairsPerRow = S / 2;
+    __shared__ float4 ws[27][16];  // ws[k][n/4] = w[n..n+3][k]
+    __shared__ float sb[64], sp[64], ss[64], sbb[64];
+    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+        const int k = i / 64, n = i % 64;
+        reinterpret_cast<float*>(&ws[k][0])[n] = w[n * 27 + k];
+    }
+    if (threadIdx.x < 64) {
+        sb[threadIdx.x] = bias[threadIdx.x];
+        sp[threadIdx.x] = prelu[threadIdx.x];
+        ss[threadIdx.x] = bn_s ? bn_s[threadIdx.x] : 1.f;
+        sbb[threadIdx.x] = bn_b ? bn_b[threadIdx.x] : 0.f;
+    }
+    __syncthreads();
+    // grid-stride over the pixel pairs: the 6.9 KiB of weights staged above are amortised over several pairs per thread
+    const long long total = static_cast<long long>(batch) * S * kPairsPerRow;
+    for (long long pr = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pr < total;
+         pr += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int img = static_cast<int>(pr / (S * kPairsPerRow));
+        const int rc = static_cast<int>(pr - static_cast<long long>(img) * S * kPairsPerRow);
+        const int r = rc / kPairsPerRow, c = (rc % kPairsPerRow) * 2;
+        float xin[3][4][3];  // [ky][input column c - 1 + j][ch], ch in R,G,B order
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int rr = r + ky - 1, cc = c + j - 1;
+                const bool ok = rr >= 0 && rr < S && cc >= 0 && cc < S;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    float v = 0.f;
+                    if (ok) {
+                        if (kU8) {
+                            const uint8_t u = static_cast<const uint8_t*>(in)[(static_cast<size_t>(img) * S * S + rr * S + cc) * 3 + (2 - ch)];
+                            v = (static_cast<float>(u) - 127.5f) * 0.0078125f;
+                        } else {
+                            v = static_cast<const float*>(in)[(static_cast<size_t>(img) * 3 + ch) * S * S + rr * S + cc];
+                        }
+                    }
+                    xin[ky][j][ch] = v;
+                }
+            }
+        const size_t o = (static_cast<size_t>(img) * HpWp + r * Wp + c) * 64;  // pixel c; pixel c + 1 follows 64 channels later
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+            float acc[2][16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = sb[g * 16 + j];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const int k = (ky * 3 + kx) * 3 + ch;
+                        const float a0 = xin[ky][kx][ch], a1 = xin[ky][kx + 1][ch];
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 wv = ws[k][g * 4 + j4];
+                            acc[0][4 * j4 + 0] = fmaf(a0, wv.x, acc[0][4 * j4 + 0]);
+                            acc[0][4 * j4 + 1] = fmaf(a0, wv.y, acc[0][4 * j4 + 1]);
+                            acc[0][4 * j4 + 2] = fmaf(a0, wv.z, acc[0][4 * j4 + 2]);
+                            acc[0][4 * j4 + 3] = fmaf(a0, wv.w, acc[0][4 * j4 + 3]);
+                            acc[1][4 * j4 + 0] = fmaf(a1, wv.x, acc[1][4 * j4 + 0]);
+                            acc[1][4 * j4 + 1] = fmaf(a1, wv.y, acc[1][4 * j4 + 1]);
+                            acc[1][4 * j4 + 2] = fmaf(a1, wv.z, acc[1][4 * j4 + 2]);
+                            acc[1][4 * j4 + 3] = fmaf(a1, wv.w, acc[1][4 * j4 + 3]);
+                        }
+                    }
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                uint4 pk[2], pb[2];
+                __half2* hp = reinterpret_cast<__half2*>(pk);
+                __half2* hb = reinterpret_cast<__half2*>(pb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = g * 16 + 2 * j;
+                    float a = acc[px][2 * j], b = acc[px][2 * j + 1];
+                    a = a > 0.f ? a : a * sp[n];
+                    b = b > 0.f ? b : b * sp[n + 1];
+                    hp[j] = __floats2half2_rn(a, b);
+                    const float2 yr = __half22float2(hp[j]);
+                    hb[j] = __floats2half2_rn(fmaf(yr.x, ss[n], sbb[n]), fmaf(yr.y, ss[n + 1], sbb[n + 1]));
+                }
+                uint4* d0 = reinterpret_cast<uint4*>(y + o + px * 64 + g * 16);
+                d0[0] = pk[0];
+                d0[1] = pk[1];
+                if (y_bn) {
+                    uint4* d1 = reinterpret_cast<uint4*>(y_bn + o + px * 64 + g * 16);
+                    d1[0] = pb[0];
+                    d1[1] = pb[1];
+                }
+            }
+        }
+    }
+}
+
+// one thread per pixel (FR_STEM_PAIR=0; see the A/B note at the launch site in embedder.cu)
 template <bool kU8>
 __global__ void __launch_bounds__(128) arcface_stem_kernel(const void* __restrict__ in, int batch, const float* __restrict__ w /*[64][27]*/,
                                                            const float* __restrict__ bias, const float* __restrict__ prelu,

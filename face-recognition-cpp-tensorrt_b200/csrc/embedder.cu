@@ -150,14 +150,25 @@ void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
 
 void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cudaStream_t st = nullptr) {
     if (!st) st = e->stream;
-    const long long pixels = static_cast<long long>(batch) * 112 * 112;
-    const int blocks = static_cast<int>(std::min<long long>((pixels + 127) / 128, 148LL * 16));  // grid-stride inside the kernel
-    if (u8_input)
+    // one thread per pair of adjacent pixels (arcface_stem_pair_kernel, default) or per pixel (FR_STEM_PAIR=0); bit-identical outputs.
+    // A/B on B200, whole IR-SE-50 forward, two interleaved runs each: 1.545 vs 1.569 ms at batch 32, 7.30 vs 7.36 ms at batch 256.
+    static const bool stem_pair = std::getenv("FR_STEM_PAIR") == nullptr || std::atoi(std::getenv("FR_STEM_PAIR")) != 0;
+    const long long work = static_cast<long long>(batch) * 112 * (stem_pair ? 56 : 112);
+    const int blocks = static_cast<int>(std::min<long long>((work + 127) / 128, 148LL * 16));  // grid-stride inside the kernels
+    if (stem_pair) {
+        if (u8_input)
+            arcface_stem_pair_kernel<true><<<blocks, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
+                                                                   e->stem_y.p, e->stem_yb.p);
+        else
+            arcface_stem_pair_kernel<false><<<blocks, 128, 0, st>>>(e->in_f32, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
+                                                                    e->stem_y.p, e->stem_yb.p);
+    } else if (u8_input) {
         arcface_stem_kernel<true><<<blocks, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
                                                           e->stem_y.p, e->stem_yb.p);
-    else
+    } else {
         arcface_stem_kernel<false><<<blocks, 128, 0, st>>>(e->in_f32, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
                                                            e->stem_y.p, e->stem_yb.p);
+    }
     count_launch();
     for (const Step& s : e->steps) {
         if (s.unit > stop_after_unit) break;
