@@ -550,4 +550,237 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 stride-1 conv, 64 -> 64 channels, WEIGHT-STATIONARY and PERSISTENT (experimental: FR_HALO=3).
+// The whole weight matrix of such a layer is 9 taps x 64 x 64 fp16 = 72 KiB: every CTA loads it ONCE and then walks position tiles
+// (tile = blockIdx.x, + gridDim.x, ...), fetching per tile only the halo tile of conv3x3_halo_kernel (double buffered) - 32-48 KiB of
+// L2 traffic per [128 x 64] tile instead of 216 KiB (conv_gemm_kernel) or 104-120 KiB (conv3x3_halo_kernel). Two 64-column TMEM
+// accumulators are ping-ponged: the epilogue of tile i (all 64 columns read to registers, accumulator released at once) overlaps
+// the MMAs of tile i + 1. Same parameters, tensor maps and epilogue arithmetic as conv_gemm_kernel<64>.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWsBN = 64;
+constexpr int kWsWeightBytes = 9 * kWsBN * 128;  // 72 KiB
+__global__ void __launch_bounds__(kConvThreads)
+conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ ConvGemmParams prm) {
+    constexpr int BN = kWsBN;
+    constexpr int kABytes = kConvBM * 128, kBBytes = BN * 128;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    // [halo buffers: 2 x halo_chunks x 16 KiB][weights: 9 x 8 KiB][barriers][epilogue params]
+    const int halo_bytes = prm.halo_chunks * kABytes;
+    uint8_t* wsm = smem + 2 * halo_bytes;
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(wsm + kWsWeightBytes);
+    uint64_t* hfull_bar = w_bar + 1;       // [2] halo tile landed
+    uint64_t* hempty_bar = hfull_bar + 2;  // [2] halo tile consumed by all nine taps
+    uint64_t* tfull_bar = hempty_bar + 2;  // [2] accumulator complete
+    uint64_t* tempty_bar = tfull_bar + 2;  // [2] accumulator read out by the four epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(wsm + kWsWeightBytes + 256);
+    float* s_prelu = s_bias + BN;
+    float* s_bns = s_prelu + BN;
+    float* s_bnb = s_bns + BN;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int Wp = prm.W + 1;
+    const int tiles = (prm.P + kConvBM - 1) / kConvBM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(w_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&hfull_bar[b], 1);
+            mbar_init(&hempty_bar[b], 1);
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+    if (warp >= 4) {
+        for (int i = threadIdx.x - 128; i < BN; i += 128) {
+            s_bias[i] = prm.bias ? __ldg(prm.bias + i) : 0.f;
+            s_prelu[i] = prm.prelu ? __ldg(prm.prelu + i) : 1.f;
+            s_bns[i] = prm.out_bn ? __ldg(prm.bn_s + i) : 1.f;
+            s_bnb[i] = prm.out_bn ? __ldg(prm.bn_b + i) : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(w_bar, kWsWeightBytes);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(wsm + tap * kBBytes, &tmap_b, w_bar, tap * 64, 0, kEvictLast);
+            int i = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait(&hempty_bar[buf], ((i >> 1) & 1) ^ 1);
+                mbar_expect_tx(&hfull_bar[buf], halo_bytes);
+                for (int ch = 0; ch < prm.halo_chunks; ++ch)
+                    tma_load_2d(smem + buf * halo_bytes + ch * kABytes, &tmap_a, &hfull_bar[buf], 0, t * kConvBM - Wp - 1 + ch * kConvBM,
+                                kEvictNormal);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc(kConvBM, BN, 0, 0);
+            mbar_wait(w_bar, 0);
+            tc_fence_after();
+            const uint32_t w_addr = smem_u32(wsm);
+            int i = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+                const int buf = i & 1;
+                const uint32_t ph = (i >> 1) & 1;
+                mbar_wait(&tempty_bar[buf], ph ^ 1);
+                tc_fence_after();
+                mbar_wait(&hfull_bar[buf], ph);
+                tc_fence_after();
+                const uint32_t halo_addr = smem_u32(smem + buf * halo_bytes);
+                const uint32_t d_tmem = tmem_base + buf * BN;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3, dx = tap - dy * 3;
+                    const uint32_t a_addr = halo_addr + static_cast<uint32_t>(dy * Wp + dx) * 128u;  // row-shifted view, base offset 0
+                    const uint32_t b_addr = w_addr + tap * kBBytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (tap > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&hempty_bar[buf]);
+                umma_commit(&tfull_bar[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue: lane = output position ----------------
+        const int ew = warp & 3;
+        const int HpWp = (prm.H + 1) * Wp;
+        const int ldo = prm.ld_out ? prm.ld_out : prm.cout;
+        const int ldr = prm.ld_res ? prm.ld_res : prm.cout;
+        int i = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int p = t * kConvBM + ew * 32 + lane;
+            const int img = p / HpWp;
+            const int rem = p - img * HpWp;
+            const int r = rem / Wp;
+            const int c = rem - r * Wp;
+            const bool valid = p < prm.P && r < prm.H && c < prm.W;
+            size_t o_main = 0, o_sub = 0, o_res = 0;
+            bool sub_ok = false;
+            if (valid) {
+                if (prm.out_mode == kOutPhaseSplit) {
+                    const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                    const int phs = ((r & 1) << 1) | (c & 1);
+                    o_main = static_cast<size_t>(phs) * prm.out_phase_rows + static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
+                } else {
+                    o_main = static_cast<size_t>(p);
+                }
+                if (prm.out_sub && !(r & 1) && !(c & 1)) {
+                    const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                    o_sub = static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
+                    sub_ok = true;
+                }
+                if (prm.res_mode == kResSame) {
+                    o_res = static_cast<size_t>(p);
+                } else if (prm.res_mode == kResSubsample) {
+                    const int W2p = 2 * prm.W + 1, H2pW2p = (2 * prm.H + 1) * W2p;
+                    o_res = static_cast<size_t>(img) * H2pW2p + (2 * r) * W2p + 2 * c;
+                } else if (prm.res_mode == kResUpsample) {
+                    const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                    o_res = static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
+                }
+            }
+            uint4 resv[BN / 8];
+            if (valid && prm.res_mode != kResNone) {
+                const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * ldr);
+#pragma unroll
+                for (int j = 0; j < BN / 8; ++j) resv[j] = __ldg(rp + j);
+            }
+            mbar_wait(&tfull_bar[buf], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
+            uint32_t raw0[16], raw1[16], raw2[16], raw3[16];
+            tmem_ld_32x32b_x16(taddr, raw0);
+            tmem_ld_32x32b_x16(taddr + 16, raw1);
+            tmem_ld_32x32b_x16(taddr + 32, raw2);
+            tmem_ld_32x32b_x16(taddr + 48, raw3);
+            tmem_ld_wait_x16(raw0);
+            tmem_ld_wait_x16(raw1);
+            tmem_ld_wait_x16(raw2);
+            tmem_ld_wait_x16(raw3);
+            // the accumulator is in registers: hand it back to the MMA warp before the arithmetic and the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (!valid) continue;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const uint32_t(&raw)[16] = q4 == 0 ? raw0 : (q4 == 1 ? raw1 : (q4 == 2 ? raw2 : raw3));
+                const int cc = q4 * 16;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + s_bias[cc + j];
+                if (prm.prelu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * s_prelu[cc + j];
+                }
+                if (prm.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (prm.res_mode != kResNone) {
+                    const uint4 r0 = resv[cc / 8], r1 = resv[cc / 8 + 1];
+                    const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                    const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+                        v[2 * j] += a.x;
+                        v[2 * j + 1] += a.y;
+                        v[8 + 2 * j] += b.x;
+                        v[8 + 2 * j + 1] += b.y;
+                    }
+                }
+                uint4 pk[2];
+                __half2* hp = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hp[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                if (prm.out) {
+                    uint4* dst = reinterpret_cast<uint4*>(prm.out + o_main * ldo + cc);
+                    dst[0] = pk[0];
+                    dst[1] = pk[1];
+                }
+                if (sub_ok) {
+                    uint4* dst = reinterpret_cast<uint4*>(prm.out_sub + o_sub * ldo + cc);
+                    dst[0] = pk[0];
+                    dst[1] = pk[1];
+                }
+                if (prm.out_bn) {
+                    uint4 pb[2];
+                    __half2* hb = reinterpret_cast<__half2*>(pb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 y = __half22float2(hp[j]);
+                        hb[j] = __floats2half2_rn(fmaf(y.x, s_bns[cc + 2 * j], s_bnb[cc + 2 * j]), fmaf(y.y, s_bns[cc + 2 * j + 1], s_bnb[cc + 2 * j + 1]));
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(prm.out_bn + o_main * ldo + cc);
+                    dst[0] = pb[0];
+                    dst[1] = pb[1];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+}
+
 }  // namespace frb

@@ -121,20 +121,28 @@ DevBuf make_buf(FrEmbedder* e, size_t rows, int C) {
 
 // conv3x3_halo_kernel (one halo tile per channel block instead of nine per-tap loads) policy, FR_HALO: 0 = never, 1 (default) = only the
 // 64-input-channel layers (one channel block: the layers that are most L2-bound per tap, and the halo tile + weight ring still let two
-// CTAs share an SM), 2 = every stride-1 3x3 conv. Measured on B200 (IR-SE-50) for FR_HALO=2: 1.55 vs 1.64 ms at batch 32 but 8.65 vs
+// CTAs share an SM), 2 = every stride-1 3x3 conv, 3 = experimental persistent weight-stationary kernel on the 64 -> 64 layers (others as 0). Measured on B200 (IR-SE-50) for FR_HALO=2: 1.55 vs 1.64 ms at batch 32 but 8.65 vs
 // 7.54 ms at batch 256 (with two halo buffers only one CTA fits per SM on the 128..512-channel layers); FR_HALO=1: 1.576 vs 1.601 ms
 // at batch 32 and 7.43 vs 7.52 ms at batch 256 (gpurun_out/halo_policy.txt, two interleaved runs each).
 // The tap operands start at 128-byte-row offsets inside the 1024-byte swizzle atom; the hardware swizzles on absolute shared-memory
 // address bits, so the descriptor's base-offset field must stay 0 (setting it to (addr >> 7) & 7 breaks parity: measured).
 const int g_halo_level = std::getenv("FR_HALO") ? std::atoi(std::getenv("FR_HALO")) : 1;
 const int g_halo_baseoff = 0;
+int g_conv_sms = 148;  // SM count of the embedder's device (set at create): grid of the persistent conv
 
 template <int BN>
 void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
     ConvGemmParams prm = s.prm;
     prm.P = P;
     dim3 grid((P + kConvBM - 1) / kConvBM, prm.cout / BN, s.splits);
-    if (prm.taps == 9 && !prm.tap_phase && s.splits == 1 && (g_halo_level >= 2 || (g_halo_level == 1 && prm.cin_blocks == 1))) {
+    if (BN == 64 && g_halo_level == 3 && prm.taps == 9 && !prm.tap_phase && s.splits == 1 && prm.cin_blocks == 1 && prm.cout == 64 &&
+        !prm.partial) {
+        // experimental: persistent weight-stationary 64 -> 64 conv (conv3x3_ws_kernel): weights loaded once per CTA, halo tiles streamed
+        prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
+        const int smem = 1024 + 2 * prm.halo_chunks * kConvBM * 128 + kWsWeightBytes + 256 + 4 * kWsBN * 4;
+        const int ctas = std::min<int>(static_cast<int>(grid.x), g_conv_sms);
+        conv3x3_ws_kernel<<<ctas, kConvThreads, smem, st>>>(s.ta, s.tb, prm);
+    } else if (prm.taps == 9 && !prm.tap_phase && s.splits == 1 && (g_halo_level >= 2 || (g_halo_level == 1 && prm.cin_blocks == 1))) {
         // 3x3 stride-1 conv: one halo tile per 64-channel block feeds all nine taps (conv3x3_halo_kernel)
         prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
         prm.halo_bufs = prm.cin_blocks > 1 ? 2 : 1;
@@ -485,6 +493,8 @@ int fr_embedder_create(const char* weights_path, int max_batch, int device, FrEm
             FRB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
+            g_conv_sms = e->sms;
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             FRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             FRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             build_plan(e.get(), wf);
