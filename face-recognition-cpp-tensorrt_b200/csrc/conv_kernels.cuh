@@ -560,7 +560,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kWsBN = 64;
 constexpr int kWsWeightBytes = 9 * kWsBN * 128;  // 72 KiB
-__global__ void __launch_bounds__(kConvThreads)
+static __global__ void __launch_bounds__(kConvThreads)  // static: this header is included by two translation units
 conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ ConvGemmParams prm) {
     constexpr int BN = kWsBN;
