@@ -560,7 +560,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kWsBN = 64;
 constexpr int kWsWeightBytes = 9 * kWsBN * 128;  // 72 KiB
-static __global__ void __launch_bounds__(kConvThreads)  // static: this header is included by two translation units
+// 8 epilogue warps (TMEM lane quarter x column half): with one persistent CTA per SM, four were not enough to write a tile's 32 KiB of
+// outputs inside the 1152 MMA cycles of the next tile (measured: 8.2 vs 7.2 ms for the whole forward at batch 256)
+constexpr int kWsThreads = 128 + 8 * 32;
+static __global__ void __launch_bounds__(kWsThreads)  // static: this header is included by two translation units
 conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ ConvGemmParams prm) {
     constexpr int BN = kWsBN;
@@ -568,13 +571,15 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    // [halo buffers: 2 x halo_chunks x 16 KiB][weights: 9 x 8 KiB][barriers][epilogue params]
+    // [halo buffers: NB x halo_chunks x 16 KiB][weights: 9 x 8 KiB][barriers][epilogue params]; NB = prm.halo_bufs (2..4) halo tiles
+    // in flight: with 2 the kernel is bound by the latency of ONE 32-48 KiB halo load per tile (measured, see embedder.cu)
     const int halo_bytes = prm.halo_chunks * kABytes;
-    uint8_t* wsm = smem + 2 * halo_bytes;
+    const int NB = prm.halo_bufs;
+    uint8_t* wsm = smem + NB * halo_bytes;
     uint64_t* w_bar = reinterpret_cast<uint64_t*>(wsm + kWsWeightBytes);
-    uint64_t* hfull_bar = w_bar + 1;       // [2] halo tile landed
-    uint64_t* hempty_bar = hfull_bar + 2;  // [2] halo tile consumed by all nine taps
-    uint64_t* tfull_bar = hempty_bar + 2;  // [2] accumulator complete
+    uint64_t* hfull_bar = w_bar + 1;       // [4] halo tile landed
+    uint64_t* hempty_bar = hfull_bar + 4;  // [4] halo tile consumed by all nine taps
+    uint64_t* tfull_bar = hempty_bar + 4;  // [2] accumulator complete
     uint64_t* tempty_bar = tfull_bar + 2;  // [2] accumulator read out by the four epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* s_bias = reinterpret_cast<float*>(wsm + kWsWeightBytes + 256);
@@ -593,17 +598,19 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         mbar_init(w_bar, 1);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(&hfull_bar[b], 1);
             mbar_init(&hempty_bar[b], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
-            mbar_init(&tempty_bar[b], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
     if (warp >= 4) {
-        for (int i = threadIdx.x - 128; i < BN; i += 128) {
+        for (int i = threadIdx.x - 128; i < BN; i += kWsThreads - 128) {
             s_bias[i] = prm.bias ? __ldg(prm.bias + i) : 0.f;
             s_prelu[i] = prm.prelu ? __ldg(prm.prelu + i) : 1.f;
             s_bns[i] = prm.out_bn ? __ldg(prm.bn_s + i) : 1.f;
@@ -619,14 +626,18 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (elect_one()) {
             mbar_expect_tx(w_bar, kWsWeightBytes);
             for (int tap = 0; tap < 9; ++tap) tma_load_2d(wsm + tap * kBBytes, &tmap_b, w_bar, tap * 64, 0, kEvictLast);
-            int i = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-                const int buf = i & 1;
-                mbar_wait(&hempty_bar[buf], ((i >> 1) & 1) ^ 1);
-                mbar_expect_tx(&hfull_bar[buf], halo_bytes);
+            int hb = 0;
+            uint32_t hph = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                mbar_wait(&hempty_bar[hb], hph ^ 1);
+                mbar_expect_tx(&hfull_bar[hb], halo_bytes);
                 for (int ch = 0; ch < prm.halo_chunks; ++ch)
-                    tma_load_2d(smem + buf * halo_bytes + ch * kABytes, &tmap_a, &hfull_bar[buf], 0, t * kConvBM - Wp - 1 + ch * kConvBM,
+                    tma_load_2d(smem + hb * halo_bytes + ch * kABytes, &tmap_a, &hfull_bar[hb], 0, t * kConvBM - Wp - 1 + ch * kConvBM,
                                 kEvictNormal);
+                if (++hb == NB) {
+                    hb = 0;
+                    hph ^= 1;
+                }
             }
         }
     } else if (warp == 1) {
@@ -635,15 +646,16 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             mbar_wait(w_bar, 0);
             tc_fence_after();
             const uint32_t w_addr = smem_u32(wsm);
-            int i = 0;
+            int i = 0, hb = 0;
+            uint32_t hph = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-                const int buf = i & 1;
+                const int buf = i & 1;  // accumulator
                 const uint32_t ph = (i >> 1) & 1;
                 mbar_wait(&tempty_bar[buf], ph ^ 1);
                 tc_fence_after();
-                mbar_wait(&hfull_bar[buf], ph);
+                mbar_wait(&hfull_bar[hb], hph);
                 tc_fence_after();
-                const uint32_t halo_addr = smem_u32(smem + buf * halo_bytes);
+                const uint32_t halo_addr = smem_u32(smem + hb * halo_bytes);
                 const uint32_t d_tmem = tmem_base + buf * BN;
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
@@ -654,13 +666,18 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     for (int k = 0; k < 4; ++k)
                         umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (tap > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(&hempty_bar[buf]);
+                umma_commit(&hempty_bar[hb]);
                 umma_commit(&tfull_bar[buf]);
+                if (++hb == NB) {
+                    hb = 0;
+                    hph ^= 1;
+                }
             }
         }
     } else if (warp >= 4) {
-        // ---------------- epilogue: lane = output position ----------------
+        // ---------------- epilogue: lane = output position, warp = (TMEM lane quarter, column half) ----------------
         const int ew = warp & 3;
+        const int c0 = ((warp - 4) >> 2) * (BN / 2);  // first of this warp's 32 output channels
         const int HpWp = (prm.H + 1) * Wp;
         const int ldo = prm.ld_out ? prm.ld_out : prm.cout;
         const int ldr = prm.ld_res ? prm.ld_res : prm.cout;
@@ -698,33 +715,29 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     o_res = static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
                 }
             }
-            uint4 resv[BN / 8];
+            uint4 resv[BN / 16];
             if (valid && prm.res_mode != kResNone) {
-                const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * ldr);
+                const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * ldr + c0);
 #pragma unroll
-                for (int j = 0; j < BN / 8; ++j) resv[j] = __ldg(rp + j);
+                for (int j = 0; j < BN / 16; ++j) resv[j] = __ldg(rp + j);
             }
             mbar_wait(&tfull_bar[buf], (i >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
-            uint32_t raw0[16], raw1[16], raw2[16], raw3[16];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN + c0;
+            uint32_t raw0[16], raw1[16];
             tmem_ld_32x32b_x16(taddr, raw0);
             tmem_ld_32x32b_x16(taddr + 16, raw1);
-            tmem_ld_32x32b_x16(taddr + 32, raw2);
-            tmem_ld_32x32b_x16(taddr + 48, raw3);
             tmem_ld_wait_x16(raw0);
             tmem_ld_wait_x16(raw1);
-            tmem_ld_wait_x16(raw2);
-            tmem_ld_wait_x16(raw3);
             // the accumulator is in registers: hand it back to the MMA warp before the arithmetic and the stores
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
             if (!valid) continue;
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const uint32_t(&raw)[16] = q4 == 0 ? raw0 : (q4 == 1 ? raw1 : (q4 == 2 ? raw2 : raw3));
-                const int cc = q4 * 16;
+            for (int q4 = 0; q4 < 2; ++q4) {
+                const uint32_t(&raw)[16] = q4 == 0 ? raw0 : raw1;
+                const int cc = c0 + q4 * 16;
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + s_bias[cc + j];
@@ -737,7 +750,7 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 if (prm.res_mode != kResNone) {
-                    const uint4 r0 = resv[cc / 8], r1 = resv[cc / 8 + 1];
+                    const uint4 r0 = resv[q4 * 2], r1 = resv[q4 * 2 + 1];
                     const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
                     const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll

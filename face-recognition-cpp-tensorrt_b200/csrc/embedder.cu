@@ -138,10 +138,16 @@ void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
     if (BN == 64 && g_halo_level == 3 && prm.taps == 9 && !prm.tap_phase && s.splits == 1 && prm.cin_blocks == 1 && prm.cout == 64 &&
         !prm.partial) {
         // experimental: persistent weight-stationary 64 -> 64 conv (conv3x3_ws_kernel): weights loaded once per CTA, halo tiles streamed
+        // Measured on B200 with 2 halo buffers and 8 epilogue warps (parity green): 1.45 vs 1.56 ms at batch 32, but 8.06 vs 7.29 ms at
+        // batch 256 - with one 32-48 KiB halo load in flight per SM the steady state is bound by that load's latency. FR_WS_BUFS=3/4
+        // keeps more halo tiles in flight (not yet run on hardware).
+        static const int ws_bufs = std::getenv("FR_WS_BUFS") ? std::atoi(std::getenv("FR_WS_BUFS")) : 2;
         prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
-        const int smem = 1024 + 2 * prm.halo_chunks * kConvBM * 128 + kWsWeightBytes + 256 + 4 * kWsBN * 4;
+        const int halo_bytes = prm.halo_chunks * kConvBM * 128;
+        prm.halo_bufs = std::max(2, std::min({4, ws_bufs, (227 * 1024 - 1024 - kWsWeightBytes - 256 - 4 * kWsBN * 4) / halo_bytes}));
+        const int smem = 1024 + prm.halo_bufs * halo_bytes + kWsWeightBytes + 256 + 4 * kWsBN * 4;
         const int ctas = std::min<int>(static_cast<int>(grid.x), g_conv_sms);
-        conv3x3_ws_kernel<<<ctas, kConvThreads, smem, st>>>(s.ta, s.tb, prm);
+        conv3x3_ws_kernel<<<ctas, kWsThreads, smem, st>>>(s.ta, s.tb, prm);
     } else if (prm.taps == 9 && !prm.tap_phase && s.splits == 1 && (g_halo_level >= 2 || (g_halo_level == 1 && prm.cin_blocks == 1))) {
         // 3x3 stride-1 conv: one halo tile per 64-channel block feeds all nine taps (conv3x3_halo_kernel)
         prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
@@ -494,7 +500,7 @@ int fr_embedder_create(const char* weights_path, int max_batch, int device, FrEm
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
             g_conv_sms = e->sms;
-            FRB_CUDA(cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             FRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             FRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             build_plan(e.get(), wf);
