@@ -121,7 +121,7 @@ DevBuf make_buf(FrEmbedder* e, size_t rows, int C) {
 
 // conv3x3_halo_kernel (one halo tile per channel block instead of nine per-tap loads) policy, FR_HALO: 0 = never, 1 (default) = only the
 // 64-input-channel layers (one channel block: the layers that are most L2-bound per tap, and the halo tile + weight ring still let two
-// CTAs share an SM), 2 = every stride-1 3x3 conv, 3 = experimental persistent weight-stationary kernel on the 64 -> 64 layers (others as 0), 4 = that kernel on small grids only (others as 1). Measured on B200 (IR-SE-50) for FR_HALO=2: 1.55 vs 1.64 ms at batch 32 but 8.65 vs
+// CTAs share an SM), 2 = every stride-1 3x3 conv, 3 = experimental persistent weight-stationary kernel on the 64 -> 64 layers (others as 1), 4 = that kernel on small grids only (others as 1). Measured on B200 (IR-SE-50) for FR_HALO=2: 1.55 vs 1.64 ms at batch 32 but 8.65 vs
 // 7.54 ms at batch 256 (with two halo buffers only one CTA fits per SM on the 128..512-channel layers); FR_HALO=1: 1.576 vs 1.601 ms
 // at batch 32 and 7.43 vs 7.52 ms at batch 256 (gpurun_out/halo_policy.txt, two interleaved runs each).
 // The tap operands start at 128-byte-row offsets inside the 1024-byte swizzle atom; the hardware swizzles on absolute shared-memory
@@ -140,9 +140,10 @@ void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
     const bool ws_ok = BN == 64 && prm.taps == 9 && !prm.tap_phase && s.splits == 1 && prm.cin_blocks == 1 && prm.cout == 64 && !prm.partial;
     if (ws_ok && (g_halo_level == 3 || (g_halo_level == 4 && static_cast<int>(grid.x) <= 24 * g_conv_sms))) {
         // experimental: persistent weight-stationary 64 -> 64 conv (conv3x3_ws_kernel): weights loaded once per CTA, halo tiles streamed
-        // Measured on B200 with 2 halo buffers and 8 epilogue warps (parity green): 1.45 vs 1.56 ms at batch 32, but 8.06 vs 7.29 ms at
-        // batch 256 - with one 32-48 KiB halo load in flight per SM the steady state is bound by that load's latency. FR_WS_BUFS=3/4
-        // keeps more halo tiles in flight (not yet run on hardware).
+        // Measured on B200 with 2 halo buffers and 8 epilogue warps (parity green), in a build where every OTHER stride-1 3x3 layer ran
+        // conv3x3_halo_kernel (the FR_HALO=2 behaviour: 8.65 ms at batch 256): 1.45 vs 1.56 ms (FR_HALO=1) at batch 32, 8.06 vs 7.29 ms
+        // at batch 256 - i.e. about -0.6 ms against FR_HALO=2, not yet isolated against FR_HALO=1. With one 32-48 KiB halo load in
+        // flight per SM the steady state is bound by that load's latency; FR_WS_BUFS=3/4 keeps more in flight (not yet run).
         static const int ws_bufs = std::getenv("FR_WS_BUFS") ? std::atoi(std::getenv("FR_WS_BUFS")) : 2;
         prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
         const int halo_bytes = prm.halo_chunks * kConvBM * 128;
@@ -151,7 +152,7 @@ void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
         const int ctas = std::min<int>(static_cast<int>(grid.x), g_conv_sms);
         conv3x3_ws_kernel<<<ctas, kWsThreads, smem, st>>>(s.ta, s.tb, prm);
     } else if (prm.taps == 9 && !prm.tap_phase && s.splits == 1 &&
-               (g_halo_level == 2 || ((g_halo_level == 1 || g_halo_level == 4) && prm.cin_blocks == 1))) {
+               (g_halo_level == 2 || (g_halo_level != 0 && prm.cin_blocks == 1))) {
         // 3x3 stride-1 conv: one halo tile per 64-channel block feeds all nine taps (conv3x3_halo_kernel)
         prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
         prm.halo_bufs = prm.cin_blocks > 1 ? 2 : 1;
