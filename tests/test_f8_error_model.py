@@ -51,3 +51,24 @@ def test_error_model_and_bound(dist):
     worst = max(float((err / bound).abs().max()), float((e2 / b2).abs().max()))
     assert worst < 0.7 * K_Z, worst
     assert K_Z >= 6.0 and np.isclose(K_SCALE, 256.0)
+
+
+def test_true_best_survives_the_margin_for_unmatched_queries():
+    # the statement the e4m3 scan relies on, emulated on the CPU for the hard case (queries with NO match, so hundreds of rows sit
+    # within the margin of the best impostor): the exact fp32 top-1 is always among the rows whose coarse (e4m3) score is within
+    # margin = kF8Z * sqrt(2) * kF8Delta * |q|_4 * max_rows |g|_4 of the best coarse score, and the set re-scored stays small
+    torch.manual_seed(5)
+    n, nq = 300_000, 256
+    g, q = unit(torch.randn(n, 512)), unit(torch.randn(nq, 512))
+    exact = q @ g.T
+    coarse = f8(q) @ f8(g).T
+    g4max = float(((g ** 4).sum(1)).max())
+    margin = K_Z * 2 ** 0.5 * K_DELTA * ((q ** 4).sum(1) * g4max) ** 0.25            # per query, cosine units
+    best_exact = exact.argmax(1)
+    cbest = coarse.max(1).values
+    survives = coarse[torch.arange(nq), best_exact] >= cbest - margin
+    assert bool(survives.all())
+    slack = (coarse[torch.arange(nq), best_exact] - (cbest - margin)) / margin      # 1 = at the coarse best, 0 = at the edge
+    assert float(slack.min()) > 0.5, float(slack.min())                             # never closer than half the margin to being dropped
+    in_margin = (coarse >= (cbest - margin)[:, None]).sum(1)
+    assert int(in_margin.max()) <= 1024 and float(in_margin.float().mean()) < 200   # kAppRescoreMax bounds the re-score
