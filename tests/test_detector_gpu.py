@@ -127,6 +127,38 @@ def test_postprocess_hook_adversarial_cases(ckpt):
     det.close()
 
 
+@pytest.mark.parametrize("geom", [(640, 640, 640, 640), (288, 320, 480, 640), (320, 288, 640, 480), (640, 640, 720, 1280)])
+def test_decode_nms_kernel_matches_compiled_reference(ckpt, geom):
+    """det_decode_nms_kernel vs the reference's OWN RetinaFace::postprocessing / create_anchor_retinaface / nms
+    (/root/reference/src/retinaface.cpp:154-271 compiled verbatim into oracle/_ref/libref_retina.so): Bbox integers and scores
+    bit-exact on random heads, both letterbox branches, clipping."""
+    from oracle import ref_retina as rr
+
+    if not rr.available():
+        pytest.skip("oracle/_ref/libref_retina.so not built")
+    full, sd, f = ckpt
+    nh, nw, fh, fw = geom
+    for max_faces, nms_thr, bbox_thr, seed in ((4, 0.4, 0.6, 0), (32, 0.3, 0.7, 1)):
+        det = frb200.Detector(f, (nh, nw), frame_hw=(fh, fw), max_batch=3, max_faces=max_faces, nms_thr=nms_thr, bbox_thr=bbox_thr, landmarks=full)
+        ref = rr.RefRetinaFace(nh, nw, fh, fw, max_faces=max_faces, nms_thr=nms_thr, bbox_thr=bbox_thr)
+        assert det.anchors == ref.output_size_base
+        A = det.anchors
+        rng = np.random.default_rng(17 + seed)
+        loc = (rng.standard_normal((3, A, 4)) * (1.5 + seed)).astype(np.float32)
+        p = rng.random((3, A)).astype(np.float32)
+        p = np.where(rng.random((3, A)) < 0.02, 0.6 + 0.4 * p, 0.6 * p).astype(np.float32)
+        conf = np.stack([1 - p, p], axis=-1).astype(np.float32)
+        lm = rng.standard_normal((3, A, 10)).astype(np.float32) if full else None
+        boxes, counts, _ = det.post(loc, conf, lm)
+        for i in range(3):
+            want = ref.postprocess(loc[i], conf[i])
+            assert counts[i] == len(want) > 0
+            assert _boxes_list(boxes, counts, i) == [w[:4] for w in want], (geom, i)
+            assert np.array_equal(boxes["score"][i, : counts[i]].view(np.uint32), np.array([w[4] for w in want], np.float32).view(np.uint32))
+        ref.close()
+        det.close()
+
+
 def test_detector_errors(ckpt, tmp_path):
     full, sd, f = ckpt
     with pytest.raises(frb200.FrError) as e:
