@@ -19,7 +19,7 @@ int use_device(int device) {
     if (device < 0 || device >= count) throw ArgError{"device index out of range"};
     cudaDeviceProp prop{};
     FRB_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
+    if (prop.major != 10 || prop.minor != 0) {  // sm_100a cubins do not run on other 10.x parts
         throw FileError{FR_ENODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
                                           ", kernels are built for sm_100a only"};
     }
@@ -90,6 +90,6 @@ CUtensorMap make_tmap_nhwc_f16(const void* base, uint64_t n, uint64_t h, uint64_
 
 extern "C" {
 const char* fr_last_error(void) { return frb::t_last_error.c_str(); }
-int fr_abi_version(void) { return 1; }
+int fr_abi_version(void) { return 2; }
 uint64_t fr_launch_count(void) { return frb::g_launches.load(); }
 }

@@ -27,6 +27,8 @@ struct FrGallery {
     uint8_t* rows_f8 = nullptr;       // optional e4m3 scan copy (FR_SCAN_F8), 512 B / row
     float* gmax = nullptr;
     float* g4max = nullptr;           // largest sum of fourth powers of a row (set with the e4m3 copy): scales the fp8 margin
+    float* w4max = nullptr;           // largest sum of fourth powers of a row's e4m3 rounding steps (same)
+    uint64_t f8_seed = 0x5EEDF8B200ull;  // dither stream of the stochastic e4m3 rounding (FR_F8_SEED overrides)
     CUtensorMap tmap{};
     CUtensorMap tmap8{};
     int scan = FR_SCAN_F16;
@@ -34,7 +36,10 @@ struct FrGallery {
     // scratch, sized for one chunk of 256 queries
     float* q_dev = nullptr;          // 256 x 512
     void* q_img = nullptr;           // 256 x 512 fp16 (or e4m3): the scan's query operand, written by prep_queries_kernel per search
-    float* q_margin = nullptr;       // 256: 2 eps |q| gmax in accumulator units
+    float* q_margin = nullptr;       // 256: scan margin in accumulator units (fp16: 2 eps |q| gmax; e4m3: (1 + gap) E, search_kernels.cuh)
+    float* q_gap = nullptr;          // 256: certificate gap of the e4m3 scan in cosine units (+inf on the fp16 copy)
+    bool first_chunk = true;         // the first chunk of a topk call resets flagged_acc (inside its prep kernel: no extra launch)
+    int* flagged_acc = nullptr;      // device: flagged queries accumulated over the chunks of the last topk call
     CUtensorMap tmq16{}, tmq8{};     // two views of q_img
     float* cand_s = nullptr;         // [lists <= 296][256][16]
     int* cand_i = nullptr;
@@ -68,6 +73,10 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMalloc(&g->q_dev, sizeof(float) * kChunkQ * kDim));
     FRB_CUDA(cudaMalloc(&g->q_img, sizeof(__half) * kChunkQ * kDim));
     FRB_CUDA(cudaMalloc(&g->q_margin, sizeof(float) * kChunkQ));
+    FRB_CUDA(cudaMalloc(&g->q_gap, sizeof(float) * kChunkQ));
+    FRB_CUDA(cudaMalloc(&g->flagged_acc, sizeof(int)));
+    FRB_CUDA(cudaMemsetAsync(g->flagged_acc, 0, sizeof(int), g->stream));
+    if (const char* e = std::getenv("FR_F8_SEED")) g->f8_seed = std::strtoull(e, nullptr, 0);
     g->tmq16 = make_tmap_2d_f16(g->q_img, kChunkQ, kDim, 128, 64);
     g->tmq8 = make_tmap_2d_u8(g->q_img, kChunkQ, kDim, 128, 128);
     FRB_CUDA(cudaMalloc(&g->cand_s, sizeof(float) * kMaxLists * kChunkQ * 16));
@@ -85,6 +94,8 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
     FRB_CUDA(cudaMalloc(&g->g4max, sizeof(float)));
     FRB_CUDA(cudaMemsetAsync(g->g4max, 0, sizeof(float), g->stream));
+    FRB_CUDA(cudaMalloc(&g->w4max, sizeof(float)));
+    FRB_CUDA(cudaMemsetAsync(g->w4max, 0, sizeof(float), g->stream));
 }
 
 FrGallery* new_gallery(int64_t n, int dim, int device, int64_t row_offset) {
@@ -159,10 +170,10 @@ void grow_rows(FrGallery* g, int64_t capacity) {
     refresh_tmaps(g);
 }
 
-// FR_F8_Z overrides the fp8 margin's number of standard deviations (experiments); FR_SEARCH_APPEND: 0 = sorted register lists
-// everywhere, 1 = append epilogue for top-1 searches on the fp8 scan copy only, 2 (default) = for top-1 searches on either scan copy
-float f8_z() {
-    static const float v = std::getenv("FR_F8_Z") ? static_cast<float>(std::atof(std::getenv("FR_F8_Z"))) : kF8Z;
+// FR_F8_LOGP overrides ln(1/p) of the e4m3 certificate (p = per-query bound on a wrong top-1; experiments); FR_SEARCH_APPEND: 0 =
+// sorted register lists everywhere, 1 = append epilogue for top-1 searches on the fp8 scan copy only, 2 (default) = on either scan copy
+float f8_logp() {
+    static const float v = std::getenv("FR_F8_LOGP") ? static_cast<float>(std::atof(std::getenv("FR_F8_LOGP"))) : kF8LogP;
     return v;
 }
 int append_mode() {
@@ -172,7 +183,8 @@ int append_mode() {
 
 template <int CG, int KSEL, bool F8, bool APP = false>
 void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tiles, cudaStream_t st) {
-    prep_queries_kernel<F8><<<kChunkQ / 8, 256, 0, st>>>(q_dev, nq, g->gmax, g->g4max, F8 ? f8_z() : kCoarseEps, g->q_img, g->q_margin);
+    prep_queries_kernel<F8><<<kChunkQ / 8, 256, 0, st>>>(q_dev, nq, g->gmax, g->g4max, g->w4max, F8 ? f8_logp() : kCoarseEps, g->f8_seed, g->q_img,
+                                                         g->q_margin, g->q_gap, g->first_chunk ? g->flagged_acc : nullptr);
     count_launch();
     std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
     if (g->timing) {
@@ -235,7 +247,7 @@ void launch_exact(FrGallery* g, const float* q_dev, int nq, int k, const int* fl
     // flagged-query fix-up: one pass of blocks that loop over the (normally empty) list; exact path: spread the queries too
     const int qsplit = flags ? 1 : std::min(nq, 64);
     exact_scan_kernel<<<dim3(slices, qsplit), kScanThreads, 0, st>>>(g->rows_f32, g->n, q_dev, nq, flags, g->part_s, g->part_i, k, g->row_offset,
-                                                                     scores_dev, idx_dev, g->scan_ticket);
+                                                                     scores_dev, idx_dev, g->scan_ticket, flags ? g->flagged_acc : nullptr);
     count_launch();
     if (!flags) {  // all queries: the merge is spread over its own grid; the fix-up's last block merges in the same launch
         exact_merge_kernel<<<std::min(nq, 148), kSelThreads, 0, st>>>(g->part_s, g->part_i, slices, nq, flags, k, g->row_offset, scores_dev, idx_dev);
@@ -249,6 +261,7 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     const bool exact = g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows);
     g->stats = FrSearchStats{};
     if (exact) {
+        if (g->first_chunk) FRB_CUDA(cudaMemsetAsync(g->flagged_acc, 0, sizeof(int), st));  // nothing is ever flagged on this path
         launch_exact(g, q_dev, nq, k, nullptr, scores_dev, idx_dev, st);
         g->stats.scan_bytes = g->n * kDim * 4 * nq;
         g->stats.flops = 2LL * nq * g->n * kDim;
@@ -268,7 +281,7 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
         FRB_CUDA(cudaMalloc(&g->app_cnt, sizeof(int) * kMaxLists * kChunkQ));
     }
     if (cg == 2) {
-        units = std::min(g->sms / 2, tiles);
+        units = std::min({g->sms / 2, tiles, kMaxLists / 2});  // scratch and the re-rank kernels are sized for kMaxLists lists
         if (f8) {
             if (app) launch_coarse<2, 1, true, true>(g, q_dev, nq, units, tiles, st);
             else if (k == 1) launch_coarse<2, 1, true>(g, q_dev, nq, units, tiles, st);
@@ -279,7 +292,7 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
             else launch_coarse<2, 8, false>(g, q_dev, nq, units, tiles, st);
         }
     } else {
-        units = std::min(g->sms, tiles);
+        units = std::min({g->sms, tiles, kMaxLists / 2});
         if (f8) {
             if (app) launch_coarse<1, 1, true, true>(g, q_dev, nq, units, tiles, st);
             else if (k == 1) launch_coarse<1, 1, true>(g, q_dev, nq, units, tiles, st);
@@ -292,10 +305,12 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     }
     if (app)
         append_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->app_buf, g->app_cnt, units * 2, cg * kQRows, q_dev, g->rows_f32, g->q_margin,
-                                                         f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
+                                                         g->q_gap, f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, g->row_offset, scores_dev, idx_dev, g->flags,
+                                                         g->gbest);
     else
         topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->q_margin,
-                                                       f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, k, g->row_offset, scores_dev, idx_dev, g->flags, g->gbest);
+                                                       g->q_gap, f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, k, g->row_offset, scores_dev, idx_dev, g->flags,
+                                                       g->gbest);
     count_launch();
     FRB_CUDA(cudaGetLastError());
     // queries whose candidate set may be incomplete (flagged by the re-rank) are recomputed exactly; no-op otherwise
@@ -390,6 +405,9 @@ void fr_gallery_destroy(FrGallery* g) {
     cudaFree(g->rows_f8);
     cudaFree(g->gmax);
     cudaFree(g->g4max);
+    cudaFree(g->w4max);
+    cudaFree(g->q_gap);
+    cudaFree(g->flagged_acc);
     cudaFree(g->q_dev);
     cudaFree(g->q_img);
     cudaFree(g->q_margin);
@@ -438,7 +456,7 @@ int fr_gallery_set_scan(FrGallery* g, int scan) {
             FRB_CUDA(cudaMalloc(&g->rows_f8, static_cast<size_t>(g->capacity) * kDim));
             if (g->n > 0) {
                 const int blocks = static_cast<int>(std::min<int64_t>((g->n + 7) / 8, g->sms * 16LL));
-                make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f8, g->n, g->g4max);
+                make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, g->rows_f8, g->n, g->f8_seed, g->row_offset, g->g4max, g->w4max);
                 count_launch();
                 FRB_CUDA(cudaGetLastError());
                 FRB_CUDA(cudaStreamSynchronize(g->stream));
@@ -483,7 +501,7 @@ int fr_gallery_append(FrGallery* g, const float* rows, int64_t n) {
         make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f16 + g->n * kDim, n, g->gmax);
         count_launch();
         if (g->rows_f8) {
-            make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f8 + g->n * kDim, n, g->g4max);
+            make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f8 + g->n * kDim, n, g->f8_seed, g->row_offset + g->n, g->g4max, g->w4max);
             count_launch();
         }
         FRB_CUDA(cudaGetLastError());
@@ -521,6 +539,7 @@ int fr_gallery_clear(FrGallery* g) {
         g->n = 0;
         FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
         FRB_CUDA(cudaMemsetAsync(g->g4max, 0, sizeof(float), g->stream));
+        FRB_CUDA(cudaMemsetAsync(g->w4max, 0, sizeof(float), g->stream));
         FRB_CUDA(cudaStreamSynchronize(g->stream));
     });
 }
@@ -576,6 +595,7 @@ int fr_gallery_topk_dev(FrGallery* g, const float* q_dev, int nq, int k, float* 
         FrSearchStats total{};
         for (int q0 = 0; q0 < nq; q0 += kChunkQ) {
             const int m = std::min(kChunkQ, nq - q0);
+            g->first_chunk = q0 == 0;
             topk_chunk(g, q_dev + static_cast<size_t>(q0) * kDim, m, k, scores_dev + static_cast<size_t>(q0) * k,
                        reinterpret_cast<long long*>(idx_dev) + static_cast<size_t>(q0) * k, st);
             add_stats(total, g->stats);
@@ -594,6 +614,7 @@ int fr_gallery_topk(FrGallery* g, const float* q, int nq, int k, float* scores, 
         for (int q0 = 0; q0 < nq; q0 += kChunkQ) {
             const int m = std::min(kChunkQ, nq - q0);
             FRB_CUDA(cudaMemcpyAsync(g->q_dev, q + static_cast<size_t>(q0) * kDim, sizeof(float) * m * kDim, cudaMemcpyHostToDevice, g->stream));
+            g->first_chunk = q0 == 0;
             topk_chunk(g, g->q_dev, m, k, g->res_s, g->res_i, g->stream);
             FRB_CUDA(cudaMemcpyAsync(scores + static_cast<size_t>(q0) * k, g->res_s, sizeof(float) * m * k, cudaMemcpyDeviceToHost, g->stream));
             FRB_CUDA(cudaMemcpyAsync(idx + static_cast<size_t>(q0) * k, g->res_i, sizeof(long long) * m * k, cudaMemcpyDeviceToHost, g->stream));
@@ -647,7 +668,37 @@ int fr_gallery_last_flagged(FrGallery* g, int* out) {
         if (!g || !out) throw ArgError{"null argument"};
         DeviceGuard dg(g->device);
         FRB_CUDA(cudaStreamSynchronize(g->stream));
-        FRB_CUDA(cudaMemcpy(out, g->flags, sizeof(int), cudaMemcpyDeviceToHost));
+        FRB_CUDA(cudaMemcpy(out, g->flagged_acc, sizeof(int), cudaMemcpyDeviceToHost));  // summed over the call's 256-query chunks
+    });
+}
+
+int fr_gallery_debug_read(FrGallery* g, int what, int64_t first, int64_t count, void* out) {
+    return guarded([&] {
+        if (!g || !out) throw ArgError{"null argument"};
+        DeviceGuard dg(g->device);
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+        switch (what) {
+        case 0:
+            if (!g->rows_f8) throw StateError{"no e4m3 scan copy (fr_gallery_set_scan(FR_SCAN_F8) first)"};
+            if (first < 0 || count < 0 || first + count > g->n) throw ArgError{"row range out of bounds"};
+            FRB_CUDA(cudaMemcpy(out, g->rows_f8 + first * kDim, static_cast<size_t>(count) * kDim, cudaMemcpyDeviceToHost));
+            break;
+        case 1:
+            FRB_CUDA(cudaMemcpy(out, g->q_img, static_cast<size_t>(kChunkQ) * kDim * (g->scan == FR_SCAN_F8 ? 1 : 2), cudaMemcpyDeviceToHost));
+            break;
+        case 2: FRB_CUDA(cudaMemcpy(out, g->q_margin, sizeof(float) * kChunkQ, cudaMemcpyDeviceToHost)); break;
+        case 3: FRB_CUDA(cudaMemcpy(out, g->q_gap, sizeof(float) * kChunkQ, cudaMemcpyDeviceToHost)); break;
+        case 4: {
+            float* o = static_cast<float*>(out);
+            FRB_CUDA(cudaMemcpy(o, g->gmax, sizeof(float), cudaMemcpyDeviceToHost));
+            FRB_CUDA(cudaMemcpy(o + 1, g->g4max, sizeof(float), cudaMemcpyDeviceToHost));
+            FRB_CUDA(cudaMemcpy(o + 2, g->w4max, sizeof(float), cudaMemcpyDeviceToHost));
+            break;
+        }
+        case 5: FRB_CUDA(cudaMemcpy(out, g->cand_s, sizeof(float) * kMaxLists * kChunkQ * 16, cudaMemcpyDeviceToHost)); break;
+        case 6: FRB_CUDA(cudaMemcpy(out, g->cand_i, sizeof(int) * kMaxLists * kChunkQ * 16, cudaMemcpyDeviceToHost)); break;
+        default: throw ArgError{"unknown debug read"};
+        }
     });
 }
 

@@ -42,21 +42,62 @@ constexpr int kLdCols = 16;                          // accumulator columns per 
 constexpr float kCoarseEps = 1.25e-3f;
 
 // fp8 (e4m3) scan copy: rows and queries are multiplied by kF8Scale before the conversion (unit-norm components ~0.044 land in
-// e4m3's normal range), accumulators are kF8Scale^2 x the cosine. The worst-case rounding bound (2^-4 per operand through
-// Cauchy-Schwarz) is useless, so the margin is statistical: the error of one coarse score is a sum of 512 independent rounding errors
-// with standard deviation  kF8Delta * sqrt(sum q_i^2 g_i^2)  <=  kF8Delta * |q|_4 * |g|_4  (Cauchy-Schwarz on the squares; equality for a
-// matched pair), kF8Delta = 0.0373 = the rms relative error of an e4m3 x e4m3 product (tools/f8_error_model.py: 1.65e-3 measured for
-// unrelated unit vectors, 2.5e-3 for matched pairs, bound 2.85e-3). "The true best's coarse score >= the best coarse score - margin"
-// involves two such errors, so  margin = kF8Z * sqrt(2) * kF8Delta * |q|_4 * max_rows |g|_4 : kF8Z = 6.5 standard deviations of the
-// BOUND (8.7 of the measured sum for Gaussian-like embeddings), ~2.6e-2 for isotropic unit vectors, wider for heavy-tailed ones.
+// e4m3's normal range), accumulators are kF8Scale^2 x the cosine. Round-to-nearest e4m3 has no useful error bound (2^-4 per operand
+// through Cauchy-Schwarz, and structured rows make the "independent errors" reading false), so both operands are rounded
+// STOCHASTICALLY (f8_round_dither: to one of the two neighbouring e4m3 values, up with probability = the fractional position,
+// uniform variates from a counter-based hash of (seed, row, column)). Then, for ANY fixed query q and row g,
+//     coarse - exact = sum_i qhat_i r_i(g) + sum_i g_i r_i(q)     (r = rounding error, independent, zero-mean, |range| = the e4m3 step u_i)
+// and Hoeffding's inequality gives  P(exact - coarse >= t) <= exp(-2 t^2 / V),
+//     V = sum qbar_i^2 u_i(g)^2 + sum g_i^2 u_i(q)^2  <=  |qbar|_4^2 W^2 + G4^2 |u(q)|_4^2
+// (qbar = outward-rounded |q|; W = max_rows |u(g)|_4 and G4 = max_rows |g|_4 are recorded when the copy is built, w4max / g4max).
+// The search is CERTIFIED per query (append_rerank_kernel / topk_rerank_kernel): with E = sqrt(V ln(1/p) / 2) + eps_det, rows are
+// pruned only below  (best coarse) - m,  m = (1 + kF8GapFrac) E, and the result is accepted only if the best EXACT score L among the
+// re-scored rows satisfies  L >= (best coarse) - m + E. If the true best row A had been pruned, then coarse_A < best coarse - m
+// <= L - E <= exact_A - E: a single fixed row's error exceeded E, which has probability <= p = exp(-kF8LogP) (no union over the
+// gallery). Queries that fail the certificate are recomputed by the exact fp32 scan. eps_det covers the deterministic parts: the
+// tensor core's fp32 accumulation of the exact e4m3 products and the fp32 rounding of the exact re-score (kF8AccEps |qbar| |g|).
 constexpr float kF8Scale = 256.f;
-constexpr float kF8Delta = 0.0373f;
-constexpr float kF8Z = 6.5f;
+constexpr float kF8LogP = 27.631f;     // ln(1e12): per-query bound on the probability of a wrong top-1, for arbitrary rows / queries
+constexpr float kF8GapFrac = 0.3f;     // room between the best coarse score and the best exact score before a query is recomputed
+constexpr float kF8AccEps = 1.1e-3f;   // >= 2^-10 + gamma_512: accumulation in the MMA pipe and in dot512, relative to |qbar| |ghat|
+constexpr float kF8Max = 448.f;        // largest e4m3 magnitude
+
+// e4m3 neighbours of a scaled magnitude a in [0, 448]: lo = largest e4m3 value <= a, step = distance to the next one
+// (2^(e-3) for a in [2^e, 2^(e+1)), e >= -6; 2^-9 in the subnormal range). Exact in fp32: power-of-two scalings and a floor.
+__host__ __device__ __forceinline__ void f8_bracket(float a, float& lo, float& step) {
+    union { float f; uint32_t u; } v;
+    v.f = a;
+    int e = static_cast<int>((v.u >> 23) & 0xFF) - 127;
+    e = e < -6 ? -6 : e;
+    v.u = static_cast<uint32_t>(e - 3 + 127) << 23;
+    step = v.f;
+#ifdef __CUDA_ARCH__
+    lo = floorf(a / step) * step;
+#else
+    lo = static_cast<float>(static_cast<int>(a / step)) * step;
+#endif
+}
+// Stochastic rounding of x * kF8Scale to e4m3 with the 24-bit uniform variate r24. Returns the rounded SCALED value (exactly
+// representable); u = the step of the bracket (0 when the value is representable: no randomness), abar = outward-rounded magnitude.
+__host__ __device__ __forceinline__ float f8_round_dither(float x, uint32_t r24, float& u, float& abar) {
+    float a = x < 0.f ? -x : x;
+    a *= kF8Scale;
+    a = a > kF8Max ? kF8Max : a;  // saturation is reported by the callers (rows are refused, queries go to the exact scan)
+    float lo, step;
+    f8_bracket(a, lo, step);
+    const float frac = (a - lo) / step;  // exact, in [0, 1)
+    const bool inexact = frac > 0.f;
+    const bool up = static_cast<float>(r24) < frac * 16777216.f;
+    u = inexact ? step : 0.f;
+    abar = inexact ? lo + step : lo;
+    const float r = up ? lo + step : lo;
+    return x < 0.f ? -r : r;
+}
 // "append" epilogue (top-1 searches on the fp8 scan copy): instead of a sorted register list every epilogue thread appends the
 // rows that pass its running threshold to a private buffer in global memory; the wide fp8 margin makes passes frequent (a few per
 // thousand rows), and an append is a predicated 8-byte store where a sorted insert is a divergent 8-deep compare-swap chain.
 constexpr int kAppCap = 128;          // entries per (unit, column half, query); more than that hands the query to the exact scan
-constexpr int kAppRescoreMax = 1024;  // rows re-scored exactly per query in append mode
+constexpr int kAppRescoreMax = 4096;  // rows re-scored exactly per query in append mode (unmatched queries on a 10 M-row shard: ~600)
 template <int CG, bool F8 = false>
 struct CoarseCfg {
     static constexpr int kKB = F8 ? 4 : 8;                         // k-blocks of 128 bytes per row
@@ -538,9 +579,9 @@ constexpr int kRescoreMax = 64;               // rows re-scored exactly per quer
 __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* __restrict__ cand_s, const int* __restrict__ cand_i,
                                                                   int lists, int q_stride, int kc, const float* __restrict__ q,
                                                                   const float* __restrict__ rows, const float* __restrict__ q_margin,
-                                                                  float inv_raw, int k, long long row_offset, float* __restrict__ out_s,
-                                                                  long long* __restrict__ out_i, int* __restrict__ flag_list,
-                                                                  int* __restrict__ gbest) {
+                                                                  const float* __restrict__ q_gap, float inv_raw, int k, long long row_offset,
+                                                                  float* __restrict__ out_s, long long* __restrict__ out_i,
+                                                                  int* __restrict__ flag_list, int* __restrict__ gbest) {
     __shared__ float cs[kHeadMax];
     __shared__ long long ci[kHeadMax];
     __shared__ float sel_s[kTopkMax];
@@ -603,6 +644,9 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
         out_s[static_cast<size_t>(qi) * k + threadIdx.x] = sel_s[threadIdx.x];
         out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
     }
+    // certificate of the e4m3 scan (see kF8LogP): the k-th best EXACT score must not fall more than the gap below the k-th best
+    // coarse score, else a pruned row could belong to the top-k with probability > p. (+inf gap on the fp16 copy: always passes.)
+    if (threadIdx.x == 0 && sel_s[k - 1] < ck - __ldg(q_gap + qi)) overflow = 1;
     if (threadIdx.x == 0 && overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
     if (threadIdx.x == 0) gbest[qi] = 0;  // ready for the next search (0 = nothing published)
 }
@@ -615,9 +659,9 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
 __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2* __restrict__ app_buf, const int* __restrict__ app_cnt,
                                                                     int lists, int q_stride, const float* __restrict__ q,
                                                                     const float* __restrict__ rows, const float* __restrict__ q_margin,
-                                                                    float inv_raw, long long row_offset, float* __restrict__ out_s,
-                                                                    long long* __restrict__ out_i, int* __restrict__ flag_list,
-                                                                    int* __restrict__ gbest) {
+                                                                    const float* __restrict__ q_gap, float inv_raw, long long row_offset,
+                                                                    float* __restrict__ out_s, long long* __restrict__ out_i,
+                                                                    int* __restrict__ flag_list, int* __restrict__ gbest) {
     constexpr int kListsMax = 2 * 148;
     __shared__ float rs[kAppRescoreMax];
     __shared__ int ri[kAppRescoreMax];
@@ -742,6 +786,9 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
         }
         out_s[qi] = bi >= 0 ? bs : -INFINITY;
         out_i[qi] = bi >= 0 ? bi + row_offset : -1;
+        // certificate of the e4m3 scan (see kF8LogP): accept only if the best exact score is within the gap of the best coarse score;
+        // then a pruned true best would need a rounding error beyond E. (+inf gap on the fp16 copy: always passes.)
+        if (bi >= 0 && bs < ck - __ldg(q_gap + qi)) overflow = 1;
         if (overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
         gbest[qi] = 0;  // ready for the next search
     }
@@ -757,9 +804,11 @@ constexpr int kScanSlicesMax = 148 * 2;
 __global__ void __launch_bounds__(kScanThreads) exact_scan_kernel(const float* __restrict__ rows, long long n, const float* __restrict__ q,
                                                                   int nq, const int* __restrict__ flag_list, float* part_s, long long* part_i,
                                                                   int k, long long row_offset, float* __restrict__ out_s,
-                                                                  long long* __restrict__ out_i, unsigned int* __restrict__ ticket) {
+                                                                  long long* __restrict__ out_i, unsigned int* __restrict__ ticket,
+                                                                  int* __restrict__ flagged_acc) {
     const int total = flag_list ? flag_list[0] : nq;
     if (total == 0) return;
+    if (flagged_acc && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(flagged_acc, total);
     for (int f = blockIdx.y; f < total; f += gridDim.y) {
     const int qi = flag_list ? flag_list[1 + f] : f;
     __shared__ float cs[8 * kTopkMax];
@@ -962,15 +1011,70 @@ __global__ void __launch_bounds__(256) synth_rows_kernel(float* __restrict__ row
     }
 }
 
-// Query operand of the fused scan: 256 rows (nq real ones, then zeros) x 512 as fp16, or e4m3 scaled by kF8Scale, row-major, plus the
-// per-query margin 2 eps |q| gmax in accumulator units. One warp per row; runs once per search, so that the scan's CTAs fetch their
-// operand with TMA instead of each converting the fp32 queries themselves.
+// Query operand of the fused scan: 256 rows (nq real ones, then zeros) x 512 as fp16, or e4m3 scaled by kF8Scale (stochastically
+// rounded, see kF8LogP), row-major, plus per query the scan margin (accumulator units) and the certificate gap (cosine units; +inf on
+// the fp16 copy, whose margin 2 eps |q| gmax is a deterministic bound and needs no certificate). One warp per row; runs once per search,
+// so that the scan's CTAs fetch their operand with TMA instead of each converting the fp32 queries themselves.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// uniform 24-bit variates for the dither: pair p of row key `key` -> (r24 for the even element, r24 for the odd element)
+__host__ __device__ __forceinline__ uint64_t dither_key(uint64_t seed, uint64_t row) {
+    uint64_t z = seed ^ (row * 0xD6E8FEB86659FD93ull);
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t dither_bits(uint64_t key, uint32_t pair) {
+    uint64_t z = key + pair;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+constexpr uint64_t kQueryDitherSalt = 0x51ED270B7F4A7C15ull;  // queries and rows draw from different streams of the same seed
+
+// stochastic e4m3 image of 16 elements of a 512-vector held as 4 float4 (element (lane + 32 i) * 4 + e), written to dst8 (row base);
+// accumulates sum u^4, sum abar^4, sum abar^2 (scaled units) and whether anything saturated
+__device__ __forceinline__ void f8_dither_row(const float4 (&a)[4], int lane, uint64_t key, uint8_t* __restrict__ dst8, float& u4,
+                                              float& a4, float& a2, bool& sat) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t pair0 = static_cast<uint32_t>(lane + 32 * i) * 2u;
+        const uint64_t h0 = dither_bits(key, pair0), h1 = dither_bits(key, pair0 + 1u);
+        const float x[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+        const uint32_t r[4] = {static_cast<uint32_t>(h0) & 0xFFFFFFu, static_cast<uint32_t>(h0 >> 32) & 0xFFFFFFu,
+                               static_cast<uint32_t>(h1) & 0xFFFFFFu, static_cast<uint32_t>(h1 >> 32) & 0xFFFFFFu};
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float u, abar;
+            v[e] = f8_round_dither(x[e], r[e], u, abar);
+            sat |= fabsf(x[e]) * kF8Scale > kF8Max;
+            const float uu = u * u, aa = abar * abar;
+            u4 = fmaf(uu, uu, u4);
+            a4 = fmaf(aa, aa, a4);
+            a2 += aa;
+        }
+        // the values are exactly representable: the conversion below cannot round
+        const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(v[0], v[1]), __NV_SATFINITE, __NV_E4M3);
+        const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(v[2], v[3]), __NV_SATFINITE, __NV_E4M3);
+        reinterpret_cast<uint32_t*>(dst8)[lane + 32 * i] = lo | (hi << 16);
+    }
+}
+
 template <bool F8>
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restrict__ q, int nq, const float* __restrict__ gmax_ptr,
-                                                           const float* __restrict__ g4max_ptr, float scale, void* __restrict__ q_img,
-                                                           float* __restrict__ q_margin) {
+                                                           const float* __restrict__ g4max_ptr, const float* __restrict__ w4max_ptr,
+                                                           float scale, unsigned long long seed, void* __restrict__ q_img,
+                                                           float* __restrict__ q_margin, float* __restrict__ q_gap,
+                                                           int* __restrict__ flagged_acc_reset) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (flagged_acc_reset && blockIdx.x == 0 && threadIdx.x == 0) *flagged_acc_reset = 0;  // first chunk of a call
     if (r >= 2 * kQRows) return;
     float4 a[4];
     if (r < nq) load512(q + static_cast<size_t>(r) * kDim, lane, a);
@@ -978,24 +1082,34 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float m;
-    if (F8) {  // scale = kF8Z (or its override): margin = scale * sqrt(2) * kF8Delta * (sum q^4 * max_rows sum g^4)^(1/4), in accumulator units
-        float4 a2[4];
+    if (F8) {
+        // scale = ln(1/p) (kF8LogP or its override). All norms below in cosine units (scaled sums / kF8Scale^n).
+        float u4 = 0.f, a4 = 0.f, a2 = 0.f;
+        bool sat = false;
+        f8_dither_row(a, lane, dither_key(seed ^ kQueryDitherSalt, static_cast<uint64_t>(r)), static_cast<uint8_t*>(q_img) + static_cast<size_t>(r) * kDim,
+                      u4, a4, a2, sat);
+        u4 = warp_sum(u4);
+        a4 = warp_sum(a4);
+        a2 = warp_sum(a2);
+        sat = __any_sync(0xffffffffu, sat);
+        constexpr float kS2 = 1.f / (kF8Scale * kF8Scale), kS4 = kS2 * kS2;
+        const float qbar4 = a4 * kS4, uq4 = u4 * kS4, qbar2 = a2 * kS2;
+        // V <= |qbar|_4^2 W^2 + G4^2 |u(q)|_4^2 ; E = sqrt(V ln(1/p) / 2) + eps_det, rounded up
+        const float V = sqrtf(qbar4 * __ldg(w4max_ptr)) + sqrtf(__ldg(g4max_ptr) * uq4);
+        const float E = (sqrtf(0.5f * scale * V) + kF8AccEps * sqrtf(qbar2) * 1.125f * __ldg(gmax_ptr)) * 1.001f + 1e-7f;
+        if (lane == 0) {
+            q_margin[r] = r < nq ? (1.f + kF8GapFrac) * E * (kF8Scale * kF8Scale) : 0.f;
+            // a saturated query component breaks the error model: the certificate can never pass and the exact scan answers
+            q_gap[r] = sat ? -INFINITY : kF8GapFrac * E;
+        }
+    } else {  // scale = kCoarseEps: provable margin 2 eps |q| gmax
+        const float m = 2.f * scale * sqrtf(dot512(a, a)) * __ldg(gmax_ptr);
+        if (lane == 0) {
+            q_margin[r] = r < nq ? m : 0.f;
+            q_gap[r] = INFINITY;
+        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a2[i] = make_float4(a[i].x * a[i].x, a[i].y * a[i].y, a[i].z * a[i].z, a[i].w * a[i].w);
-        const float q4 = dot512(a2, a2);
-        m = scale * 1.41421356f * kF8Delta * sqrtf(sqrtf(q4 * __ldg(g4max_ptr))) * (kF8Scale * kF8Scale);
-    } else {   // scale = kCoarseEps: provable margin 2 eps |q| gmax
-        m = 2.f * scale * sqrtf(dot512(a, a)) * __ldg(gmax_ptr);
-    }
-    if (lane == 0) q_margin[r] = r < nq ? m : 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (F8) {
-            const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a[i].x * kF8Scale, a[i].y * kF8Scale), __NV_SATFINITE, __NV_E4M3);
-            const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a[i].z * kF8Scale, a[i].w * kF8Scale), __NV_SATFINITE, __NV_E4M3);
-            reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(q_img) + static_cast<size_t>(r) * kDim)[lane + 32 * i] = lo | (hi << 16);
-        } else {
+        for (int i = 0; i < 4; ++i) {
             __half2 lo = __floats2half2_rn(a[i].x, a[i].y), hi = __floats2half2_rn(a[i].z, a[i].w);
             uint2 o;
             o.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -1005,28 +1119,30 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
     }
 }
 
-// e4m3 scan copy (rows x kF8Scale). One warp per row.
-// Also the largest sum of fourth powers of a row (g4max, as the bits of a non-negative float): the fp8 margin scales with it.
+// e4m3 scan copy (rows x kF8Scale, stochastically rounded with the dither stream of (seed, global row id)). One warp per row.
+// Also the bounds the certificate scales with, as the bits of non-negative floats (running maxima): g4max = largest sum of fourth
+// powers of a row, w4max = largest sum of fourth powers of a row's e4m3 steps (both in cosine units).
 __global__ void __launch_bounds__(256) make_f8_copy_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, long long n,
-                                                           float* __restrict__ g4max) {
+                                                           unsigned long long seed, long long first_row_id, float* __restrict__ g4max,
+                                                           float* __restrict__ w4max) {
     const int lane = threadIdx.x & 31;
     const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-    float w4 = 0.f;
+    float g4 = 0.f, w4 = 0.f;
     for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps) {
         float4 a[4];
         load512(src + static_cast<size_t>(r) * kDim, lane, a);
         float4 a2[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) a2[i] = make_float4(a[i].x * a[i].x, a[i].y * a[i].y, a[i].z * a[i].z, a[i].w * a[i].w);
-        w4 = fmaxf(w4, dot512(a2, a2));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a[i].x * kF8Scale, a[i].y * kF8Scale), __NV_SATFINITE, __NV_E4M3);
-            const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(a[i].z * kF8Scale, a[i].w * kF8Scale), __NV_SATFINITE, __NV_E4M3);
-            reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r) * kDim)[lane + 32 * i] = lo | (hi << 16);
-        }
+        g4 = fmaxf(g4, dot512(a2, a2));
+        float u4 = 0.f, b4 = 0.f, b2 = 0.f;
+        bool sat = false;
+        f8_dither_row(a, lane, dither_key(seed, static_cast<uint64_t>(first_row_id + r)), dst + static_cast<size_t>(r) * kDim, u4, b4, b2, sat);
+        constexpr float kS4 = 1.f / (kF8Scale * kF8Scale * kF8Scale * kF8Scale);
+        w4 = fmaxf(w4, warp_sum(u4) * kS4);
     }
-    if (lane == 0 && w4 > 0.f) atomicMax(reinterpret_cast<int*>(g4max), __float_as_int(w4));
+    if (lane == 0 && g4 > 0.f) atomicMax(reinterpret_cast<int*>(g4max), __float_as_int(g4 * 1.0001f));
+    if (lane == 0 && w4 > 0.f) atomicMax(reinterpret_cast<int*>(w4max), __float_as_int(w4 * 1.0001f));
 }
 
 // scan copy + largest row norm (the margin of the coarse pass scales with it). One warp per row.

@@ -170,6 +170,17 @@ class Gallery:
         lib().fr_gallery_set_scan.argtypes = [C.c_void_p, C.c_int]
         check(lib().fr_gallery_set_scan(self._h, scan))
 
+    def debug_read(self, what: int, first: int = 0, count: int = 0) -> np.ndarray:
+        """test hook (fr_gallery_debug_read): 0 = e4m3 rows [count, 512] u8, 1 = query operand image, 2 = q_margin, 3 = q_gap,
+        4 = (gmax, g4max, w4max), 5 / 6 = sorted candidate lists (coarse scores / local rows) of the last k > 1 search"""
+        L = lib()
+        L.fr_gallery_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+        out = {0: lambda: np.empty((count, 512), np.uint8), 1: lambda: np.empty((256, 1024), np.uint8), 2: lambda: np.empty(256, np.float32),
+               3: lambda: np.empty(256, np.float32), 4: lambda: np.empty(3, np.float32),
+               5: lambda: np.empty((296, 256, 16), np.float32), 6: lambda: np.empty((296, 256, 16), np.int32)}[what]()
+        check(L.fr_gallery_debug_read(self._h, what, first, count, _ptr(out)))
+        return out
+
     def read_rows(self, first: int, count: int) -> np.ndarray:
         out = np.empty((count, 512), np.float32)
         check(lib().fr_gallery_read_rows(self._h, first, count, _ptr(out)))

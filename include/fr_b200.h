@@ -114,17 +114,29 @@ int fr_topk_merge_dev(const float *scores_parts_dev, const int64_t *idx_parts_de
 #define FR_PATH_EXACT 1
 #define FR_PATH_TENSOR 2
 int fr_gallery_set_path(FrGallery *g, int path);
-/* Precision of the scan copy the fused kernel streams. FR_SCAN_F16 (default): 1 KiB/row, provable error bound -> the result is the
- * exact fp32 top-k unconditionally. FR_SCAN_F8 (opt-in, L2-normalised rows only): e4m3, 512 B/row, half the HBM traffic and twice
- * the tensor rate; rows whose coarse score is within margin = 6.5 * sqrt(2) * 0.0373 * |q|_4 * max_rows |g|_4 of the best coarse score
- * (about 0.03 for isotropic unit vectors) are re-scored in exact fp32: exact unless the rounding errors of two scores exceed 6.5 sigma
- * of the bound on their standard deviation (no useful provable bound exists for fp8; csrc/search_kernels.cuh, tools/f8_error_model.py).
- * Scores returned are exact fp32 either way. Top-1 searches (the reference's getOutputs) use the append epilogue and stay fast for
- * queries without a match; k > 1 on the e4m3 copy keeps the sorted-list epilogue, whose 16-entry lists overflow under the wide
- * margin when nothing matches — such queries are recomputed by the exact fp32 scan (correct, slow): prefer FR_SCAN_F16 for k > 1. */
+/* Precision of the scan copy the fused kernel streams. Scores returned are exact fp32 either way (re-scored from the f32 rows).
+ * FR_SCAN_F16 (default): 1 KiB/row. |coarse - exact| <= 1.25e-3 |q| |row| is a deterministic bound, so the result is the exact fp32
+ *   top-k whenever rows and queries stay inside fp16's normal range (|component| <= 65504 and row norms >= ~1e-3; always true for
+ *   L2-normalised embeddings). Rows outside that range are refused by create / append with FR_ESTATE unless the gallery is switched to
+ *   FR_PATH_EXACT.
+ * FR_SCAN_F8 (opt-in, L2-normalised rows only): e4m3, 512 B/row, half the HBM traffic and twice the tensor rate. Rows and queries are
+ *   rounded STOCHASTICALLY (counter-based dither keyed by (seed, row id, column); FR_F8_SEED sets the seed), which makes the coarse
+ *   error of any fixed (query, row) pair a sum of independent bounded zero-mean terms whatever the data look like; every query is
+ *   certified after the re-score (best exact score within a gap of the best coarse score) or recomputed by the exact fp32 scan. The
+ *   returned top-1 differs from the exact fp32 top-1 with probability <= 1e-12 per query — over the dither, for ARBITRARY rows and
+ *   queries chosen without knowledge of the seed (Hoeffding; csrc/search_kernels.cuh kF8LogP; k > 1: <= k * 1e-12).
+ *   Query components beyond +-1.75 saturate e4m3: such queries are always recomputed exactly. Top-1 searches (the reference's
+ *   getOutputs) use the append epilogue and stay fast for queries without a match; k > 1 on the e4m3 copy keeps the sorted-list
+ *   epilogue, whose 16-entry lists overflow under the wide margin when nothing matches — such queries are recomputed by the exact fp32
+ *   scan (correct, slow): prefer FR_SCAN_F16 for k > 1. */
 #define FR_SCAN_F16 0
 #define FR_SCAN_F8 1
 int fr_gallery_set_scan(FrGallery *g, int scan);
+/* Test hook (parity of the e4m3 image with oracle/f8_dither.py): what = 0: `count` rows of the e4m3 scan copy from row `first`
+ * (count x 512 bytes); 1: the query operand image of the last <= 256-query chunk (256 x 512 bytes e4m3 or 256 x 512 fp16);
+ * 2: q_margin[256] f32 (accumulator units); 3: q_gap[256] f32; 4: {gmax, g4max, w4max} f32; 5 / 6: the sorted candidate lists of the
+ * last k > 1 search, [296 lists][256][16] coarse scores f32 / local rows i32. Waits for the gallery's stream. */
+int fr_gallery_debug_read(FrGallery *g, int what, int64_t first, int64_t count, void *out);
 
 /* Fused exchange + merge over NVLink peer memory (replaces "all-gather, then fr_topk_merge_dev"): one kernel per rank stores its
  * nq x k results into every peer's mailbox, publishes per-query flags, waits for the peers and merges. One FrExchange per rank

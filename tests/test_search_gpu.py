@@ -338,6 +338,149 @@ def test_fp8_scan_unknown_queries_and_near_ties():
     g.close()
 
 
+def _e4m3_bytes_to_float(b):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(b)).view(torch.float8_e4m3fn).float().numpy()
+
+
+def test_fp8_dither_image_and_margins_match_the_emulation():
+    # the CPU suite proves the exactness argument on oracle/f8_dither.py's emulation; here the kernels' e4m3 images (rows AND
+    # queries), the row bounds and the per-query margin / certificate gap are checked against that emulation, bit for bit where
+    # they are integers/bytes
+    from oracle import f8_dither as fd
+
+    rng = np.random.default_rng(21)
+    n, off = 5000, 1234567
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    G[7] = np.where(rng.random(512) < 0.5, -1, 1).astype(np.float32) / np.sqrt(512)        # binarised row
+    G[8, :] = 0
+    G[8, 3] = 1.0                                                                         # one-hot row (256 is representable)
+    q = so.l2_normalise(rng.standard_normal((200, 512))).astype(np.float32)
+    q[5] = G[7]
+    g = frb200.Gallery.from_rows(G, row_offset=off)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(frb200.FR_SCAN_F8)
+    g.topk(q, 1)
+    keys = fd.dither_key(fd.DEFAULT_SEED, np.arange(n, dtype=np.uint64) + np.uint64(off))
+    want, u, _, _ = fd.round_dither(G, fd.dither_r24(keys))
+    got = _e4m3_bytes_to_float(g.debug_read(0, 0, n))
+    assert np.array_equal(got, want)
+    gmax, g4max, w4max = g.debug_read(4)
+    _, g4, w4 = fd.dither_gallery(G, first_row_id=off)
+    assert abs(g4max / g4 - 1) < 1e-4 and abs(w4max / w4 - 1) < 1e-4
+    qh, m, gap, E = fd.dither_queries(q, float(g4max), float(w4max), float(gmax))
+    qimg = _e4m3_bytes_to_float(g.debug_read(1).reshape(-1)[: 256 * 512].reshape(256, 512))
+    assert np.array_equal(qimg[:200], qh) and not qimg[200:].any()
+    assert np.allclose(g.debug_read(2)[:200] / fd.SCALE ** 2, m, rtol=2e-4) and np.allclose(g.debug_read(3)[:200], gap, rtol=2e-4)
+    # appended rows continue the same dither stream (global row id), removed rows move their bytes
+    extra = so.l2_normalise(rng.standard_normal((300, 512)))
+    g.append(extra)
+    keys2 = fd.dither_key(fd.DEFAULT_SEED, np.arange(n, n + 300, dtype=np.uint64) + np.uint64(off))
+    assert np.array_equal(_e4m3_bytes_to_float(g.debug_read(0, n, 300)), fd.round_dither(extra, fd.dither_r24(keys2))[0])
+    g.close()
+
+
+def test_fp8_tensor_core_accumulation_is_inside_eps_det():
+    # the certificate budgets kF8AccEps |qbar| |ghat| for the MMA pipe's fp32 accumulation of the (exact) e4m3 products. Measure it:
+    # coarse scores of a k = 8 search (sorted-list epilogue keeps them) against the exact sum of the emulated operands.
+    from oracle import f8_dither as fd
+
+    rng = np.random.default_rng(33)
+    n = 40_000
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    planted = rng.integers(0, n, 256)
+    q = so.planted_queries(G[planted], noise=0.75, seed=3)
+    q[:64] = G[planted[:64]]                                    # cos = 1: the largest accumulators
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(frb200.FR_SCAN_F8)
+    g.topk(q, 8)
+    cs, ci = g.debug_read(5), g.debug_read(6)
+    gh = fd.round_dither(G, fd.dither_r24(fd.dither_key(fd.DEFAULT_SEED, np.arange(n, dtype=np.uint64))))[0].astype(np.float64)
+    qh = fd.dither_queries(q, 1.0, 1.0, 1.0)[0].astype(np.float64)
+    lists = 2 * min(74, (n + 255) // 256)
+    worst, seen = 0.0, 0
+    for l in range(lists):
+        for qi in range(0, 256, 5):
+            ok = ci[l, qi] >= 0
+            if not ok.any():
+                continue
+            want = (gh[ci[l, qi][ok]] @ qh[qi]) / fd.SCALE ** 2
+            scale = np.linalg.norm(qh[qi]) * np.linalg.norm(gh[ci[l, qi][ok]], axis=1) / fd.SCALE ** 2
+            worst = max(worst, float(np.abs(cs[l, qi][ok] - want).max() / scale.min()))
+            seen += int(ok.sum())
+    assert seen > 10_000
+    assert worst <= 0.5 * fd.ACC_EPS, worst                     # half the budget at most (fp32 accumulation: ~1e-6 expected)
+
+
+@pytest.mark.parametrize("kind", ["counter_example", "sign", "int8", "grid", "near_dup"])
+def test_fp8_structured_galleries_top1_exact(kind):
+    # structured rows broke the round-to-nearest e4m3 scan (wrong identity, no fallback). Same galleries as the CPU
+    # emulation tests, on the kernels: exact fp32 top-1, identical to the fp16 path, and no exact-scan fallback needed.
+    rng = np.random.default_rng(abs(hash(kind)) % 997)
+    n = 60_000
+    if kind == "counter_example":
+        sign = np.where(rng.random(512) < 0.5, -1.0, 1.0)
+        A = sign / np.sqrt(512.0)
+        B = sign * np.where(np.arange(512) % 2 == 0, 10.51, 12.06) / 256.0
+        G = so.l2_normalise(rng.standard_normal((n, 512)))
+        G[100], G[41_000] = A, B / np.linalg.norm(B)
+        q = np.concatenate([A[None, :], G[41_000][None, :], so.l2_normalise(rng.standard_normal((30, 512)))]).astype(np.float32)
+    elif kind == "sign":
+        G = so.l2_normalise(np.where(rng.random((n, 512)) < 0.5, -1.0, 1.0))
+        q = np.concatenate([G[rng.integers(0, n, 100)], so.l2_normalise(np.where(rng.random((100, 512)) < 0.5, -1.0, 1.0))]).astype(np.float32)
+    elif kind == "int8":
+        G = so.l2_normalise(np.clip(np.round(rng.standard_normal((n, 512)) * 24), -127, 127) + 1e-9)
+        q = np.concatenate([so.planted_queries(G[rng.integers(0, n, 128)], noise=0.75, seed=1), so.l2_normalise(rng.standard_normal((128, 512)))]).astype(np.float32)
+    elif kind == "grid":
+        lv = np.array([8.5, 9.5, 10.5, 11.5, 12.5, 13.5]) / 256.0
+        G = so.l2_normalise(rng.choice(lv, (n, 512)) * np.where(rng.random((n, 512)) < 0.5, -1.0, 1.0))
+        q = np.concatenate([G[rng.integers(0, n, 64)], so.l2_normalise(rng.standard_normal((64, 512)))]).astype(np.float32)
+    else:
+        G = so.l2_normalise(rng.standard_normal((n, 512)))
+        base = G[777].astype(np.float64)
+        for j, w in enumerate(np.sort(rng.choice(np.arange(1000, n - 10), 50, replace=False))):
+            c = 0.995 + 0.004 * j / 49
+            v = rng.standard_normal(512)
+            v -= v.dot(base) * base
+            G[w] = (c * base + np.sqrt(1 - c * c) * v / np.linalg.norm(v)).astype(np.float32)
+        G[n - 3] = G[777]
+        q = np.concatenate([G[777][None, :], so.l2_normalise(base[None, :] + 0.02 * rng.standard_normal((63, 512)))]).astype(np.float32)
+    G = np.ascontiguousarray(G, np.float32)
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(frb200.FR_SCAN_F8)
+    s, i = g.topk(q, 1)
+    flagged = g.last_flagged()
+    sim = so.sims(G, q)
+    oi, ov = so.get_outputs(sim)
+    assert np.array_equal(i[:, 0], oi), (kind, np.nonzero(i[:, 0] != oi)[0][:5])
+    assert np.abs(s[:, 0] - ov).max() <= SCORE_TOL
+    assert flagged <= 1, (kind, flagged)
+    g.set_scan(frb200.FR_SCAN_F16)
+    s2, i2 = g.topk(q, 1)
+    assert np.array_equal(i, i2) and np.array_equal(s.view(np.uint32), s2.view(np.uint32))
+    if kind == "counter_example":
+        assert i[0, 0] == 100 and i[1, 0] == 41_000
+    g.close()
+
+
+def test_fp8_saturating_query_goes_to_the_exact_scan():
+    rng = np.random.default_rng(2)
+    G = so.l2_normalise(rng.standard_normal((20_000, 512)))
+    q = so.l2_normalise(rng.standard_normal((3, 512))).astype(np.float32)
+    q[1] *= 50.0                                                 # components beyond 1.75: e4m3 saturates, the error model does not hold
+    g = frb200.Gallery.from_rows(G)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(frb200.FR_SCAN_F8)
+    s, i = g.topk(q, 1)
+    oi, ov = so.get_outputs(so.sims(G, q))
+    assert np.array_equal(i[:, 0], oi) and np.allclose(s[:, 0], ov, rtol=1e-5)
+    assert g.last_flagged() == 1
+    g.close()
+
+
 def test_fp8_scan_everything_inside_margin_falls_back_exactly():
     # all rows identical up to 1e-4 noise: every row is inside the margin of the best, the append lists overflow, and the flagged
     # exact scan must still return the fp32 answer (lowest row among exact ties)
