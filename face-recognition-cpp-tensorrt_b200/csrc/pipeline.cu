@@ -31,7 +31,7 @@ struct FaceRef {
     int x1, y1, x2, y2;  // Bbox semantics: x = row, y = column
 };
 
-// cubic convolution coefficients, A = -0.75 (OpenCV interpolateCubic), float arithmetic
+// cubic convolution coefficients, A = -0.75 (OpenCV interpolateCubic, imgproc/src/resize.cpp), float arithmetic without contraction
 __device__ __forceinline__ void cubic_coeffs(float x, float (&c)[4]) {
     const float A = -0.75f;
     c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, __fadd_rn(x, 1.f)), __fmul_rn(5.f, A)), __fadd_rn(x, 1.f)), __fmul_rn(8.f, A)),
@@ -43,46 +43,62 @@ __device__ __forceinline__ void cubic_coeffs(float x, float (&c)[4]) {
     c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
 }
 
+// One axis of OpenCV's resize set-up (modules/imgproc/src/resize.cpp, hal::resize + resizeGeneric_ tables): destination index d of a
+// src -> 112 resize: scale = 1 / ((double)112 / src) (NOT src / 112: OpenCV inverts inv_scale), f = (float)((d + 0.5) * scale - 0.5),
+// s = floor(f), f -= s, float cubic coefficients, then the fixed-point table  saturate_cast<short>(c * INTER_RESIZE_COEF_SCALE)
+// with INTER_RESIZE_COEF_BITS = 11 (round half to even). No fused multiply-adds: the x86 baseline build has none.
+__device__ __forceinline__ void cubic_axis(int d, int src, int& s, int (&ic)[4]) {
+    const double inv_scale = __ddiv_rn(112.0, static_cast<double>(src));
+    const double scale = __ddiv_rn(1.0, inv_scale);
+    float f = static_cast<float>(__dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(d), 0.5), scale), 0.5));
+    s = static_cast<int>(floorf(f));
+    f = __fsub_rn(f, static_cast<float>(s));
+    float c[4];
+    cubic_coeffs(f, c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ic[k] = __float2int_rn(__fmul_rn(c[k], 2048.f));
+}
+
 // getCroppedFaces (src/arcface.cpp:3-17): ROI = Rect(Point(y1, x1), Point(y2, x2)) = rows [x1, x2), columns [y1, y2) of the frame,
-// cv::resize(..., Size(112, 112), INTER_CUBIC). The arithmetic follows OpenCV 4.13's u8 bicubic as observed through cv2 (float
-// coefficients, horizontal pass then vertical pass, taps replicated at the ROI border, round-half-even, saturate): third-party
-// code the reference links (OpenCV 4.5.5, README.md:11) — agreement with cv2 is within 1 LSB (tests/test_pipeline_gpu.py).
+// cv::resize(..., Size(112, 112), INTER_CUBIC). Byte-exact restatement of OpenCV's own u8 bicubic (resizeGeneric_<HResizeCubic<uchar,
+// int, short>, VResizeCubic<..., VResizeCubicVec_32s8u>>): horizontal pass in integers with the 11-bit coefficient table (taps
+// clamped to the ROI), vertical pass as the SIMD kernel computes it — float, beta * 2^-22, accumulated from tap 3 down to tap 0 with
+// separate multiplies and adds, round half to even, saturate. (OpenCV is third-party code the reference links, README.md:11; the
+// oracle is cv2 with its closed-source IPP accelerator switched off, tests/test_pipeline_gpu.py.)
 // One thread per output pixel; output u8 BGR HWC = CroppedFace::face, and the embedder's input.
 __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frames, int frame_h, int frame_w, int stride,
-                                                          const FaceRef* __restrict__ faces, int n_faces, uint8_t* __restrict__ out) {
+                                                          const FaceRef* __restrict__ faces, const int* __restrict__ n_faces_dev, int n_faces,
+                                                          uint8_t* __restrict__ out) {
     constexpr int D = 112;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int face = blockIdx.y;
+    if (n_faces_dev) n_faces = min(n_faces, *n_faces_dev);  // device-side face list (fr_pipeline_run): the count lives on the device
     if (t >= D * D || face >= n_faces) return;
     const int dy = t / D, dx = t % D;
     const FaceRef f = faces[face];
     const int r0 = min(f.x1, f.x2), c0 = min(f.y1, f.y2);
     const int sh = max(abs(f.x2 - f.x1), 1), sw = max(abs(f.y2 - f.y1), 1);  // an empty ROI would throw in OpenCV; use 1 pixel
     const uint8_t* base = frames + static_cast<size_t>(f.frame) * frame_h * stride;
-    const double scale_x = static_cast<double>(sw) / D, scale_y = static_cast<double>(sh) / D;
-    float fx = static_cast<float>((dx + 0.5) * scale_x - 0.5);
-    int sx = static_cast<int>(floorf(fx));
-    fx = __fsub_rn(fx, static_cast<float>(sx));
-    float fy = static_cast<float>((dy + 0.5) * scale_y - 0.5);
-    int sy = static_cast<int>(floorf(fy));
-    fy = __fsub_rn(fy, static_cast<float>(sy));
-    float cx[4], cy[4];
-    cubic_coeffs(fx, cx);
-    cubic_coeffs(fy, cy);
+    int sx, sy, ia[4], ib[4];
+    cubic_axis(dx, sw, sx, ia);
+    cubic_axis(dy, sh, sy, ib);
+    int cols[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cols[i] = min(max(min(max(sx - 1 + i, 0), sw - 1) + c0, 0), frame_w - 1) * 3;
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 3; j >= 0; --j) {
         const int rr = min(max(sy - 1 + j, 0), sh - 1) + r0;
         const uint8_t* row = base + static_cast<size_t>(min(max(rr, 0), frame_h - 1)) * stride;
-        float h[3] = {0.f, 0.f, 0.f};
+        const float b = __fmul_rn(static_cast<float>(ib[j]), 1.f / 4194304.f);  // beta * 1 / (INTER_RESIZE_COEF_SCALE^2): exact
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int cc = min(max(min(max(sx - 1 + i, 0), sw - 1) + c0, 0), frame_w - 1);
+        for (int ch = 0; ch < 3; ++ch) {
+            int h = 0;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) h[ch] = __fadd_rn(h[ch], __fmul_rn(static_cast<float>(row[cc * 3 + ch]), cx[i]));
+            for (int i = 0; i < 4; ++i) h += static_cast<int>(row[cols[i] + ch]) * ia[i];
+            const float p = __fmul_rn(static_cast<float>(h), b);
+            acc[ch] = j == 3 ? p : __fadd_rn(p, acc[ch]);
         }
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) acc[ch] = __fadd_rn(acc[ch], __fmul_rn(h[ch], cy[j]));
     }
     uint8_t* o = out + (static_cast<size_t>(face) * D * D + t) * 3;
 #pragma unroll
@@ -112,7 +128,7 @@ namespace {
 
 void crop_into_embedder(FrPipeline* p, const uint8_t* frames_dev, int stride, const FaceRef* faces_dev, int n, cudaStream_t st) {
     dim3 grid((112 * 112 + 255) / 256, n);
-    crop_resize_kernel<<<grid, 256, 0, st>>>(frames_dev, p->frame_h, p->frame_w, stride, faces_dev, n, embedder_u8_input(p->emb));
+    crop_resize_kernel<<<grid, 256, 0, st>>>(frames_dev, p->frame_h, p->frame_w, stride, faces_dev, nullptr, n, embedder_u8_input(p->emb));
     count_launch();
     FRB_CUDA(cudaGetLastError());
 }
@@ -265,7 +281,7 @@ int fr_embedder_run_boxes(FrEmbedder* e, const uint8_t* frame, int frame_h, int 
             for (int beg = 0; beg < n; beg += mb) {
                 const int m = std::min(mb, n - beg);
                 dim3 grid((112 * 112 + 255) / 256, m);
-                crop_resize_kernel<<<grid, 256, 0, st>>>(fdev, frame_h, frame_w, frame_w * 3, faces_dev + beg, m, embedder_u8_input(e));
+                crop_resize_kernel<<<grid, 256, 0, st>>>(fdev, frame_h, frame_w, frame_w * 3, faces_dev + beg, nullptr, m, embedder_u8_input(e));
                 count_launch();
                 if (crops_u8)
                     FRB_CUDA(cudaMemcpyAsync(crops_u8 + static_cast<size_t>(beg) * 112 * 112 * 3, embedder_u8_input(e),
