@@ -302,7 +302,9 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
     FRB_CUDA(cudaGetLastError());
 }
 
-void run_post(FrDetector* d, const float* loc, const float* conf, const float* landm, int batch, cudaStream_t st) {
+// slot0: results of image i go to result slot slot0 + i (the pipeline detects a large batch in sub-batches while later frames are
+// still in flight over PCIe)
+void run_post(FrDetector* d, const float* loc, const float* conf, const float* landm, int batch, cudaStream_t st, int slot0 = 0) {
     DetPostParams p;
     p.net_w = d->net_w;
     p.net_h = d->net_h;
@@ -312,16 +314,19 @@ void run_post(FrDetector* d, const float* loc, const float* conf, const float* l
     p.bbox_thr = d->bbox_thr;
     p.max_faces = d->max_faces;
     p.anchors = d->anchors;
-    det_decode_nms_kernel<<<batch, 256, 0, st>>>(loc, conf, landm, p, d->cand, d->boxes, d->counts, d->out_landm, d->out_ids);
+    det_decode_nms_kernel<<<batch, 256, 0, st>>>(loc, conf, landm, p, d->cand, d->boxes + static_cast<size_t>(slot0) * d->max_faces, d->counts + slot0,
+                                                 d->out_landm + static_cast<size_t>(slot0) * d->max_faces * 10,
+                                                 d->out_ids + static_cast<size_t>(slot0) * d->max_faces);
     count_launch();
     FRB_CUDA(cudaGetLastError());
 }
 
 // network (+ decode/NMS) replayed from a CUDA graph per (canvas pointer, stride, batch, with_post)
-void forward_graph(FrDetector* d, const uint8_t* canvas, int cs, int batch, bool with_post, cudaStream_t st) {
-    d->graphs.run({reinterpret_cast<uint64_t>(canvas), (static_cast<uint64_t>(cs) << 32) | static_cast<uint64_t>(batch), with_post ? 1ull : 0ull}, st, [&] {
+void forward_graph(FrDetector* d, const uint8_t* canvas, int cs, int batch, bool with_post, cudaStream_t st, int slot0 = 0) {
+    d->graphs.run({reinterpret_cast<uint64_t>(canvas), (static_cast<uint64_t>(cs) << 32) | static_cast<uint64_t>(batch),
+                   (with_post ? 1ull : 0ull) | (static_cast<uint64_t>(slot0) << 1)}, st, [&] {
         run_net(d, canvas, cs, nullptr, batch, st);
-        if (with_post) run_post(d, d->loc, d->conf, d->landm, batch, st);
+        if (with_post) run_post(d, d->loc, d->conf, d->landm, batch, st, slot0);
     });
 }
 
@@ -392,10 +397,11 @@ void copy_raw(FrDetector* d, int batch, float* loc, float* conf, float* landm, c
 
 // internal hooks for the end-to-end pipeline (csrc/pipeline.cu)
 namespace frb {
-void detector_forward_dev(FrDetector* d, const uint8_t* frames_dev, int stride, int batch, cudaStream_t st) {
+void detector_forward_dev(FrDetector* d, const uint8_t* frames_dev, int stride, int batch, cudaStream_t st, int slot0) {
+    if (slot0 < 0 || slot0 + batch > d->max_batch) throw ArgError{"detector sub-batch outside max_batch"};
     int cs = 0;
     const uint8_t* canvas = stage_frames(d, frames_dev, stride, batch, true, &cs, st);
-    forward_graph(d, canvas, cs, batch, true, st);
+    forward_graph(d, canvas, cs, batch, true, st, slot0);
 }
 uint8_t* detector_frames_buffer(FrDetector* d) { return d->frames_dev; }
 const FrBbox* detector_boxes(const FrDetector* d) { return d->boxes; }

@@ -89,6 +89,11 @@ struct FrEmbedder {
     std::vector<std::pair<const __half*, int>> unit_out;  // per unit: (y buffer, geometry index) for fr_embedder_trace
     int last_batch = 0;
     bool last_u8 = false;
+    // persistent scratch of fr_embedder_run_boxes (ArcFaceIR50::forward): one frame + its face list, grown on demand
+    uint8_t* box_frame = nullptr;
+    size_t box_frame_cap = 0;
+    void* box_faces = nullptr;
+    size_t box_faces_cap = 0;
     GraphCache graphs;
 };
 
@@ -479,6 +484,30 @@ uint8_t* embedder_u8_input(FrEmbedder* e) { return e->in_u8; }
 float* embedder_output(FrEmbedder* e) { return e->out_dev; }
 int embedder_max_batch(const FrEmbedder* e) { return e->max_batch; }
 int embedder_device(const FrEmbedder* e) { return e->device; }
+cudaStream_t embedder_stream(FrEmbedder* e) { return e->stream; }
+// grow-only device scratch owned by the embedder (freed with it); the caller has synchronised the embedder's stream
+static void* grow_scratch(FrEmbedder* e, void*& buf, size_t& cap, size_t bytes) {
+    if (bytes <= cap) return buf;
+    void* nb = nullptr;
+    FRB_CUDA(cudaMalloc(&nb, bytes));
+    if (buf) {
+        cudaFree(buf);
+        for (auto& a : e->allocs)
+            if (a == buf) a = nb;
+    } else {
+        e->allocs.push_back(nb);
+    }
+    buf = nb;
+    cap = bytes;
+    return buf;
+}
+uint8_t* embedder_frame_scratch(FrEmbedder* e, size_t bytes) {
+    void* b = e->box_frame;
+    grow_scratch(e, b, e->box_frame_cap, bytes);
+    e->box_frame = static_cast<uint8_t*>(b);
+    return e->box_frame;
+}
+void* embedder_faces_scratch(FrEmbedder* e, size_t bytes) { return grow_scratch(e, e->box_faces, e->box_faces_cap, bytes); }
 void embedder_forward_u8(FrEmbedder* e, int batch, cudaStream_t st) {
     e->last_batch = batch;
     e->last_u8 = true;

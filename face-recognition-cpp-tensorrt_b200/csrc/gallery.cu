@@ -321,6 +321,15 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     g->stats.ctas = units * cg;
 }
 
+// the e4m3 copy scales by 256 and saturates at 448: only L2-normalised rows may enter it
+void check_unit_rows(const float* rows, int64_t n) {
+    for (int64_t r = 0; r < n; ++r) {
+        double ss = 0;
+        for (int i = 0; i < kDim; ++i) ss += static_cast<double>(rows[r * kDim + i]) * rows[r * kDim + i];
+        if (ss > 1.001 * 1.001) throw StateError{"FR_SCAN_F8 needs L2-normalised rows (row norm > 1)"};
+    }
+}
+
 void check_query_args(const FrGallery* g, const void* q, int nq) {
     if (!g) throw ArgError{"null gallery"};
     if (!q || nq <= 0) throw ArgError{"no queries"};
@@ -433,6 +442,7 @@ void fr_gallery_destroy(FrGallery* g) {
 }
 
 int64_t fr_gallery_rows(const FrGallery* g) { return g ? g->n : -1; }
+int fr_gallery_device(const FrGallery* g) { return g ? g->device : FR_EINVAL; }
 
 int fr_gallery_set_path(FrGallery* g, int path) {
     return guarded([&] {
@@ -486,13 +496,7 @@ int fr_gallery_append(FrGallery* g, const float* rows, int64_t n) {
         if (n == 0) return;
         DeviceGuard dg(g->device);
         FRB_CUDA(cudaStreamSynchronize(g->stream));
-        if (g->rows_f8 || g->scan == FR_SCAN_F8) {  // the e4m3 copy scales by 256 and saturates at 448: only L2-normalised rows may enter it
-            for (int64_t r = 0; r < n; ++r) {
-                double ss = 0;
-                for (int i = 0; i < kDim; ++i) ss += static_cast<double>(rows[r * kDim + i]) * rows[r * kDim + i];
-                if (ss > 1.001 * 1.001) throw StateError{"FR_SCAN_F8 needs L2-normalised rows (appended row norm > 1)"};
-            }
-        }
+        if (g->rows_f8 || g->scan == FR_SCAN_F8) check_unit_rows(rows, n);
         if (g->n + n > g->capacity) grow_rows(g, std::max<int64_t>(g->n + n, g->capacity + g->capacity / 2 + 1024));
         float* dst = g->rows_f32 + g->n * kDim;
         FRB_CUDA(cudaMemcpyAsync(dst, rows, sizeof(float) * n * kDim, cudaMemcpyHostToDevice, g->stream));
@@ -508,6 +512,30 @@ int fr_gallery_append(FrGallery* g, const float* rows, int64_t n) {
         FRB_CUDA(cudaStreamSynchronize(g->stream));
         g->n += n;
         refresh_tmaps(g);
+    });
+}
+
+int fr_gallery_update(FrGallery* g, int64_t first, const float* rows, int64_t n) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        if (n < 0 || (n > 0 && !rows)) throw ArgError{"bad rows / n"};
+        if (first < 0 || first + n > g->n) throw ArgError{"row range out of bounds"};
+        if (n == 0) return;
+        DeviceGuard dg(g->device);
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
+        if (g->rows_f8 || g->scan == FR_SCAN_F8) check_unit_rows(rows, n);
+        float* dst = g->rows_f32 + first * kDim;
+        FRB_CUDA(cudaMemcpyAsync(dst, rows, sizeof(float) * n * kDim, cudaMemcpyHostToDevice, g->stream));
+        const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, g->sms * 16LL));
+        // the bounds (gmax, g4max, w4max) are running maxima: they keep the replaced rows' contribution and stay upper bounds
+        make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f16 + first * kDim, n, g->gmax);
+        count_launch();
+        if (g->rows_f8) {
+            make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f8 + first * kDim, n, g->f8_seed, g->row_offset + first, g->g4max, g->w4max);
+            count_launch();
+        }
+        FRB_CUDA(cudaGetLastError());
+        FRB_CUDA(cudaStreamSynchronize(g->stream));
     });
 }
 

@@ -1,5 +1,7 @@
-// End-to-end pipeline on one GPU: detect -> crop + bicubic resize -> embed -> search, one stream, no host round trip except
-// the (tiny) box list. Replaces the body of the reference's /inference handler (/root/reference src/app.cpp:293-352):
+// End-to-end pipeline on one GPU: detect -> face-list compaction -> crop + bicubic resize -> embed -> search, all on the device.
+// The frames travel over PCIe in sub-batches on a copy stream while earlier sub-batches are already being detected; the face
+// list is compacted by a kernel (no host round trip between detector and embedder): the host only learns the face COUNT, while the
+// first embedder chunk is already running. Replaces the body of the reference's /inference handler (/root/reference src/app.cpp:293-352):
 // detector.findFace (src/retinaface.cpp:147-152) -> recognizer.forward (src/arcface.cpp:166-187: getCroppedFaces :3-17,
 // preprocessFaces :116-129, doInference :139-148) -> featureMatching + getOutputs (:189-217).
 #include <algorithm>
@@ -10,7 +12,7 @@
 
 // internal hooks (detector.cu / embedder.cu)
 namespace frb {
-void detector_forward_dev(FrDetector* d, const uint8_t* frames_dev, int stride, int batch, cudaStream_t st);
+void detector_forward_dev(FrDetector* d, const uint8_t* frames_dev, int stride, int batch, cudaStream_t st, int slot0);
 uint8_t* detector_frames_buffer(FrDetector* d);
 const FrBbox* detector_boxes(const FrDetector* d);
 const int* detector_counts(const FrDetector* d);
@@ -20,6 +22,9 @@ float* embedder_output(FrEmbedder* e);
 int embedder_max_batch(const FrEmbedder* e);
 int embedder_device(const FrEmbedder* e);
 void embedder_forward_u8(FrEmbedder* e, int batch, cudaStream_t st);
+cudaStream_t embedder_stream(FrEmbedder* e);
+uint8_t* embedder_frame_scratch(FrEmbedder* e, size_t bytes);
+void* embedder_faces_scratch(FrEmbedder* e, size_t bytes);
 }  // namespace frb
 
 using namespace frb;
@@ -67,12 +72,13 @@ __device__ __forceinline__ void cubic_axis(int d, int src, int& s, int (&ic)[4])
 // oracle is cv2 with its closed-source IPP accelerator switched off, tests/test_pipeline_gpu.py.)
 // One thread per output pixel; output u8 BGR HWC = CroppedFace::face, and the embedder's input.
 __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frames, int frame_h, int frame_w, int stride,
-                                                          const FaceRef* __restrict__ faces, const int* __restrict__ n_faces_dev, int n_faces,
-                                                          uint8_t* __restrict__ out) {
+                                                          const FaceRef* __restrict__ faces, const int* __restrict__ n_faces_dev, int first,
+                                                          int n_faces, uint8_t* __restrict__ out) {
     constexpr int D = 112;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int face = blockIdx.y;
-    if (n_faces_dev) n_faces = min(n_faces, *n_faces_dev);  // device-side face list (fr_pipeline_run): the count lives on the device
+    const int face = blockIdx.y;  // faces[face] is face `first + face` of the batch
+    // device-side face list (fr_pipeline_run): the total count lives on the device; chunk slots beyond it are skipped
+    if (n_faces_dev) n_faces = min(n_faces, *n_faces_dev - first);
     if (t >= D * D || face >= n_faces) return;
     const int dy = t / D, dx = t % D;
     const FaceRef f = faces[face];
@@ -105,6 +111,44 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
     for (int ch = 0; ch < 3; ++ch) o[ch] = static_cast<uint8_t>(min(max(__float2int_rn(acc[ch]), 0), 255));
 }
 
+// Face list on the device: face k of the batch = (frame, box) in frame-major, detection order — the order the host loop of the
+// reference visits them (src/app.cpp:304-310). One block; exclusive scan of the per-frame counts.
+__global__ void __launch_bounds__(256) compact_faces_kernel(const FrBbox* __restrict__ boxes, const int* __restrict__ counts, int batch,
+                                                            int max_faces, FaceRef* __restrict__ faces, int* __restrict__ n_out) {
+    __shared__ int warp_tot[8];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int f0 = 0; f0 < batch; f0 += blockDim.x) {
+        const int f = f0 + threadIdx.x;
+        const int c = f < batch ? min(max(counts[f], 0), max_faces) : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        off += inc - c;
+        for (int j = 0; j < c; ++j) {
+            const FrBbox b = boxes[static_cast<size_t>(f) * max_faces + j];
+            faces[off + j] = FaceRef{f, b.x1, b.y1, b.x2, b.y2};
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += warp_tot[w];
+            base_s += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = base_s;
+}
+
 }  // namespace
 
 struct FrPipeline {
@@ -112,59 +156,84 @@ struct FrPipeline {
     FrEmbedder* emb = nullptr;
     FrGallery* gal = nullptr;
     int device = 0, frame_h = 0, frame_w = 0, max_batch = 0, max_faces = 0, emb_batch = 0;
-    cudaStream_t stream = nullptr;
+    int sub_batch = 16;              // frames per H2D / detect sub-batch (FR_PIPE_SUB)
+    int spec = 0;                    // size of the speculative first embedder chunk (adapts to the previous call's face count)
+    cudaStream_t stream = nullptr;   // compute
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> h2d_done;
+    cudaEvent_t count_ready = nullptr;
     FaceRef* faces_dev = nullptr;
+    int* n_dev = nullptr;
+    int* h_n = nullptr;              // pinned
     float* embeds_dev = nullptr;     // max_batch * max_faces x 512
     float* score_dev = nullptr;
     long long* idx_dev = nullptr;
-    std::vector<FrBbox> h_boxes;
-    std::vector<int> h_counts;
-    std::vector<FaceRef> h_faces;
-    std::vector<float> h_score;
-    std::vector<long long> h_idx;
+    FrBbox* h_boxes = nullptr;       // pinned, max_batch * max_faces
+    int* h_counts = nullptr;         // pinned, max_batch
+    float* h_score = nullptr;        // pinned
+    long long* h_idx = nullptr;      // pinned
 };
 
 namespace {
 
-void crop_into_embedder(FrPipeline* p, const uint8_t* frames_dev, int stride, const FaceRef* faces_dev, int n, cudaStream_t st) {
-    dim3 grid((112 * 112 + 255) / 256, n);
-    crop_resize_kernel<<<grid, 256, 0, st>>>(frames_dev, p->frame_h, p->frame_w, stride, faces_dev, nullptr, n, embedder_u8_input(p->emb));
+void crop_into_embedder(FrPipeline* p, const uint8_t* frames_dev, int stride, const FaceRef* faces_dev, const int* n_dev, int beg, int m,
+                        cudaStream_t st) {
+    dim3 grid((112 * 112 + 255) / 256, m);
+    // faces beyond the device-side count leave their (stale) crop untouched; their embeddings are never read
+    crop_resize_kernel<<<grid, 256, 0, st>>>(frames_dev, p->frame_h, p->frame_w, stride, faces_dev + beg, n_dev, beg, m, embedder_u8_input(p->emb));
     count_launch();
     FRB_CUDA(cudaGetLastError());
 }
 
-// frames already on the device. Fills the host vectors of the pipeline; returns the number of faces.
-int run_device(FrPipeline* p, const uint8_t* frames_dev, int stride, int batch, float* embeddings_host) {
-    cudaStream_t st = p->stream;
-    detector_forward_dev(p->det, frames_dev, stride, batch, st);
-    FRB_CUDA(cudaMemcpyAsync(p->h_boxes.data(), detector_boxes(p->det), sizeof(FrBbox) * batch * p->max_faces, cudaMemcpyDeviceToHost, st));
-    FRB_CUDA(cudaMemcpyAsync(p->h_counts.data(), detector_counts(p->det), sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
-    FRB_CUDA(cudaStreamSynchronize(st));
-    p->h_faces.clear();
-    for (int f = 0; f < batch; ++f)
-        for (int j = 0; j < p->h_counts[f]; ++j) {
-            const FrBbox& b = p->h_boxes[static_cast<size_t>(f) * p->max_faces + j];
-            p->h_faces.push_back(FaceRef{f, b.x1, b.y1, b.x2, b.y2});
-        }
-    const int n = static_cast<int>(p->h_faces.size());
-    if (n == 0) return 0;
-    FRB_CUDA(cudaMemcpyAsync(p->faces_dev, p->h_faces.data(), sizeof(FaceRef) * n, cudaMemcpyHostToDevice, st));
-    for (int beg = 0; beg < n; beg += p->emb_batch) {  // chunked like ArcFaceIR50::forward (src/arcface.cpp:177-185), rows i -> i
-        const int m = std::min(p->emb_batch, n - beg);
-        crop_into_embedder(p, frames_dev, stride, p->faces_dev + beg, m, st);
-        embedder_forward_u8(p->emb, m, st);
-        FRB_CUDA(cudaMemcpyAsync(p->embeds_dev + static_cast<size_t>(beg) * 512, embedder_output(p->emb), sizeof(float) * m * 512,
-                                 cudaMemcpyDeviceToDevice, st));
+void embed_chunk(FrPipeline* p, const uint8_t* frames_dev, int stride, int beg, int m, cudaStream_t st) {
+    crop_into_embedder(p, frames_dev, stride, p->faces_dev, p->n_dev, beg, m, st);
+    embedder_forward_u8(p->emb, m, st);
+    FRB_CUDA(cudaMemcpyAsync(p->embeds_dev + static_cast<size_t>(beg) * 512, embedder_output(p->emb), sizeof(float) * m * 512,
+                             cudaMemcpyDeviceToDevice, st));
+}
+
+// frames: host. Fills the pinned host arrays of the pipeline; returns the number of faces.
+int run_batch(FrPipeline* p, const uint8_t* frames, int stride, int batch, float* embeddings_host) {
+    cudaStream_t st = p->stream, cs = p->copy_stream;
+    uint8_t* fdev = detector_frames_buffer(p->det);
+    const size_t row_bytes = static_cast<size_t>(p->frame_w) * 3, frame_bytes = row_bytes * p->frame_h;
+    // the previous call's kernels no longer read the frame buffer (every call ends with a stream sync), so the copies may start now
+    int k = 0;
+    for (int f0 = 0; f0 < batch; f0 += p->sub_batch, ++k) {
+        const int m = std::min(p->sub_batch, batch - f0);
+        FRB_CUDA(cudaMemcpy2DAsync(fdev + f0 * frame_bytes, row_bytes, frames + static_cast<size_t>(f0) * p->frame_h * stride, stride, row_bytes,
+                                   static_cast<size_t>(m) * p->frame_h, cudaMemcpyHostToDevice, cs));
+        FRB_CUDA(cudaEventRecord(p->h2d_done[k], cs));
+        FRB_CUDA(cudaStreamWaitEvent(st, p->h2d_done[k], 0));
+        detector_forward_dev(p->det, fdev + f0 * frame_bytes, static_cast<int>(row_bytes), m, st, f0);
     }
-    if (embeddings_host) FRB_CUDA(cudaMemcpyAsync(embeddings_host, p->embeds_dev, sizeof(float) * n * 512, cudaMemcpyDeviceToHost, st));
-    if (p->gal && fr_gallery_rows(p->gal) > 0) {
-        const int rc = fr_gallery_topk_dev(p->gal, p->embeds_dev, n, 1, p->score_dev, reinterpret_cast<int64_t*>(p->idx_dev), st);
-        if (rc != FR_OK) throw CudaError{std::string("pipeline search failed: ") + fr_last_error()};
-        FRB_CUDA(cudaMemcpyAsync(p->h_score.data(), p->score_dev, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-        FRB_CUDA(cudaMemcpyAsync(p->h_idx.data(), p->idx_dev, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
-    } else {
-        std::fill(p->h_idx.begin(), p->h_idx.begin() + n, -1LL);
-        std::fill(p->h_score.begin(), p->h_score.begin() + n, 0.f);
+    compact_faces_kernel<<<1, 256, 0, st>>>(detector_boxes(p->det), detector_counts(p->det), batch, p->max_faces, p->faces_dev, p->n_dev);
+    count_launch();
+    FRB_CUDA(cudaGetLastError());
+    FRB_CUDA(cudaMemcpyAsync(p->h_n, p->n_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FRB_CUDA(cudaMemcpyAsync(p->h_boxes, detector_boxes(p->det), sizeof(FrBbox) * batch * p->max_faces, cudaMemcpyDeviceToHost, st));
+    FRB_CUDA(cudaMemcpyAsync(p->h_counts, detector_counts(p->det), sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    FRB_CUDA(cudaEventRecord(p->count_ready, st));
+    // speculative first chunk: enqueued before the host knows the face count, so the GPU never waits for the host in the middle
+    const int slots = batch * p->max_faces;
+    const int s0 = std::min({p->emb_batch, slots, p->spec > 0 ? p->spec : slots});
+    embed_chunk(p, fdev, static_cast<int>(row_bytes), 0, s0, st);
+    FRB_CUDA(cudaEventSynchronize(p->count_ready));  // the GPU is busy with the chunk above while the host learns the count
+    const int n = *p->h_n;
+    p->spec = std::max(32, (n + 31) / 32 * 32);
+    for (int beg = s0; beg < n; beg += p->emb_batch)  // chunked like ArcFaceIR50::forward (src/arcface.cpp:177-185), rows i -> i
+        embed_chunk(p, fdev, static_cast<int>(row_bytes), beg, std::min(p->emb_batch, n - beg), st);
+    if (n > 0) {
+        if (embeddings_host) FRB_CUDA(cudaMemcpyAsync(embeddings_host, p->embeds_dev, sizeof(float) * n * 512, cudaMemcpyDeviceToHost, st));
+        if (p->gal && fr_gallery_rows(p->gal) > 0) {
+            const int rc = fr_gallery_topk_dev(p->gal, p->embeds_dev, n, 1, p->score_dev, reinterpret_cast<int64_t*>(p->idx_dev), st);
+            if (rc != FR_OK) throw CudaError{std::string("pipeline search failed: ") + fr_last_error()};
+            FRB_CUDA(cudaMemcpyAsync(p->h_score, p->score_dev, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+            FRB_CUDA(cudaMemcpyAsync(p->h_idx, p->idx_dev, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        } else {
+            std::fill(p->h_idx, p->h_idx + n, -1LL);
+            std::fill(p->h_score, p->h_score + n, 0.f);
+        }
     }
     FRB_CUDA(cudaStreamSynchronize(st));
     return n;
@@ -183,23 +252,31 @@ int fr_pipeline_create(FrDetector* det, FrEmbedder* emb, FrGallery* gal, FrPipel
         p->gal = gal;
         detector_dims(det, &p->frame_h, &p->frame_w, &p->max_batch, &p->max_faces, &p->device);
         if (embedder_device(emb) != p->device) throw ArgError{"detector and embedder live on different devices"};
+        if (gal && fr_gallery_device(gal) != p->device) throw ArgError{"the gallery lives on a different device than the detector"};
         p->emb_batch = embedder_max_batch(emb);
+        if (const char* e = std::getenv("FR_PIPE_SUB")) p->sub_batch = std::max(1, std::atoi(e));
         DeviceGuard dg(p->device);
         const size_t slots = static_cast<size_t>(p->max_batch) * p->max_faces;
         try {
             FRB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+            FRB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+            p->h2d_done.resize((p->max_batch + p->sub_batch - 1) / p->sub_batch);
+            for (auto& e : p->h2d_done) FRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            FRB_CUDA(cudaEventCreateWithFlags(&p->count_ready, cudaEventDisableTiming));
             FRB_CUDA(cudaMalloc(&p->faces_dev, sizeof(FaceRef) * slots));
+            FRB_CUDA(cudaMalloc(&p->n_dev, sizeof(int)));
             FRB_CUDA(cudaMalloc(&p->embeds_dev, sizeof(float) * slots * 512));
             FRB_CUDA(cudaMalloc(&p->score_dev, sizeof(float) * slots));
             FRB_CUDA(cudaMalloc(&p->idx_dev, sizeof(long long) * slots));
+            FRB_CUDA(cudaMallocHost(&p->h_n, sizeof(int)));
+            FRB_CUDA(cudaMallocHost(&p->h_boxes, sizeof(FrBbox) * slots));
+            FRB_CUDA(cudaMallocHost(&p->h_counts, sizeof(int) * p->max_batch));
+            FRB_CUDA(cudaMallocHost(&p->h_score, sizeof(float) * slots));
+            FRB_CUDA(cudaMallocHost(&p->h_idx, sizeof(long long) * slots));
         } catch (...) {
             fr_pipeline_destroy(p.release());
             throw;
         }
-        p->h_boxes.resize(slots);
-        p->h_counts.resize(p->max_batch);
-        p->h_score.resize(slots);
-        p->h_idx.resize(slots);
         *out = p.release();
     });
 }
@@ -209,11 +286,22 @@ void fr_pipeline_destroy(FrPipeline* p) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(p->device);
+    if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     if (p->stream) cudaStreamSynchronize(p->stream);
     cudaFree(p->faces_dev);
+    cudaFree(p->n_dev);
     cudaFree(p->embeds_dev);
     cudaFree(p->score_dev);
     cudaFree(p->idx_dev);
+    cudaFreeHost(p->h_n);
+    cudaFreeHost(p->h_boxes);
+    cudaFreeHost(p->h_counts);
+    cudaFreeHost(p->h_score);
+    cudaFreeHost(p->h_idx);
+    for (auto e : p->h2d_done)
+        if (e) cudaEventDestroy(e);
+    if (p->count_ready) cudaEventDestroy(p->count_ready);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (prev >= 0) cudaSetDevice(prev);
     delete p;
@@ -226,9 +314,6 @@ int fr_pipeline_run(FrPipeline* p, const uint8_t* frames, int stride, int batch,
         if (batch < 1 || batch > p->max_batch) throw ArgError{"batch out of range (1..max_batch)"};
         if (stride < p->frame_w * 3) throw ArgError{"stride smaller than frame_w * 3"};
         DeviceGuard dg(p->device);
-        uint8_t* fdev = detector_frames_buffer(p->det);
-        FRB_CUDA(cudaMemcpy2DAsync(fdev, static_cast<size_t>(p->frame_w) * 3, frames, stride, static_cast<size_t>(p->frame_w) * 3,
-                                   static_cast<size_t>(batch) * p->frame_h, cudaMemcpyHostToDevice, p->stream));
         // per-frame face slots: face j of frame f -> slot f * max_faces + j; embeddings are compact (face order)
         std::vector<float> compact;
         float* emb_tmp = nullptr;
@@ -236,9 +321,16 @@ int fr_pipeline_run(FrPipeline* p, const uint8_t* frames, int stride, int batch,
             compact.resize(static_cast<size_t>(batch) * p->max_faces * 512);
             emb_tmp = compact.data();
         }
-        const int n = run_device(p, fdev, p->frame_w * 3, batch, emb_tmp);
-        std::copy(p->h_boxes.begin(), p->h_boxes.begin() + static_cast<size_t>(batch) * p->max_faces, boxes);
-        std::copy(p->h_counts.begin(), p->h_counts.begin() + batch, counts);
+        int n = 0;
+        try {
+            n = run_batch(p, frames, stride, batch, emb_tmp);
+        } catch (...) {  // leave no work in flight that still reads the caller's buffers
+            cudaStreamSynchronize(p->copy_stream);
+            cudaStreamSynchronize(p->stream);
+            throw;
+        }
+        std::copy(p->h_boxes, p->h_boxes + static_cast<size_t>(batch) * p->max_faces, boxes);
+        std::copy(p->h_counts, p->h_counts + batch, counts);
         int k = 0;
         for (int f = 0; f < batch; ++f)
             for (int j = 0; j < p->max_faces; ++j) {
@@ -252,12 +344,13 @@ int fr_pipeline_run(FrPipeline* p, const uint8_t* frames, int stride, int batch,
                 }
                 if (live) ++k;
             }
-        (void)n;
+        if (k != n) throw CudaError{"pipeline: device face count disagrees with the per-frame counts"};
     });
 }
 
 /* getCroppedFaces + preprocessFaces + doInference for caller-provided boxes of ONE frame (ArcFaceIR50::forward,
- * src/arcface.cpp:166-187). crops_u8 (optional): n x 112 x 112 x 3 BGR = CroppedFace::face. Host buffers. */
+ * src/arcface.cpp:166-187). crops_u8 (optional): n x 112 x 112 x 3 BGR = CroppedFace::face. Host buffers. The frame and face-list
+ * device buffers belong to the embedder and are reused from call to call (the reference's forward runs once per video frame). */
 int fr_embedder_run_boxes(FrEmbedder* e, const uint8_t* frame, int frame_h, int frame_w, int stride, const FrBbox* boxes, int n, float* out512,
                           uint8_t* crops_u8) {
     return guarded([&] {
@@ -265,23 +358,21 @@ int fr_embedder_run_boxes(FrEmbedder* e, const uint8_t* frame, int frame_h, int 
         if (n < 1) throw ArgError{"no boxes"};
         if (frame_h < 1 || frame_w < 1 || stride < frame_w * 3) throw ArgError{"bad frame geometry"};
         DeviceGuard dg(embedder_device(e));
-        cudaStream_t st = nullptr;
-        FRB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        uint8_t* fdev = nullptr;
-        FaceRef* faces_dev = nullptr;
+        cudaStream_t st = embedder_stream(e);
+        FRB_CUDA(cudaStreamSynchronize(st));
+        uint8_t* fdev = embedder_frame_scratch(e, static_cast<size_t>(frame_h) * frame_w * 3);
+        FaceRef* faces_dev = static_cast<FaceRef*>(embedder_faces_scratch(e, sizeof(FaceRef) * std::max(n, 64)));
+        FRB_CUDA(cudaMemcpy2DAsync(fdev, static_cast<size_t>(frame_w) * 3, frame, stride, static_cast<size_t>(frame_w) * 3, frame_h,
+                                   cudaMemcpyHostToDevice, st));
+        std::vector<FaceRef> faces(n);
+        for (int i = 0; i < n; ++i) faces[i] = FaceRef{0, boxes[i].x1, boxes[i].y1, boxes[i].x2, boxes[i].y2};
+        FRB_CUDA(cudaMemcpyAsync(faces_dev, faces.data(), sizeof(FaceRef) * n, cudaMemcpyHostToDevice, st));
         try {
-            FRB_CUDA(cudaMalloc(&fdev, static_cast<size_t>(frame_h) * frame_w * 3));
-            FRB_CUDA(cudaMalloc(&faces_dev, sizeof(FaceRef) * n));
-            FRB_CUDA(cudaMemcpy2DAsync(fdev, static_cast<size_t>(frame_w) * 3, frame, stride, static_cast<size_t>(frame_w) * 3, frame_h,
-                                       cudaMemcpyHostToDevice, st));
-            std::vector<FaceRef> faces(n);
-            for (int i = 0; i < n; ++i) faces[i] = FaceRef{0, boxes[i].x1, boxes[i].y1, boxes[i].x2, boxes[i].y2};
-            FRB_CUDA(cudaMemcpyAsync(faces_dev, faces.data(), sizeof(FaceRef) * n, cudaMemcpyHostToDevice, st));
             const int mb = embedder_max_batch(e);
             for (int beg = 0; beg < n; beg += mb) {
                 const int m = std::min(mb, n - beg);
                 dim3 grid((112 * 112 + 255) / 256, m);
-                crop_resize_kernel<<<grid, 256, 0, st>>>(fdev, frame_h, frame_w, frame_w * 3, faces_dev + beg, nullptr, m, embedder_u8_input(e));
+                crop_resize_kernel<<<grid, 256, 0, st>>>(fdev, frame_h, frame_w, frame_w * 3, faces_dev + beg, nullptr, 0, m, embedder_u8_input(e));
                 count_launch();
                 if (crops_u8)
                     FRB_CUDA(cudaMemcpyAsync(crops_u8 + static_cast<size_t>(beg) * 112 * 112 * 3, embedder_u8_input(e),
@@ -291,15 +382,9 @@ int fr_embedder_run_boxes(FrEmbedder* e, const uint8_t* frame, int frame_h, int 
             }
             FRB_CUDA(cudaStreamSynchronize(st));
         } catch (...) {
-            cudaStreamSynchronize(st);
-            cudaFree(fdev);
-            cudaFree(faces_dev);
-            cudaStreamDestroy(st);
+            cudaStreamSynchronize(st);  // `faces` (pageable host memory) must outlive its copy
             throw;
         }
-        cudaFree(fdev);
-        cudaFree(faces_dev);
-        cudaStreamDestroy(st);
     });
 }
 

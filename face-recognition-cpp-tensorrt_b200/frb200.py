@@ -154,6 +154,14 @@ class Gallery:
             rows = rows[None, :]
         check(lib().fr_gallery_append(self._h, _ptr(rows), rows.shape[0]))
 
+    def update(self, first: int, rows) -> None:
+        """replace rows [first, first + n) in place (all resident copies follow)"""
+        rows = _f32(rows)
+        if rows.ndim == 1:
+            rows = rows[None, :]
+        lib().fr_gallery_update.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        check(lib().fr_gallery_update(self._h, first, _ptr(rows), rows.shape[0]))
+
     def remove(self, row: int) -> int:
         """deletes local row `row`; returns the index the row that now sits in its slot had before (the old last row)"""
         moved = C.c_int64()

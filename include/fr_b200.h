@@ -70,6 +70,8 @@ int fr_gallery_create_dev(const float *rows_dev, int64_t n, int dim, int device,
 int fr_gallery_create_synthetic(int64_t n, int dim, uint64_t seed, int device, int64_t row_offset, FrGallery **out);
 void fr_gallery_destroy(FrGallery *g);
 int64_t fr_gallery_rows(const FrGallery *g);
+/* CUDA device the gallery (shard) lives on */
+int fr_gallery_device(const FrGallery *g);
 /* copy rows [first, first+count) (f32) back to the host — test hook */
 int fr_gallery_read_rows(FrGallery *g, int64_t first, int64_t count, float *out_rows);
 
@@ -82,9 +84,11 @@ int fr_gallery_read_rows(FrGallery *g, int64_t first, int64_t count, float *out_
  *   append   add n rows (host f32, n x 512) after the last row; their local indices are [rows, rows + n)
  *   remove   delete local row `row` by moving the LAST row into its slot (*moved_from = index the moved row had, == row when the
  *            last row itself was deleted); the caller applies the same move to its row -> userId table (classNames)
+ *   update   replace rows [first, first + n) in place (re-enrolment of a known face: src/app.cpp:131-217 deletes and re-inserts)
  *   clear    drop all rows, keep the buffers (resetEmbeddings) */
 int fr_gallery_reserve(FrGallery *g, int64_t capacity);
 int fr_gallery_append(FrGallery *g, const float *rows, int64_t n);
+int fr_gallery_update(FrGallery *g, int64_t first, const float *rows, int64_t n);
 int fr_gallery_remove(FrGallery *g, int64_t row, int64_t *moved_from);
 int fr_gallery_clear(FrGallery *g);
 int64_t fr_gallery_capacity(const FrGallery *g);

@@ -539,6 +539,12 @@ def test_gallery_lifecycle_append_remove_clear(scan):
         model[row] = model[moved]
         model = model[:-1]
         check()
+    fresh = so.l2_normalise(rng.standard_normal((300, 512)))   # re-enrolment in place: rows 1000..1299 replaced
+    g.update(1000, fresh)
+    model[1000:1300] = fresh
+    check()
+    with pytest.raises(frb200.FrError):
+        g.update(len(model) - 5, fresh[:10])                   # range beyond the last row
     g.clear()
     assert g.rows == 0
     with pytest.raises(frb200.FrError) as e:
