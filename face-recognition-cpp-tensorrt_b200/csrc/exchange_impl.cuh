@@ -1,31 +1,29 @@
-// Cross-GPU exchange of per-shard search results over NVLink peer memory, fused with the final merge.
+// Cross-GPU exchange of per-shard search results over NVLink peer memory, fused with the search's re-rank on the sending side
+// and with the final merge on the receiving side.
 //
-// The reference has no multi-GPU code; this is the "one exchange step" of the gallery-sharded search. Instead of an NCCL
-// all-gather followed by a merge kernel, ONE kernel per rank (a) stores its nq x k (score, idx) results straight into every
-// peer's mailbox (remote st.global over NVLink / NVSwitch), (b) publishes a per-query flag, (c) waits for the peers' flags and
-// (d) merges all shards' candidates by (score desc, global row asc). Mailboxes are cudaMalloc'ed per rank and mapped into the
-// peers with CUDA IPC (one process per GPU); the 64-byte handles travel once, at setup, through any host channel
-// (torch.distributed in bench.py). No host synchronisation and no NCCL call in the step, so the whole search step is
-// CUDA-graph capturable.
+// The reference has no multi-GPU code; this is the "one exchange step" of the gallery-sharded search. Instead of an NCCL all-gather
+// followed by a merge kernel:
+//   push   the re-rank kernel of the search (append_rerank_kernel / topk_rerank_kernel; for queries recomputed by the exact scan, its
+//          merging block) stores each query's k (score, global row) results straight into EVERY peer's mailbox (remote st.global over
+//          NVLink / NVSwitch) the moment that query is finished, then publishes a per-query flag (st.release.sys). No extra launch.
+//   merge  one small kernel per rank waits for the peers' flags of each query (ld.acquire.sys), merges all shards' candidates by
+//          (score desc, global row asc) and writes the final result.
+// Mailboxes are cudaMalloc'ed per rank and mapped into the peers with CUDA IPC (one process per GPU); the 64-byte handles travel once,
+// at setup, through any host channel (torch.distributed in bench.py). No host synchronisation and no NCCL call in the step, so the
+// whole multi-GPU search step is CUDA-graph capturable.
 //
-// Mailbox layout on every rank:  entry[parity 2][world][nq_max][k_max] {f32 score, i32 pad, i64 idx}  +  flag[2][world][nq_max] u32.
-// A call with sequence number `epoch` uses parity = epoch & 1; a rank cannot be two calls ahead of a peer (its merge of call e+1
-// needs the peer's push of e+1, which is stream-ordered after the peer's merge of call e), so two parities suffice.
+// Mailbox layout on every rank:  entry[slot 4][world][nq_max][k_max] {f32 score, i32 pad, i64 idx}  +  flag[4][world][nq_max] u32.
+// Pushes and merges are numbered separately (device-resident counters, so a captured graph can be replayed): push number e uses slot
+// e & 3 and flag value e; merge number e waits for flag value e in slot e & 3. The host may run the merge of batch i AFTER the search
+// (and push) of batch i + 1 ("lag 1": the flag wait of batch i hides behind the scan of batch i + 1). With lag <= 1 a rank is at most
+// 3 pushes ahead of a peer's merge — push e follows the local merge e - 2, which needed the peer's push e - 2, which follows the peer's
+// merge e - 4 — so four slots never collide.
+// A peer that never arrives is reported, not trapped on: after FR_XCHG_TIMEOUT_MS (default 20 s, %globaltimer) the waiting block records
+// the failure in a status word the host can read (fr_exchange_status), substitutes (-inf, -1) for the missing shard and carries on.
 // (textually included at the end of gallery.cu: it shares that translation unit's kernels and helpers)
 #include <memory>
 
 namespace {
-
-struct __align__(16) XEntry {
-    float score;
-    int pad;
-    long long idx;
-};
-
-struct XPeers {
-    XEntry* entries[16];
-    unsigned int* flags[16];
-};
 
 __device__ __forceinline__ void st_flag_system(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -35,16 +33,33 @@ __device__ __forceinline__ unsigned int ld_flag_system(const unsigned int* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
-// The call sequence number lives in device memory so that a CUDA graph of the step can be replayed. Every block of a call reads
-// epoch_state[0] + 1 when it starts; the block that finishes last (ticket counter epoch_state[1]) stores the new value, i.e. after
-// every block of the call has read the old one and before the next call (stream order) starts.
+// Stand-alone push (results already in device memory): the unfused form, used by fr_exchange_merge_dev, by empty shards and by tests.
+// local_s == nullptr pushes (-inf, -1): a shard without rows still takes part in the protocol.
+__global__ void __launch_bounds__(64) exchange_push_kernel(XPush xp, int nq, int k, const float* __restrict__ local_s,
+                                                           const long long* __restrict__ local_i) {
+    __shared__ float s_s[kTopkMax];
+    __shared__ long long s_i[kTopkMax];
+    const int q = blockIdx.x;
+    const unsigned int epoch = xpush_epoch(xp, false);
+    if (threadIdx.x < k) {
+        s_s[threadIdx.x] = local_s ? local_s[static_cast<size_t>(q) * k + threadIdx.x] : -INFINITY;
+        s_i[threadIdx.x] = local_s ? local_i[static_cast<size_t>(q) * k + threadIdx.x] : -1;
+    }
+    __syncthreads();
+    xpush_query(xp, epoch, q, k, s_s, s_i);
+    xpush_finish(xp, epoch, gridDim.x);
+}
 
-// grid = nq blocks of 64 threads. local_s / local_i: this rank's nq x k results (global row ids).
-__global__ void __launch_bounds__(64) exchange_merge_kernel(XPeers peers, int world, int rank, int nq_max, int k_max, int nq, int k,
-                                                            unsigned int* epoch_state, const float* __restrict__ local_s,
-                                                            const long long* __restrict__ local_i, float* __restrict__ out_s,
-                                                            long long* __restrict__ out_i) {
+// grid = nq blocks of 64 threads: wait for every shard's entries of this query in MY mailbox, merge, write the result.
+__global__ void __launch_bounds__(64) exchange_wait_merge_kernel(XPeers peers, int world, int rank, int nq_max, int k_max, int k,
+                                                                 unsigned int* state, unsigned long long timeout_ns,
+                                                                 float* __restrict__ out_s, long long* __restrict__ out_i) {
     __shared__ float cs[16 * kTopkMax];
     __shared__ long long ci[16 * kTopkMax];
     __shared__ float sel_s[kTopkMax];
@@ -52,38 +67,34 @@ __global__ void __launch_bounds__(64) exchange_merge_kernel(XPeers peers, int wo
     __shared__ float red_s[32];
     __shared__ long long red_i[32];
     __shared__ int red_p[32];
+    __shared__ int arrived[16];
     const int q = blockIdx.x;
-    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(epoch_state) + 1u;
-    const int par = epoch & 1;
-    const size_t slot = ((static_cast<size_t>(par) * world + rank) * nq_max + q) * k_max;  // my slot in every mailbox
-    // (a) push: thread t -> (peer t / k, entry t % k)
-    for (int t = threadIdx.x; t < world * k; t += blockDim.x) {
-        const int peer = t / k, j = t % k;
-        XEntry e;
-        e.score = local_s[static_cast<size_t>(q) * k + j];
-        e.pad = 0;
-        e.idx = local_i[static_cast<size_t>(q) * k + j];
-        peers.entries[peer][slot + j] = e;
-    }
-    __threadfence_system();
-    __syncthreads();
-    // (b) publish
-    if (threadIdx.x < world)
-        st_flag_system(peers.flags[threadIdx.x] + (static_cast<size_t>(par) * world + rank) * nq_max + q, epoch);
-    // (c) wait for every shard's entry of this query in MY mailbox
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(state + 2) + 1u;
+    const int slot = epoch & 3;
     if (threadIdx.x < world) {
-        const unsigned int* f = peers.flags[rank] + (static_cast<size_t>(par) * world + threadIdx.x) * nq_max + q;
-        unsigned int spins = 0;
-        while (ld_flag_system(f) != epoch) {
-            if (++spins == (1u << 25)) __trap();  // a peer never arrived: fail loudly instead of hanging the GPU
+        const unsigned int* f = peers.flags[rank] + (static_cast<size_t>(slot) * world + threadIdx.x) * nq_max + q;
+        int ok = 1;
+        if (ld_flag_system(f) != epoch) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int probes = 0;
+            while (ld_flag_system(f) != epoch) {
+                if ((++probes & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+                    ok = 0;
+                    atomicMax(state + 4, 1u + static_cast<unsigned int>(threadIdx.x));  // status: 1 + the rank that never arrived
+                    break;
+                }
+            }
         }
+        arrived[threadIdx.x] = ok;
     }
     __syncthreads();
-    // (d) merge
     const int count = world * k;
     for (int t = threadIdx.x; t < count; t += blockDim.x) {
         const int r = t / k, j = t % k;
-        const XEntry e = peers.entries[rank][((static_cast<size_t>(par) * world + r) * nq_max + q) * k_max + j];
+        XEntry e;
+        e.score = -INFINITY;
+        e.idx = -1;
+        if (arrived[r]) e = peers.entries[rank][((static_cast<size_t>(slot) * world + r) * nq_max + q) * k_max + j];
         cs[t] = e.score;
         ci[t] = e.idx;
     }
@@ -93,9 +104,10 @@ __global__ void __launch_bounds__(64) exchange_merge_kernel(XPeers peers, int wo
         out_s[static_cast<size_t>(q) * k + threadIdx.x] = sel_s[threadIdx.x];
         out_i[static_cast<size_t>(q) * k + threadIdx.x] = sel_i[threadIdx.x];
     }
-    if (threadIdx.x == 0 && atomicAdd(epoch_state + 1, 1u) == gridDim.x - 1) {
-        epoch_state[1] = 0u;
-        epoch_state[0] = epoch;
+    if (threadIdx.x == 0 && atomicAdd(state + 3, 1u) == gridDim.x - 1) {
+        state[3] = 0u;
+        __threadfence();
+        state[2] = epoch;
     }
 }
 
@@ -107,9 +119,33 @@ struct FrExchange {
     size_t entry_bytes = 0, flag_bytes = 0;
     XPeers peers{};
     std::vector<void*> opened;
-    unsigned int* epoch_dev = nullptr;
+    unsigned int* state_dev = nullptr;  // [0] pushes completed [1] push ticket [2] merges completed [3] merge ticket [4] status
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
     bool connected = false;
 };
+
+namespace {
+XPush make_push(const FrExchange* x) {
+    XPush p{};
+    p.peers = x->peers;
+    p.world = x->world;
+    p.rank = x->rank;
+    p.nq_max = x->nq_max;
+    p.k_max = x->k_max;
+    p.state = x->state_dev;
+    return p;
+}
+void check_step(const FrExchange* x, int nq, int k) {
+    if (!x) throw ArgError{"null exchange"};
+    if (!x->connected) throw StateError{"exchange not connected"};
+    if (nq < 1 || nq > x->nq_max || k < 1 || k > x->k_max) throw ArgError{"nq/k exceed the exchange's capacity"};
+}
+void launch_wait_merge(FrExchange* x, int nq, int k, float* scores_dev, long long* idx_dev, cudaStream_t st) {
+    exchange_wait_merge_kernel<<<nq, 64, 0, st>>>(x->peers, x->world, x->rank, x->nq_max, x->k_max, k, x->state_dev, x->timeout_ns, scores_dev, idx_dev);
+    count_launch();
+    FRB_CUDA(cudaGetLastError());
+}
+}  // namespace
 
 extern "C" {
 
@@ -125,12 +161,13 @@ int fr_exchange_create(int device, int world, int rank, int nq_max, int k_max, F
         x->rank = rank;
         x->nq_max = nq_max;
         x->k_max = k_max;
-        x->entry_bytes = sizeof(XEntry) * 2 * world * nq_max * k_max;
-        x->flag_bytes = sizeof(unsigned int) * 2 * world * nq_max;
+        x->entry_bytes = sizeof(XEntry) * 4 * world * nq_max * k_max;
+        x->flag_bytes = sizeof(unsigned int) * 4 * world * nq_max;
+        if (const char* e = std::getenv("FR_XCHG_TIMEOUT_MS")) x->timeout_ns = std::strtoull(e, nullptr, 10) * 1000000ull;
         FRB_CUDA(cudaMalloc(&x->base, x->entry_bytes + x->flag_bytes));
         FRB_CUDA(cudaMemset(x->base, 0, x->entry_bytes + x->flag_bytes));
-        FRB_CUDA(cudaMalloc(&x->epoch_dev, 2 * sizeof(unsigned int)));  // [0] calls completed, [1] finished-block ticket of the running call
-        FRB_CUDA(cudaMemset(x->epoch_dev, 0, 2 * sizeof(unsigned int)));
+        FRB_CUDA(cudaMalloc(&x->state_dev, 8 * sizeof(unsigned int)));
+        FRB_CUDA(cudaMemset(x->state_dev, 0, 8 * sizeof(unsigned int)));
         FRB_CUDA(cudaDeviceSynchronize());
         *out = x.release();
     });
@@ -180,28 +217,9 @@ void fr_exchange_destroy(FrExchange* x) {
     cudaDeviceSynchronize();
     for (void* p : x->opened) cudaIpcCloseMemHandle(p);
     cudaFree(x->base);
-    cudaFree(x->epoch_dev);
+    cudaFree(x->state_dev);
     if (prev >= 0) cudaSetDevice(prev);
     delete x;
-}
-
-/* The exchange step: every rank calls it once per search with its own nq x k results (device, global row ids, as written by
- * fr_gallery_topk_dev); on return (stream order) scores_dev / idx_dev hold the merged global top-k on every rank.
- * All ranks must issue the same sequence of calls. Does not synchronise the host. */
-int fr_exchange_merge_dev(FrExchange* x, const float* local_scores_dev, const int64_t* local_idx_dev, int nq, int k, float* scores_dev,
-                          int64_t* idx_dev, void* stream) {
-    return guarded([&] {
-        if (!x || !local_scores_dev || !local_idx_dev || !scores_dev || !idx_dev) throw ArgError{"null argument"};
-        if (!x->connected) throw StateError{"exchange not connected"};
-        if (nq < 1 || nq > x->nq_max || k < 1 || k > x->k_max) throw ArgError{"nq/k exceed the exchange's capacity"};
-        DeviceGuard dg(x->device);
-        exchange_merge_kernel<<<nq, 64, 0, static_cast<cudaStream_t>(stream)>>>(x->peers, x->world, x->rank, x->nq_max, x->k_max, nq, k, x->epoch_dev,
-                                                                               local_scores_dev,
-                                                                               reinterpret_cast<const long long*>(local_idx_dev), scores_dev,
-                                                                               reinterpret_cast<long long*>(idx_dev));
-        count_launch();
-        FRB_CUDA(cudaGetLastError());
-    });
 }
 
 /* Same-process variant of fr_exchange_connect (single-process multi-GPU hosts such as the reference's app, and tests): `all` holds
@@ -226,6 +244,110 @@ int fr_exchange_connect_local(FrExchange* x, FrExchange* const* all) {
             x->peers.flags[r] = reinterpret_cast<unsigned int*>(static_cast<char*>(all[r]->base) + all[r]->entry_bytes);
         }
         x->connected = true;
+    });
+}
+
+/* Search + push, fused: fr_gallery_topk_dev whose re-rank kernel also delivers each query's results to every peer's mailbox. The
+ * local results still land in local_scores_dev / local_idx_dev. A shard without rows pushes (-inf, -1) (it must still take part). */
+int fr_gallery_topk_push_dev(FrGallery* g, FrExchange* x, const float* q_dev, int nq, int k, float* local_scores_dev, int64_t* local_idx_dev,
+                             void* stream) {
+    return guarded([&] {
+        if (!g) throw ArgError{"null gallery"};
+        check_step(x, nq, k);
+        if (nq > kChunkQ) throw ArgError{"the exchange step takes one chunk of <= 256 queries"};
+        if (!q_dev || !local_scores_dev || !local_idx_dev) throw ArgError{"null argument"};
+        if (g->device != x->device) throw ArgError{"gallery shard and exchange live on different devices"};
+        DeviceGuard dg(g->device);
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g->stream;
+        if (g->n == 0) {
+            exchange_push_kernel<<<nq, 64, 0, st>>>(make_push(x), nq, k, nullptr, nullptr);
+            count_launch();
+            FRB_CUDA(cudaGetLastError());
+            return;
+        }
+        g->first_chunk = true;
+        if (g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows)) {
+            // exact fp32 scan (tiny shards, FR_PATH_EXACT): no re-rank kernel to fuse with; deliver with the stand-alone push
+            topk_chunk(g, q_dev, nq, k, local_scores_dev, reinterpret_cast<long long*>(local_idx_dev), st);
+            exchange_push_kernel<<<nq, 64, 0, st>>>(make_push(x), nq, k, local_scores_dev, reinterpret_cast<const long long*>(local_idx_dev));
+            count_launch();
+            FRB_CUDA(cudaGetLastError());
+            return;
+        }
+        g->push = make_push(x);
+        g->push.enabled = 1;
+        try {
+            topk_chunk(g, q_dev, nq, k, local_scores_dev, reinterpret_cast<long long*>(local_idx_dev), st);
+        } catch (...) {
+            g->push.enabled = 0;
+            throw;
+        }
+        g->push.enabled = 0;
+    });
+}
+
+/* The receiving half: wait for every shard's push of the oldest unmerged batch, merge, write nq x k results (global row ids). */
+int fr_exchange_wait_merge_dev(FrExchange* x, int nq, int k, float* scores_dev, int64_t* idx_dev, void* stream) {
+    return guarded([&] {
+        check_step(x, nq, k);
+        if (!scores_dev || !idx_dev) throw ArgError{"null output"};
+        DeviceGuard dg(x->device);
+        launch_wait_merge(x, nq, k, scores_dev, reinterpret_cast<long long*>(idx_dev), static_cast<cudaStream_t>(stream));
+    });
+}
+
+/* Unfused form (results of an earlier fr_gallery_topk_dev already in device memory): push + wait + merge, two small launches.
+ * local_scores_dev == NULL: this rank has nothing (empty shard) and pushes (-inf, -1). All ranks must issue the same sequence of calls. */
+int fr_exchange_merge_dev(FrExchange* x, const float* local_scores_dev, const int64_t* local_idx_dev, int nq, int k, float* scores_dev,
+                          int64_t* idx_dev, void* stream) {
+    return guarded([&] {
+        check_step(x, nq, k);
+        if (!scores_dev || !idx_dev || (local_scores_dev && !local_idx_dev)) throw ArgError{"null argument"};
+        DeviceGuard dg(x->device);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        exchange_push_kernel<<<nq, 64, 0, st>>>(make_push(x), nq, k, local_scores_dev, reinterpret_cast<const long long*>(local_idx_dev));
+        count_launch();
+        launch_wait_merge(x, nq, k, scores_dev, reinterpret_cast<long long*>(idx_dev), st);
+    });
+}
+
+/* 0 = every wait so far was satisfied; r + 1 = a block gave up waiting for rank r (results then lack that shard). Synchronises the device. */
+int fr_exchange_status(FrExchange* x, int* out) {
+    return guarded([&] {
+        if (!x || !out) throw ArgError{"null argument"};
+        DeviceGuard dg(x->device);
+        FRB_CUDA(cudaDeviceSynchronize());
+        unsigned int v = 0;
+        FRB_CUDA(cudaMemcpy(&v, x->state_dev + 4, sizeof(v), cudaMemcpyDeviceToHost));
+        *out = static_cast<int>(v);
+    });
+}
+
+/* The public host-buffer search call of a (possibly sharded) gallery — what each rank's host code calls per query batch:
+ * queries from host memory -> this shard's fused search (+ push) -> cross-GPU merge -> results to host memory, synchronised.
+ * x == NULL: single shard (= fr_gallery_topk with an explicit stream). stream: cudaStream_t as void*, NULL = the gallery's own. */
+int fr_search_topk(FrGallery* g, FrExchange* x, const float* q, int nq, int k, float* scores, int64_t* idx, void* stream) {
+    return guarded([&] {
+        if (!g || !q || !scores || !idx) throw ArgError{"null argument"};
+        if (nq < 1 || nq > kChunkQ) throw ArgError{"1..256 queries per call"};
+        if (k < 1 || k > FR_TOPK_MAX) throw ArgError{"k out of range"};
+        if (!x && g->n == 0) throw StateError{"Feature matching: No faces in database or no faces found"};
+        DeviceGuard dg(g->device);
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g->stream;
+        FRB_CUDA(cudaMemcpyAsync(g->q_dev, q, sizeof(float) * nq * kDim, cudaMemcpyHostToDevice, st));
+        float* fs = g->res_s;
+        long long* fi = g->res_i;
+        if (x) {
+            const int rc = fr_gallery_topk_push_dev(g, x, g->q_dev, nq, k, g->loc_s, reinterpret_cast<int64_t*>(g->loc_i), st);
+            if (rc != FR_OK) throw CudaError{std::string("sharded search failed: ") + fr_last_error()};
+            launch_wait_merge(x, nq, k, fs, fi, st);
+        } else {
+            g->first_chunk = true;
+            topk_chunk(g, g->q_dev, nq, k, fs, fi, st);
+        }
+        FRB_CUDA(cudaMemcpyAsync(scores, fs, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, st));
+        FRB_CUDA(cudaMemcpyAsync(idx, fi, sizeof(long long) * nq * k, cudaMemcpyDeviceToHost, st));
+        FRB_CUDA(cudaStreamSynchronize(st));
     });
 }
 

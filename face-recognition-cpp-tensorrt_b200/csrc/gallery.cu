@@ -52,6 +52,9 @@ struct FrGallery {
     long long* part_i = nullptr;
     float* res_s = nullptr;          // 256 x FR_TOPK_MAX
     long long* res_i = nullptr;
+    float* loc_s = nullptr;          // this shard's results inside fr_search_topk (sharded), 256 x FR_TOPK_MAX
+    long long* loc_i = nullptr;
+    XPush push{};                    // enabled only inside fr_gallery_topk_push_dev: the re-rank kernels then also deliver to the peers
     float* sims_ws = nullptr;        // dense-path workspace
     size_t sims_ws_floats = 0;
     int path = FR_PATH_AUTO;
@@ -90,6 +93,8 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMalloc(&g->part_i, sizeof(long long) * kChunkQ * kScanSlicesMax * kTopkMax));
     FRB_CUDA(cudaMalloc(&g->res_s, sizeof(float) * kChunkQ * FR_TOPK_MAX));
     FRB_CUDA(cudaMalloc(&g->res_i, sizeof(long long) * kChunkQ * FR_TOPK_MAX));
+    FRB_CUDA(cudaMalloc(&g->loc_s, sizeof(float) * kChunkQ * FR_TOPK_MAX));
+    FRB_CUDA(cudaMalloc(&g->loc_i, sizeof(long long) * kChunkQ * FR_TOPK_MAX));
     FRB_CUDA(cudaMalloc(&g->gmax, sizeof(float)));
     FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
     FRB_CUDA(cudaMalloc(&g->g4max, sizeof(float)));
@@ -247,7 +252,8 @@ void launch_exact(FrGallery* g, const float* q_dev, int nq, int k, const int* fl
     // flagged-query fix-up: one pass of blocks that loop over the (normally empty) list; exact path: spread the queries too
     const int qsplit = flags ? 1 : std::min(nq, 64);
     exact_scan_kernel<<<dim3(slices, qsplit), kScanThreads, 0, st>>>(g->rows_f32, g->n, q_dev, nq, flags, g->part_s, g->part_i, k, g->row_offset,
-                                                                     scores_dev, idx_dev, g->scan_ticket, flags ? g->flagged_acc : nullptr);
+                                                                     scores_dev, idx_dev, g->scan_ticket, flags ? g->flagged_acc : nullptr,
+                                                                     flags ? g->push : XPush{});
     count_launch();
     if (!flags) {  // all queries: the merge is spread over its own grid; the fix-up's last block merges in the same launch
         exact_merge_kernel<<<std::min(nq, 148), kSelThreads, 0, st>>>(g->part_s, g->part_i, slices, nq, flags, k, g->row_offset, scores_dev, idx_dev);
@@ -306,11 +312,11 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     if (app)
         append_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->app_buf, g->app_cnt, units * 2, cg * kQRows, q_dev, g->rows_f32, g->q_margin,
                                                          g->q_gap, f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, g->row_offset, scores_dev, idx_dev, g->flags,
-                                                         g->gbest);
+                                                         g->gbest, g->push);
     else
         topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->q_margin,
                                                        g->q_gap, f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, k, g->row_offset, scores_dev, idx_dev, g->flags,
-                                                       g->gbest);
+                                                       g->gbest, g->push);
     count_launch();
     FRB_CUDA(cudaGetLastError());
     // queries whose candidate set may be incomplete (flagged by the re-rank) are recomputed exactly; no-op otherwise
@@ -431,6 +437,8 @@ void fr_gallery_destroy(FrGallery* g) {
     cudaFree(g->part_i);
     cudaFree(g->res_s);
     cudaFree(g->res_i);
+    cudaFree(g->loc_s);
+    cudaFree(g->loc_i);
     cudaFree(g->sims_ws);
     for (auto& e : g->ev_pool) {
         cudaEventDestroy(e.first);

@@ -113,6 +113,56 @@ struct ListCfg {
     static constexpr int kKC = KSEL == 1 ? 8 : 16;
 };
 
+// ---- cross-GPU push of finished results (csrc/exchange_impl.cuh has the protocol): mailboxes of every rank, mapped into this one
+struct __align__(16) XEntry {
+    float score;
+    int pad;
+    long long idx;
+};
+struct XPeers {
+    XEntry* entries[16];
+    unsigned int* flags[16];
+};
+struct XPush {
+    XPeers peers;
+    int world, rank, nq_max, k_max;
+    unsigned int* state;  // [0] pushes completed, [1] finished-block ticket of the running push
+    int enabled;
+};
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// number of the push this kernel performs = pushes completed + 1, read when the block starts (no block of the call can have
+// finished the call yet). after_advance: an earlier kernel of the same search already advanced the counter (exact-scan fix-up).
+__device__ __forceinline__ unsigned int xpush_epoch(const XPush& xp, bool after_advance) {
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(xp.state);
+    return after_advance ? e : e + 1u;
+}
+// Every thread of the block calls. s_s / s_i: the query's k results (global rows) in shared memory, visible to the block.
+__device__ __forceinline__ void xpush_query(const XPush& xp, unsigned int epoch, int q, int k, const float* s_s, const long long* s_i) {
+    const int slot = epoch & 3;
+    const size_t lane_base = (static_cast<size_t>(slot) * xp.world + xp.rank) * xp.nq_max + q;
+    for (int t = threadIdx.x; t < xp.world * k; t += blockDim.x) {
+        const int peer = t / k, j = t % k;
+        XEntry e;
+        e.score = s_s[j];
+        e.pad = 0;
+        e.idx = s_i[j];
+        xp.peers.entries[peer][lane_base * xp.k_max + j] = e;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < xp.world) st_release_sys(xp.peers.flags[threadIdx.x] + lane_base, epoch);
+}
+// Once per block, at its end: the block that finishes last advances the push counter (after every block has read the old value).
+__device__ __forceinline__ void xpush_finish(const XPush& xp, unsigned int epoch, unsigned int blocks) {
+    if (threadIdx.x == 0 && atomicAdd(xp.state + 1, 1u) == blocks - 1) {
+        xp.state[1] = 0u;
+        __threadfence();
+        xp.state[0] = epoch;
+    }
+}
+
 __device__ __forceinline__ bool better(float sa, long long ia, float sb, long long ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
@@ -389,7 +439,8 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     if (gb > 0.f) thr = fmaxf(thr, gb * kRaw - margin);
                 }
             }
-            app_cnt[list] = live ? cnt : 0;
+            // [query][list] so that the re-rank reads one query's counts contiguously
+            app_cnt[static_cast<size_t>(qrow) * (2 * num_units) + unit * 2 + half] = live ? cnt : 0;
         } else {
         float best_s[KC];
         int best_i[KC];
@@ -581,8 +632,10 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
                                                                   const float* __restrict__ rows, const float* __restrict__ q_margin,
                                                                   const float* __restrict__ q_gap, float inv_raw, int k, long long row_offset,
                                                                   float* __restrict__ out_s, long long* __restrict__ out_i,
-                                                                  int* __restrict__ flag_list, int* __restrict__ gbest) {
+                                                                  int* __restrict__ flag_list, int* __restrict__ gbest, const XPush push) {
     __shared__ float cs[kHeadMax];
+    __shared__ long long x_i[kTopkMax];
+    const unsigned int push_epoch = push.enabled ? xpush_epoch(push, false) : 0u;
     __shared__ long long ci[kHeadMax];
     __shared__ float sel_s[kTopkMax];
     __shared__ long long sel_i[kTopkMax];
@@ -649,6 +702,12 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
     if (threadIdx.x == 0 && sel_s[k - 1] < ck - __ldg(q_gap + qi)) overflow = 1;
     if (threadIdx.x == 0 && overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
     if (threadIdx.x == 0) gbest[qi] = 0;  // ready for the next search (0 = nothing published)
+    if (push.enabled) {  // deliver this query to every peer now, unless the exact scan is going to recompute (and deliver) it
+        if (threadIdx.x < k) x_i[threadIdx.x] = sel_i[threadIdx.x] >= 0 ? sel_i[threadIdx.x] + row_offset : -1;
+        __syncthreads();
+        if (!overflow) xpush_query(push, push_epoch, qi, k, sel_s, x_i);
+        xpush_finish(push, push_epoch, gridDim.x);
+    }
 }
 
 // Re-rank for the append epilogue (top-1). One block per query: the best coarse score (the scan's shared per-query best, or a pass
@@ -661,8 +720,11 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
                                                                     const float* __restrict__ rows, const float* __restrict__ q_margin,
                                                                     const float* __restrict__ q_gap, float inv_raw, long long row_offset,
                                                                     float* __restrict__ out_s, long long* __restrict__ out_i,
-                                                                    int* __restrict__ flag_list, int* __restrict__ gbest) {
+                                                                    int* __restrict__ flag_list, int* __restrict__ gbest, const XPush push) {
     constexpr int kListsMax = 2 * 148;
+    __shared__ float x_s[1];
+    __shared__ long long x_i[1];
+    const unsigned int push_epoch = push.enabled ? xpush_epoch(push, false) : 0u;
     __shared__ float rs[kAppRescoreMax];
     __shared__ int ri[kAppRescoreMax];
     __shared__ int s_off[kListsMax + 1];  // exclusive prefix sums of the (clamped) counts
@@ -685,7 +747,7 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
         const int l = l0 + threadIdx.x;
         int c = 0;
         if (l < lists) {
-            c = app_cnt[static_cast<size_t>(l) * q_stride + qi];
+            c = app_cnt[static_cast<size_t>(qi) * lists + l];  // [query][list]: one contiguous read per query
             if (c > kAppCap) {
                 overflow = 1;
                 c = kAppCap;
@@ -791,6 +853,13 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
         if (bi >= 0 && bs < ck - __ldg(q_gap + qi)) overflow = 1;
         if (overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
         gbest[qi] = 0;  // ready for the next search
+        x_s[0] = bi >= 0 ? bs : -INFINITY;
+        x_i[0] = bi >= 0 ? bi + row_offset : -1;
+    }
+    if (push.enabled) {  // deliver this query to every peer now, unless the exact scan is going to recompute (and deliver) it
+        __syncthreads();
+        if (!overflow) xpush_query(push, push_epoch, qi, 1, x_s, x_i);
+        xpush_finish(push, push_epoch, gridDim.x);
     }
 }
 
@@ -805,7 +874,7 @@ __global__ void __launch_bounds__(kScanThreads) exact_scan_kernel(const float* _
                                                                   int nq, const int* __restrict__ flag_list, float* part_s, long long* part_i,
                                                                   int k, long long row_offset, float* __restrict__ out_s,
                                                                   long long* __restrict__ out_i, unsigned int* __restrict__ ticket,
-                                                                  int* __restrict__ flagged_acc) {
+                                                                  int* __restrict__ flagged_acc, const XPush push) {
     const int total = flag_list ? flag_list[0] : nq;
     if (total == 0) return;
     if (flagged_acc && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(flagged_acc, total);
@@ -883,7 +952,11 @@ __global__ void __launch_bounds__(kScanThreads) exact_scan_kernel(const float* _
             const long long id = msel_i[threadIdx.x];
             out_s[static_cast<size_t>(qi) * k + threadIdx.x] = msel_s[threadIdx.x];
             out_i[static_cast<size_t>(qi) * k + threadIdx.x] = id >= 0 ? id + row_offset : -1;
+            msel_i[threadIdx.x] = id >= 0 ? id + row_offset : -1;
         }
+        __syncthreads();
+        // the re-rank kernel skipped this query's push (and already advanced the push counter): deliver the recomputed result
+        if (push.enabled) xpush_query(push, xpush_epoch(push, true), qi, k, msel_s, msel_i);
         __syncthreads();
     }
 }

@@ -238,6 +238,17 @@ class Gallery:
         return st
 
 
+def search_topk(gal: "Gallery", exchange, q, k: int = 1, scores_out=None, idx_out=None, stream: int = 0):
+    """fr_search_topk: host queries in, host results out, through this shard's fused search and (exchange != None) the cross-GPU merge"""
+    L = lib()
+    L.fr_search_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    nq = q.shape[0]
+    scores = scores_out if scores_out is not None else np.empty((nq, k), np.float32)
+    idx = idx_out if idx_out is not None else np.empty((nq, k), np.int64)
+    check(L.fr_search_topk(gal._h, exchange._h if exchange is not None else None, _ptr(q), nq, k, _ptr(scores), _ptr(idx), C.c_void_p(stream)))
+    return scores, idx
+
+
 def topk_merge_dev(scores_parts_t, idx_parts_t, n_parts: int, nq: int, k: int, scores_t, idx_t, device: int, stream: int = 0) -> None:
     check(lib().fr_topk_merge_dev(_ptr(scores_parts_t), _ptr(idx_parts_t), n_parts, nq, k, _ptr(scores_t), _ptr(idx_t), device,
                                   C.c_void_p(stream)))
@@ -471,6 +482,9 @@ class Exchange:
         L.fr_exchange_merge_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.fr_exchange_destroy.restype = None
         L.fr_exchange_destroy.argtypes = [C.c_void_p]
+        L.fr_gallery_topk_push_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fr_exchange_wait_merge_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fr_exchange_status.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         h = C.c_void_p()
         check(L.fr_exchange_create(device, world, rank, nq_max, k_max, C.byref(h)))
         self._h, self.device, self.world, self.rank = h, device, world, rank
@@ -490,9 +504,25 @@ class Exchange:
         check(lib().fr_exchange_connect_local(self._h, arr))
 
     def merge_dev(self, local_scores_t, local_idx_t, scores_t, idx_t, stream: int) -> None:
-        nq, k = local_scores_t.shape
+        """unfused: stand-alone push of results already on the device + wait/merge (local_scores_t None = empty shard)"""
+        nq, k = scores_t.shape
         check(lib().fr_exchange_merge_dev(self._h, _ptr(local_scores_t), _ptr(local_idx_t), nq, k, _ptr(scores_t), _ptr(idx_t),
                                           C.c_void_p(stream)))
+
+    def topk_push_dev(self, gal: "Gallery", q_t, k: int, local_scores_t, local_idx_t, stream: int) -> None:
+        """this shard's search with the push to the peers fused into its re-rank kernel"""
+        check(lib().fr_gallery_topk_push_dev(gal._h, self._h, _ptr(q_t), q_t.shape[0], k, _ptr(local_scores_t), _ptr(local_idx_t),
+                                             C.c_void_p(stream)))
+
+    def wait_merge_dev(self, scores_t, idx_t, stream: int) -> None:
+        """wait for every shard's push of the oldest unmerged batch, merge into scores_t / idx_t (nq x k)"""
+        nq, k = scores_t.shape
+        check(lib().fr_exchange_wait_merge_dev(self._h, nq, k, _ptr(scores_t), _ptr(idx_t), C.c_void_p(stream)))
+
+    def status(self) -> int:
+        v = C.c_int()
+        check(lib().fr_exchange_status(self._h, C.byref(v)))
+        return v.value
 
     def close(self) -> None:
         if self._h:

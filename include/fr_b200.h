@@ -142,11 +142,18 @@ int fr_gallery_set_scan(FrGallery *g, int scan);
  * last k > 1 search, [296 lists][256][16] coarse scores f32 / local rows i32. Waits for the gallery's stream. */
 int fr_gallery_debug_read(FrGallery *g, int what, int64_t first, int64_t count, void *out);
 
-/* Fused exchange + merge over NVLink peer memory (replaces "all-gather, then fr_topk_merge_dev"): one kernel per rank stores its
- * nq x k results into every peer's mailbox, publishes per-query flags, waits for the peers and merges. One FrExchange per rank
- * (GPU). Setup: create on every rank, all-gather the fr_exchange_handle_bytes()-byte handles through any host channel, connect.
- * Step: fr_exchange_merge_dev right after fr_gallery_topk_dev, on the same stream; all ranks must issue the same sequence of
- * calls. No host synchronisation, no NCCL: the search step is CUDA-graph capturable. */
+/* Cross-GPU exchange of per-shard results over NVLink peer memory, fused into the search (csrc/exchange_impl.cuh; replaces
+ * "NCCL all-gather, then fr_topk_merge_dev"). One FrExchange per rank (GPU). Setup: create on every rank, all-gather the
+ * fr_exchange_handle_bytes()-byte handles through any host channel, connect. Step, per query batch (<= 256 queries), on one stream:
+ *   fr_gallery_topk_push_dev    this shard's search; its re-rank kernel also stores every finished query's results into all peers'
+ *                               mailboxes and publishes a flag (no extra launch; an empty shard pushes (-inf, -1))
+ *   fr_exchange_wait_merge_dev  waits for all shards' pushes of the OLDEST unmerged batch, merges by (score desc, global row asc)
+ * All ranks issue the same sequence of calls. The merge of batch i may be issued after the search of batch i + 1 (at most one batch of
+ * lag: four mailbox slots), which hides the wait for the slowest GPU behind the next scan. No host synchronisation, no NCCL: the
+ * step is CUDA-graph capturable. A peer that never arrives is not trapped on: after FR_XCHG_TIMEOUT_MS (default 20000) the merge
+ * substitutes (-inf, -1) for that shard and fr_exchange_status reports it.
+ * fr_exchange_merge_dev is the unfused form for results already in device memory (stand-alone push kernel + wait/merge kernel);
+ * local_scores_dev == NULL pushes (-inf, -1). */
 typedef struct FrExchange FrExchange;
 int fr_exchange_create(int device, int world, int rank, int nq_max, int k_max, FrExchange **out);
 int fr_exchange_handle_bytes(void);
@@ -155,9 +162,19 @@ int fr_exchange_local_handle(FrExchange *x, void *out_handle);
 int fr_exchange_connect(FrExchange *x, const void *all_handles);
 /* same-process groups (single-process multi-GPU hosts, tests): all = the world exchange objects, rank-major */
 int fr_exchange_connect_local(FrExchange *x, FrExchange *const *all);
+int fr_gallery_topk_push_dev(FrGallery *g, FrExchange *x, const float *q_dev, int nq, int k, float *local_scores_dev,
+                             int64_t *local_idx_dev, void *stream);
+int fr_exchange_wait_merge_dev(FrExchange *x, int nq, int k, float *scores_dev, int64_t *idx_dev, void *stream);
 int fr_exchange_merge_dev(FrExchange *x, const float *local_scores_dev, const int64_t *local_idx_dev, int nq, int k, float *scores_dev,
                           int64_t *idx_dev, void *stream);
+/* 0 = every wait so far was satisfied; r + 1 = a merge gave up waiting for rank r. Synchronises the device. */
+int fr_exchange_status(FrExchange *x, int *out);
 void fr_exchange_destroy(FrExchange *x);
+/* The public host-buffer search call of a (possibly sharded) gallery — what each rank's host code calls per batch of <= 256 queries:
+ * host queries -> H2D -> this shard's fused search (+ push) -> cross-GPU merge -> D2H of nq x k (score, global row) -> synchronise.
+ * x == NULL: single shard (featureMatching + getOutputs, src/arcface.cpp:189-217). stream: cudaStream_t as void*, NULL = the
+ * gallery's own stream. With x != NULL every rank must call it with the same queries. */
+int fr_search_topk(FrGallery *g, FrExchange *x, const float *q, int nq, int k, float *scores, int64_t *idx, void *stream);
 
 /* roofline bookkeeping for bench.py: algorithmic bytes/flops of the dominant kernel of the last topk call */
 typedef struct FrSearchStats {

@@ -231,8 +231,8 @@ def test_near_tie_cluster_inside_fp16_margin(cluster, k):
 
 @pytest.mark.parametrize("world", [1, 2, 4])
 def test_fused_exchange_merge_protocol(world):
-    # the peer-memory exchange (csrc/exchange.cu) with `world` shard "ranks" sharing this GPU, one stream per rank: every rank must
-    # end up with the single-gallery result; repeated calls exercise the two-parity mailbox and the device-resident epoch
+    # the peer-memory exchange (csrc/exchange_impl.cuh, unfused form) with `world` shard "ranks" sharing this GPU, one stream per rank:
+    # every rank must end up with the single-gallery result; repeated calls exercise the four-slot mailbox and the device-resident counters
     import torch
 
     rng = np.random.default_rng(world)
@@ -277,6 +277,112 @@ def test_fused_exchange_merge_protocol(world):
             assert np.array_equal(os_.cpu().numpy().view(np.uint32), fs.view(np.uint32))
         assert fi[0, 0] == 17 and fi[0, 1] == n - 5
     for o in shards + [full] + group:
+        o.close()
+
+
+@pytest.mark.parametrize("world,k,scan,lag", [(1, 1, 0, 0), (2, 1, 0, 1), (4, 1, 1, 1), (3, 4, 0, 1), (4, 2, 1, 0)])
+def test_search_with_fused_push_and_lagged_merge(world, k, scan, lag):
+    # fr_gallery_topk_push_dev (re-rank kernel delivers to the peers) + fr_exchange_wait_merge_dev, `world` shard ranks sharing this
+    # GPU (one stream each). lag = 1: the merge of batch i is issued after the search of batch i + 1 (the throughput mode of bench.py);
+    # batches alternate between different query sets so that a result delivered for the wrong batch would be caught. One shard is
+    # EMPTY when world >= 3 (it still has to take part), one query per batch is forced through the exact-scan fix-up (all rows of a
+    # cluster inside the margin), whose merging block must deliver it.
+    import torch
+
+    rng = np.random.default_rng(100 + world + k)
+    n, nq = 50_000, 256
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    G[n - 5] = G[17]
+    base = G[4000].copy()
+    G[20_000:26_000] = so.l2_normalise(base[None, :] + 1e-4 * rng.standard_normal((6000, 512)).astype(np.float32) / np.sqrt(512))
+    cuts = np.linspace(0, n, world + 1).astype(int)
+    if world >= 3:
+        cuts[2] = cuts[1]                      # rank 1 holds no rows
+    shards = [frb200.Gallery.from_rows(G[a:b], row_offset=int(a)) for a, b in zip(cuts[:-1], cuts[1:])]
+    for sh in shards:
+        sh.set_path(frb200.FR_PATH_TENSOR)
+        if sh.rows:
+            sh.set_scan(scan)
+    group = [frb200.Exchange(0, world, r, nq_max=256, k_max=8) for r in range(world)]
+    for x in group:
+        x.connect_local(group)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    batches, want = [], []
+    for b in range(6):
+        planted = rng.integers(0, n, nq)
+        planted[0] = 17
+        q = so.planted_queries(G[planted], 0.6, b)
+        q[0] = G[17]
+        q[1] = base                              # thousands of rows inside the margin: exact-scan fix-up on the shard that holds them
+        batches.append(torch.from_numpy(q).cuda())
+        want.append(so.topk(so.sims(G, q), k))
+    loc = [(torch.empty((nq, k), dtype=torch.float32, device="cuda"), torch.empty((nq, k), dtype=torch.int64, device="cuda")) for _ in range(world)]
+    out = [(torch.empty((nq, k), dtype=torch.float32, device="cuda"), torch.empty((nq, k), dtype=torch.int64, device="cuda")) for _ in range(world)]
+
+    def check(b):
+        torch.cuda.synchronize()
+        ws, wi = want[b]
+        for os_, oi in out:
+            gi = oi.cpu().numpy()
+            gs = os_.cpu().numpy()
+            assert np.abs(gs - ws).max() <= SCORE_TOL
+            bad = np.argwhere(gi != wi)
+            for qi, j in bad:   # only fp32-level ties between distinct rows may differ
+                assert abs(so.sims(G[gi[qi, j]][None, :], batches[b][qi].cpu().numpy()[None, :])[0, 0] - ws[qi, j]) <= 2e-6
+            assert gi[0, 0] == 17
+
+    merged = 0
+    for b in range(6):
+        for r in range(world):                   # all searches (full-SM kernels) first: the ranks share ONE GPU here
+            group[r].topk_push_dev(shards[r], batches[b], k, loc[r][0], loc[r][1], stream=streams[r].cuda_stream)
+        torch.cuda.synchronize()
+        if b >= lag:
+            for r in range(world):
+                group[r].wait_merge_dev(out[r][0], out[r][1], stream=streams[r].cuda_stream)
+            check(merged)
+            merged += 1
+    while merged < 6:                            # drain
+        for r in range(world):
+            group[r].wait_merge_dev(out[r][0], out[r][1], stream=streams[r].cuda_stream)
+        check(merged)
+        merged += 1
+    assert all(x.status() == 0 for x in group)
+    assert any(sh.rows and sh.last_flagged() >= 1 for sh in shards)
+    # host-buffer entry point of the sharded search (what bench.py's e2e times)
+    if world == 1:
+        s1, i1 = frb200.search_topk(shards[0], group[0], batches[2].cpu().numpy(), k)
+        assert np.abs(s1 - want[2][0]).max() <= SCORE_TOL and i1[0, 0] == 17
+        s2, i2 = frb200.search_topk(shards[0], None, batches[2].cpu().numpy(), k)
+        assert np.array_equal(i1, i2)
+    for o in shards + group:
+        o.close()
+
+
+def test_exchange_reports_a_missing_peer_instead_of_trapping(monkeypatch):
+    # a rank that never arrives must not kill the context. With a 200 ms timeout the waiting rank substitutes (-inf, -1)
+    # for the missing shard, finishes, and fr_exchange_status names the rank; the device stays usable.
+    import torch
+
+    monkeypatch.setenv("FR_XCHG_TIMEOUT_MS", "200")
+    rng = np.random.default_rng(8)
+    G = so.l2_normalise(rng.standard_normal((6000, 512)))
+    q = torch.from_numpy(so.planted_queries(G[rng.integers(0, 3000, 32)], 0.6, 1)).cuda()
+    sh = frb200.Gallery.from_rows(G[:3000])
+    sh.set_path(frb200.FR_PATH_TENSOR)
+    group = [frb200.Exchange(0, 2, r, nq_max=32, k_max=1) for r in range(2)]
+    for x in group:
+        x.connect_local(group)
+    st = torch.cuda.Stream()
+    ls, li = torch.empty((32, 1), dtype=torch.float32, device="cuda"), torch.empty((32, 1), dtype=torch.int64, device="cuda")
+    os_, oi = torch.empty((32, 1), dtype=torch.float32, device="cuda"), torch.empty((32, 1), dtype=torch.int64, device="cuda")
+    group[0].topk_push_dev(sh, q, 1, ls, li, stream=st.cuda_stream)      # rank 1 never searches
+    group[0].wait_merge_dev(os_, oi, stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    assert group[0].status() == 2                                         # 1 + the rank that never arrived
+    assert torch.equal(oi, li) and torch.equal(os_, ls)                   # the local shard's answer survives
+    s, i = sh.topk(q.cpu().numpy(), 1)                                    # context still alive
+    assert np.array_equal(i, li.cpu().numpy())
+    for o in [sh] + group:
         o.close()
 
 
