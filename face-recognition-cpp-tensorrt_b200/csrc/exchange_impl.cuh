@@ -351,4 +351,139 @@ int fr_search_topk(FrGallery* g, FrExchange* x, const float* q, int nq, int k, f
     });
 }
 
+/* ---- asynchronous host-buffer search stream: the serving form of fr_search_topk. Up to two batches are in flight, so the GPU always
+ * has the next search queued while the host collects the previous result, and (sharded) the cross-GPU merge of batch i is issued
+ * after the search of batch i + 1 (lag 1). Queries are staged through library-owned pinned memory: the caller's buffers are free again
+ * when submit returns. All ranks of a sharded gallery must submit / collect the same batches in the same order. */
+}  // extern "C"
+
+struct FrSearchStream {
+    static constexpr int kRing = 4;
+    FrGallery* g = nullptr;
+    FrExchange* x = nullptr;
+    int k = 1;
+    cudaStream_t st = nullptr;
+    float* q_pin[kRing] = {};
+    float* q_dev[kRing] = {};
+    float* s_pin[kRing] = {};
+    long long* i_pin[kRing] = {};
+    float* res_s[kRing] = {};
+    long long* res_i[kRing] = {};
+    cudaEvent_t done[kRing] = {};
+    int nq[kRing] = {};
+    bool delivered[kRing] = {};     // merge + D2H + event of this batch already enqueued
+    long long submitted = 0, collected = 0;
+};
+
+namespace {
+// enqueue the receiving half of batch b: (sharded) wait + merge, then D2H into pinned memory, then the event collect waits on
+void enqueue_delivery(FrSearchStream* s, long long b) {
+    const int r = static_cast<int>(b % FrSearchStream::kRing);
+    if (s->delivered[r]) return;
+    if (s->x) launch_wait_merge(s->x, s->nq[r], s->k, s->res_s[r], s->res_i[r], s->st);
+    FRB_CUDA(cudaMemcpyAsync(s->s_pin[r], s->res_s[r], sizeof(float) * s->nq[r] * s->k, cudaMemcpyDeviceToHost, s->st));
+    FRB_CUDA(cudaMemcpyAsync(s->i_pin[r], s->res_i[r], sizeof(long long) * s->nq[r] * s->k, cudaMemcpyDeviceToHost, s->st));
+    FRB_CUDA(cudaEventRecord(s->done[r], s->st));
+    s->delivered[r] = true;
+}
+}  // namespace
+
+extern "C" {
+
+int fr_search_stream_create(FrGallery* g, FrExchange* x, int k, FrSearchStream** out) {
+    return guarded([&] {
+        if (!g || !out) throw ArgError{"null argument"};
+        if (k < 1 || k > FR_TOPK_MAX) throw ArgError{"k out of range"};
+        if (x && (!x->connected || x->device != g->device || k > x->k_max)) throw ArgError{"exchange not usable with this gallery / k"};
+        std::unique_ptr<FrSearchStream> s(new FrSearchStream());
+        s->g = g;
+        s->x = x;
+        s->k = k;
+        DeviceGuard dg(g->device);
+        try {
+            FRB_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+            for (int r = 0; r < FrSearchStream::kRing; ++r) {
+                FRB_CUDA(cudaMallocHost(&s->q_pin[r], sizeof(float) * kChunkQ * kDim));
+                FRB_CUDA(cudaMalloc(&s->q_dev[r], sizeof(float) * kChunkQ * kDim));
+                FRB_CUDA(cudaMallocHost(&s->s_pin[r], sizeof(float) * kChunkQ * FR_TOPK_MAX));
+                FRB_CUDA(cudaMallocHost(&s->i_pin[r], sizeof(long long) * kChunkQ * FR_TOPK_MAX));
+                FRB_CUDA(cudaMalloc(&s->res_s[r], sizeof(float) * kChunkQ * FR_TOPK_MAX));
+                FRB_CUDA(cudaMalloc(&s->res_i[r], sizeof(long long) * kChunkQ * FR_TOPK_MAX));
+                FRB_CUDA(cudaEventCreateWithFlags(&s->done[r], cudaEventDisableTiming));
+            }
+        } catch (...) {
+            fr_search_stream_destroy(s.release());
+            throw;
+        }
+        *out = s.release();
+    });
+}
+
+void fr_search_stream_destroy(FrSearchStream* s) {
+    if (!s) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->g->device);
+    if (s->st) cudaStreamSynchronize(s->st);
+    for (int r = 0; r < FrSearchStream::kRing; ++r) {
+        cudaFreeHost(s->q_pin[r]);
+        cudaFree(s->q_dev[r]);
+        cudaFreeHost(s->s_pin[r]);
+        cudaFreeHost(s->i_pin[r]);
+        cudaFree(s->res_s[r]);
+        cudaFree(s->res_i[r]);
+        if (s->done[r]) cudaEventDestroy(s->done[r]);
+    }
+    if (s->st) cudaStreamDestroy(s->st);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete s;
+}
+
+/* the CUDA stream the searches run on (cudaStream_t as void*): for callers that time the stream with their own events */
+void* fr_search_stream_cuda_stream(FrSearchStream* s) { return s ? static_cast<void*>(s->st) : nullptr; }
+
+int fr_search_stream_submit(FrSearchStream* s, const float* q, int nq) {
+    return guarded([&] {
+        if (!s || !q) throw ArgError{"null argument"};
+        if (nq < 1 || nq > kChunkQ) throw ArgError{"1..256 queries per batch"};
+        if (s->submitted - s->collected >= 2) throw StateError{"two batches already in flight: collect one first"};
+        FrGallery* g = s->g;
+        if (!s->x && g->n == 0) throw StateError{"Feature matching: No faces in database or no faces found"};
+        DeviceGuard dg(g->device);
+        const long long b = s->submitted;
+        const int r = static_cast<int>(b % FrSearchStream::kRing);
+        std::memcpy(s->q_pin[r], q, sizeof(float) * nq * kDim);
+        s->nq[r] = nq;
+        s->delivered[r] = false;
+        FRB_CUDA(cudaMemcpyAsync(s->q_dev[r], s->q_pin[r], sizeof(float) * nq * kDim, cudaMemcpyHostToDevice, s->st));
+        if (s->x) {
+            const int rc = fr_gallery_topk_push_dev(g, s->x, s->q_dev[r], nq, s->k, g->loc_s, reinterpret_cast<int64_t*>(g->loc_i), s->st);
+            if (rc != FR_OK) throw CudaError{std::string("sharded search failed: ") + fr_last_error()};
+        } else {
+            g->first_chunk = true;
+            topk_chunk(g, s->q_dev[r], nq, s->k, s->res_s[r], s->res_i[r], s->st);
+        }
+        s->submitted = b + 1;
+        // receiving half: single shard -> right away; sharded -> the PREVIOUS batch now (its wait hides behind this batch's scan)
+        if (!s->x) enqueue_delivery(s, b);
+        else if (b > s->collected) enqueue_delivery(s, b - 1);
+    });
+}
+
+int fr_search_stream_collect(FrSearchStream* s, float* scores, int64_t* idx, int* nq_out) {
+    return guarded([&] {
+        if (!s || !scores || !idx) throw ArgError{"null argument"};
+        if (s->collected == s->submitted) throw StateError{"nothing in flight"};
+        DeviceGuard dg(s->g->device);
+        const long long b = s->collected;
+        const int r = static_cast<int>(b % FrSearchStream::kRing);
+        enqueue_delivery(s, b);  // no newer batch followed: deliver now
+        FRB_CUDA(cudaEventSynchronize(s->done[r]));
+        std::memcpy(scores, s->s_pin[r], sizeof(float) * s->nq[r] * s->k);
+        std::memcpy(idx, s->i_pin[r], sizeof(long long) * s->nq[r] * s->k);
+        if (nq_out) *nq_out = s->nq[r];
+        s->collected = b + 1;
+    });
+}
+
 }  // extern "C"

@@ -249,6 +249,46 @@ def search_topk(gal: "Gallery", exchange, q, k: int = 1, scores_out=None, idx_ou
     return scores, idx
 
 
+class SearchStream:
+    """fr_search_stream_*: asynchronous host-buffer search with two batches in flight (the serving form of search_topk)"""
+
+    def __init__(self, gal: "Gallery", exchange=None, k: int = 1):
+        L = lib()
+        L.fr_search_stream_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.fr_search_stream_destroy.restype = None
+        L.fr_search_stream_destroy.argtypes = [C.c_void_p]
+        L.fr_search_stream_cuda_stream.restype = C.c_void_p
+        L.fr_search_stream_cuda_stream.argtypes = [C.c_void_p]
+        L.fr_search_stream_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.fr_search_stream_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        h = C.c_void_p()
+        check(L.fr_search_stream_create(gal._h, exchange._h if exchange is not None else None, k, C.byref(h)))
+        self._h, self.k, self._keep = h, k, (gal, exchange)
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(lib().fr_search_stream_cuda_stream(self._h) or 0)
+
+    def submit(self, q) -> None:
+        check(lib().fr_search_stream_submit(self._h, _ptr(q), q.shape[0]))
+
+    def collect(self, scores_out, idx_out) -> int:
+        n = C.c_int()
+        check(lib().fr_search_stream_collect(self._h, _ptr(scores_out), _ptr(idx_out), C.byref(n)))
+        return n.value
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_search_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def topk_merge_dev(scores_parts_t, idx_parts_t, n_parts: int, nq: int, k: int, scores_t, idx_t, device: int, stream: int = 0) -> None:
     check(lib().fr_topk_merge_dev(_ptr(scores_parts_t), _ptr(idx_parts_t), n_parts, nq, k, _ptr(scores_t), _ptr(idx_t), device,
                                   C.c_void_p(stream)))

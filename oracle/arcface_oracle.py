@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from oracle.synth_weights import arcface_blocks
+from tools.synth_weights import arcface_blocks
 
 BN_EPS = 1e-5  # nn.BatchNorm2d default, used by every BatchNorm in model_irse.py
 

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from oracle.synth_weights import arcface_blocks
+from tools.synth_weights import arcface_blocks
 
 
 def _w(t, cout, cin, k):

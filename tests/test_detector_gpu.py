@@ -12,7 +12,7 @@ import torch
 
 import frb200
 from oracle import retina_oracle as ro
-from oracle import synth_weights as sw
+from tools import synth_weights as sw
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))

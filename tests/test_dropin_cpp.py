@@ -30,7 +30,7 @@ def test_shim_compiles_and_keeps_error_conventions(tmp_path, built_lib):
 @pytest.mark.gpu
 def test_app_call_pattern_runs_on_gpu(tmp_path, built_lib):
     sys.path.insert(0, str(ROOT))
-    from oracle import synth_weights as sw
+    from tools import synth_weights as sw
     from tools import make_golden_retina as mgr
     from tools import pack_retina as pr
     from tools import pack_weights as pw

@@ -11,7 +11,7 @@ import torch
 
 import frb200
 from oracle import arcface_oracle as ao
-from oracle import synth_weights as sw
+from tools import synth_weights as sw
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))

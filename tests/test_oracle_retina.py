@@ -10,7 +10,7 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from oracle import retina_oracle as ro  # noqa: E402
-from oracle import synth_weights as sw  # noqa: E402
+from tools import synth_weights as sw  # noqa: E402
 from tools import make_golden_retina as mgr  # noqa: E402
 from tools import pack_retina as pr  # noqa: E402
 from tools import pack_weights as pw  # noqa: E402

@@ -16,7 +16,7 @@ import frb200
 from oracle import arcface_oracle as ao
 from oracle import retina_oracle as ro
 from oracle import search_oracle as so
-from oracle import synth_weights as sw
+from tools import synth_weights as sw
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))

@@ -36,15 +36,56 @@ def _event_time(torch, fn, reps, warm=3):
     return e0.elapsed_time(e1) * 1e-3 / reps
 
 
-def run_gpu(device: int, frames_batch=64, gallery_rows=1_000_000, reps=10, hbm_gbs=6542.1, tf_sust=1381.0) -> dict:
+def _oracle_plant(frames, boxes, counts, gallery_rows, noise=0.3, seed=3):
+    """the parity gate's expectation (checker, untimed): the oracle chain on the detector's boxes — OpenCV-exact crops
+    (oracle/cv_resize.py) -> fp32 IR-SE-50 (oracle/arcface_oracle.py) — gives one embedding per DISTINCT face; a noisy copy of each is
+    planted at a known gallery row, so every face of the batch has a known top-1 identity. Returns (rows [n_distinct], planted
+    vectors [n_distinct, 512], oracle embeddings)."""
+    import torch
+
+    from oracle import arcface_oracle as ao
+    from oracle import cv_resize as cr
+    from oracle import search_oracle as so
+    from tools import synth_weights as sw
+
+    arc_sd = ao.to_torch(sw.arcface_state_dict("ir_se", 7))
+    embs = []
+    for f in range(frames.shape[0]):
+        crops = cr.cropped_faces(frames[f], boxes[f, : counts[f]])
+        embs.append(ao.forward(arc_sd, torch.from_numpy(ao.preprocess_faces(crops)), "ir_se").numpy())
+    emb = np.concatenate(embs)
+    rows = (np.arange(emb.shape[0], dtype=np.int64) * 7919 + 11) % gallery_rows
+    assert len(set(rows.tolist())) == emb.shape[0]
+    return rows, so.planted_queries(emb, noise=noise, seed=seed), emb
+
+
+def run_gpu(device: int, frames_batch=64, gallery_rows=1_000_000, reps=10, hbm_gbs=6542.1, tf_sust=1381.0, dist=None, world=1, rank=0,
+            stage_breakdown=True, distinct_frames=16) -> dict:
+    """faces/sec end to end on THIS rank's GPU; with dist != None every rank runs its own replica (weights and the 1M-row gallery
+    replicated, SURVEY 8e "replicas only") between common barriers and the aggregate is reported by rank 0."""
     import torch
 
     import frb200
-    from oracle import synth_weights as sw
+    from oracle import search_oracle as so
     from tools import make_golden_nets as mg
     from tools import make_golden_retina as mgr
     from tools import pack_retina as pr
     from tools import pack_weights as pw
+    from tools import synth_weights as sw
+
+    dev = torch.device("cuda", device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     out: dict = {}
     with tempfile.TemporaryDirectory() as td:
@@ -56,72 +97,86 @@ def run_gpu(device: int, frames_batch=64, gallery_rows=1_000_000, reps=10, hbm_g
         gal = frb200.Gallery.synthetic(gallery_rows, seed=17, device=device)
         gal.set_path(frb200.FR_PATH_TENSOR)
         pipe = frb200.Pipeline(det, emb, gal)
-        base = mgr.det_frames(4, 640, 640, seed=13)
-        frames = torch.from_numpy(np.ascontiguousarray(np.concatenate([base] * (frames_batch // 4 + 1))[:frames_batch])).pin_memory()
-        res = pipe.run(frames)
+        base = mgr.det_frames(distinct_frames, 640, 640, seed=13)
+        reps_f = (frames_batch + distinct_frames - 1) // distinct_frames
+        frames = torch.from_numpy(np.ascontiguousarray(np.concatenate([base] * reps_f)[:frames_batch])).pin_memory()
+        # ---- parity gate (untimed): identities of every face of the batch are known and checked in this run
+        boxes_d, counts_d, _ = det.run(base)
+        planted = torch.zeros((int(counts_d.sum()), 512), dtype=torch.float32, device=dev)
+        rows_t = torch.zeros(int(counts_d.sum()), dtype=torch.int64, device=dev)
+        oracle_emb = None
+        if rank == 0:
+            rows, vecs, oracle_emb = _oracle_plant(base, boxes_d, counts_d, gallery_rows)
+            planted.copy_(torch.from_numpy(vecs))
+            rows_t.copy_(torch.from_numpy(rows))
+        if dist is not None:
+            dist.broadcast(planted, 0)
+            dist.broadcast(rows_t, 0)
+        rows, vecs = rows_t.cpu().numpy(), planted.cpu().numpy()
+        for r, v in zip(rows, vecs):
+            gal.update(int(r), v)
+        res = pipe.run(frames, want_embeddings=True)
         faces = int(res["counts"].sum())
+        # expected identity of face j of frame f = the planted row of that face of base frame f % distinct_frames
+        first = np.concatenate([[0], np.cumsum(counts_d)])[:-1]
+        exp = np.full(res["idx"].shape, -1, np.int64)
+        for f in range(frames_batch):
+            bf = f % distinct_frames
+            exp[f, : counts_d[bf]] = rows[first[bf] : first[bf] + counts_d[bf]]
+        ok_idx = bool(np.array_equal(res["idx"], exp) and np.array_equal(res["counts"], np.tile(counts_d, reps_f)[:frames_batch]))
+        gate = {"identities_exact": ok_idx, "faces_checked": faces, "distinct_faces": int(counts_d.sum())}
+        if rank == 0 and oracle_emb is not None:
+            got = np.concatenate([res["embeddings"][f, : counts_d[f]] for f in range(distinct_frames)])
+            gate["max_abs_dembedding_vs_fp32_oracle"] = float(np.abs(got - oracle_emb).max())
+            ws = np.einsum("ij,ij->i", oracle_emb.astype(np.float64), vecs.astype(np.float64))
+            gs = np.concatenate([res["score"][f, : counts_d[f]] for f in range(distinct_frames)])
+            gate["max_abs_dscore_vs_oracle"] = float(np.abs(gs - ws).max())
+            ok_idx = ok_idx and gate["max_abs_dembedding_vs_fp32_oracle"] <= 1e-3 and gate["max_abs_dscore_vs_oracle"] <= 1e-3
+        if not ok_idx:
+            raise RuntimeError(f"pipeline parity gate failed: {gate}")
+        # ---- timed: `reps` batches back to back through the public host-buffer call, wall clock between barriers (the call is
+        # synchronous: host frames in pinned memory -> (idx, score) on the host), max over ranks
+        for _ in range(3):
+            pipe.run(frames)
+        barrier()
         l0 = frb200.launch_count()
-        t = _event_time(torch, lambda: pipe.run(frames), reps)
-        launches = (frb200.launch_count() - l0) // (reps + 3)
-        out["e2e"] = {"metric": "faces/sec end-to-end 640x640", "value": faces / t, "unit": "faces/s", "frames_per_s": frames_batch / t,
-                      "ms_per_batch": t * 1e3, "batch_frames": frames_batch, "faces_per_batch": faces, "gallery_rows": gallery_rows,
-                      "h2d_bytes_per_batch": int(frames.numel()), "gpu_launches_per_batch": int(launches),
-                      "config": "detect(RetinaFace mobile0.25 640x640) -> crop+bicubic 112x112 -> embed(ArcFace IR-SE-50) -> top-1 search"}
-        # throughput with TWO batches in flight: a second, independent set of handles (own stream, own scratch) driven from a second
-        # host thread, so that one batch's H2D copies and host-side box compaction overlap the other's kernels. Same public call
-        # (fr_pipeline_run, host buffers in and out); wall clock around both threads, each call ends with its own stream sync.
-        try:
-            import threading
-
-            det2 = frb200.Detector(td / "det.frw", (640, 640), max_batch=frames_batch, max_faces=4, device=device)
-            emb2 = frb200.Embedder(td / "arc.frw", max_batch=256, device=device)
-            gal2 = frb200.Gallery.synthetic(gallery_rows, seed=17, device=device)
-            gal2.set_path(frb200.FR_PATH_TENSOR)
-            pipe2 = frb200.Pipeline(det2, emb2, gal2)
-            frames2 = frames.clone().pin_memory()
-            res2 = pipe2.run(frames2)
-            assert np.array_equal(res2["idx"], res["idx"]) and np.array_equal(res2["counts"], res["counts"])
-            for _ in range(2):
-                pipe.run(frames)
-                pipe2.run(frames2)
-            torch.cuda.synchronize()
-            n_iter = reps
-            start = threading.Barrier(3)
-
-            def worker(pp, ff):
-                start.wait()
-                for _ in range(n_iter):
-                    pp.run(ff)
-
-            ths = [threading.Thread(target=worker, args=(pipe, frames)), threading.Thread(target=worker, args=(pipe2, frames2))]
-            for th in ths:
-                th.start()
-            start.wait()
-            t0 = time.perf_counter()
-            for th in ths:
-                th.join()
-            torch.cuda.synchronize()
-            t2 = (time.perf_counter() - t0) / (2 * n_iter)
-            out["e2e_two_in_flight"] = {"value": faces / t2, "unit": "faces/s", "frames_per_s": frames_batch / t2, "ms_per_batch": t2 * 1e3,
-                                        "note": "two independent handle sets on two streams / host threads, wall clock; per-batch latency is the "
-                                                "single-stream ms_per_batch above"}
-            pipe2.close()
-            gal2.close()
-            det2.close()
-            emb2.close()
-        except Exception as e:  # informational
-            out["e2e_two_in_flight"] = {"error": f"{type(e).__name__}: {e}"}
-        # stage breakdown on the same handles (host-buffer API, so H2D/D2H are inside)
-        f16 = frames[:16].numpy()
-        td_ = _event_time(torch, lambda: det.run(f16), reps)
-        out["detect"] = {"batch": 16, "ms": td_ * 1e3, "frames_per_s": 16 / td_,
-                         "roofline": {"bound": "hbm", "achieved": DET_MB_PER_FRAME * 16e-3 / td_, "peak": hbm_gbs, "unit": "GB/s",
-                                      "frac": DET_MB_PER_FRAME * 16e-3 / td_ / hbm_gbs, "note": "whole detector step incl. H2D, not one kernel"}}
-        crops = np.ascontiguousarray(np.concatenate([mg.arcface_inputs()] * 4))
-        te = _event_time(torch, lambda: emb.run_crops(crops), reps)
-        out["embed"] = {"batch": 32, "mode": "ir_se", "ms": te * 1e3, "faces_per_s": 32 / te,
-                        "roofline": {"bound": "tensor", "achieved": EMB_GFLOP_PER_FACE * 32e-3 / te, "peak": tf_sust, "unit": "TFLOP/s",
-                                     "frac": EMB_GFLOP_PER_FACE * 32e-3 / te / tf_sust, "note": "whole embedder step incl. H2D, not one kernel"}}
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = pipe.run(frames)
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) / reps
+        launches = (frb200.launch_count() - l0) // reps
+        t_all = max_over_ranks(t)
+        barrier()
+        if not np.array_equal(res["idx"], exp):
+            raise RuntimeError("pipeline parity gate failed inside the timed loop")
+        out["e2e"] = {"metric": "faces/sec end-to-end 640x640", "value": world * faces / t_all, "unit": "faces/s", "n_gpus": world,
+                      "faces_per_s_per_gpu": faces / t_all, "frames_per_s": world * frames_batch / t_all, "ms_per_batch": t_all * 1e3,
+                      "batch_frames": frames_batch, "faces_per_batch": faces, "gallery_rows": gallery_rows, "parallelism": "replicas (one pipeline per GPU, no collective)",
+                      "h2d_bytes_per_batch": int(frames.numel()), "d2h_bytes_per_batch": faces * 12 + frames_batch * (4 * 20 + 4),
+                      "gpu_launches_per_batch": int(launches), "parity_gate": gate, "timing": "wall clock around the synchronous host-buffer call, barrier + synchronize on both sides, max over ranks",
+                      "config": "detect(RetinaFace mobile0.25 640x640) -> device-side face compaction -> crop+bicubic 112x112 -> embed(ArcFace IR-SE-50) -> top-1 search (BASELINE.json configs[3])"}
+        if stage_breakdown:
+            # stage breakdown on the same handles, device-resident (kernels only) and through the host-buffer entry points
+            f16 = frames[:16].numpy()
+            td_ = _event_time(torch, lambda: det.run(f16), reps)
+            out["detect"] = {"batch": 16, "ms": td_ * 1e3, "frames_per_s": 16 / td_,
+                             "roofline": {"bound": "hbm", "achieved": DET_MB_PER_FRAME * 16e-3 / td_, "peak": hbm_gbs, "unit": "GB/s",
+                                          "frac": DET_MB_PER_FRAME * 16e-3 / td_ / hbm_gbs, "note": "whole detector step incl. H2D, not one kernel"}}
+            for b in (32, 256):
+                crops = np.ascontiguousarray(np.concatenate([mg.arcface_inputs()] * ((b + 7) // 8))[:b])
+                x = torch.from_numpy((crops[..., ::-1].transpose(0, 3, 1, 2).astype(np.float32) - 127.5) * 0.0078125).to(dev).contiguous()
+                y = torch.empty((b, 512), dtype=torch.float32, device=dev)
+                st = torch.cuda.current_stream().cuda_stream
+                te = _event_time(torch, lambda: emb.run_dev(x, y, stream=st), reps)
+                out[f"embed_b{b}"] = {"batch": b, "mode": "ir_se", "ms": te * 1e3, "faces_per_s": b / te, "inputs": "device-resident f32 CHW",
+                                      "roofline": {"bound": "tensor", "achieved": EMB_GFLOP_PER_FACE * b * 1e-3 / te, "peak": tf_sust, "unit": "TFLOP/s",
+                                                   "frac": EMB_GFLOP_PER_FACE * b * 1e-3 / te / tf_sust, "note": "whole embedder forward (all kernels), device-resident"}}
+            crops32 = np.ascontiguousarray(np.concatenate([mg.arcface_inputs()] * 4))
+            te = _event_time(torch, lambda: emb.run_crops(crops32), reps)
+            out["embed"] = {"batch": 32, "mode": "ir_se", "ms": te * 1e3, "faces_per_s": 32 / te,
+                            "roofline": {"bound": "tensor", "achieved": EMB_GFLOP_PER_FACE * 32e-3 / te, "peak": tf_sust, "unit": "TFLOP/s",
+                                         "frac": EMB_GFLOP_PER_FACE * 32e-3 / te / tf_sust, "note": "whole embedder step incl. H2D/D2H (host-buffer call), not one kernel"}}
         pipe.close()
         gal.close()
         det.close()
@@ -135,7 +190,7 @@ def run_cpu(det_frames=2, emb_faces=8) -> dict:
 
     from oracle import arcface_oracle as ao
     from oracle import retina_oracle as ro
-    from oracle import synth_weights as sw
+    from tools import synth_weights as sw
     from tools import make_golden_nets as mg
     from tools import make_golden_retina as mgr
 

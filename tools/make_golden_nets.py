@@ -1,6 +1,6 @@
 """Generate tests/golden/arcface_*.npz (and retina_*.npz) HERE, in the build container, by running the reference's OWN
 PyTorch modules (imported read-only from /root/reference/conversion) on the seeded synthetic checkpoints of
-oracle/synth_weights.py. The GPU box has no /root/reference: there the tests compare against these committed vectors and
+tools/synth_weights.py. The GPU box has no /root/reference: there the tests compare against these committed vectors and
 against the restated oracles (oracle/arcface_oracle.py, oracle/retina_oracle.py), which this script also pins.
 
     PYTHONDONTWRITEBYTECODE=1 python tools/make_golden_nets.py [arcface] [retina]
@@ -16,7 +16,7 @@ sys.path.insert(0, str(ROOT))
 REF = Path("/root/reference/conversion")
 GOLD = ROOT / "tests" / "golden"
 
-from oracle import synth_weights as sw  # noqa: E402
+from tools import synth_weights as sw  # noqa: E402
 
 ARC_SEED, ARC_INPUT_SEED, ARC_N = 7, 7, 8
 

@@ -15,7 +15,7 @@ sys.path.insert(0, str(ROOT))
 REF = Path("/root/reference/conversion")
 GOLD = ROOT / "tests" / "golden"
 
-from oracle import synth_weights as sw  # noqa: E402
+from tools import synth_weights as sw  # noqa: E402
 
 DET_SEED, DET_FRAME_SEED = 11, 11
 DET_CLS_SHIFT = -4.5  # class-head bias shift: ~150 of the 16 800 anchors of a 640x640 noise frame pass the 0.6 threshold

@@ -73,7 +73,7 @@ def write_file(path, kind: int, tensors: "dict[str, np.ndarray]") -> None:
 
 # ------------------------------------------------------------------------------------------------------------ ArcFace
 def pack_arcface(sd: dict, mode: str) -> "dict[str, np.ndarray]":
-    from oracle.synth_weights import arcface_blocks
+    from tools.synth_weights import arcface_blocks
 
     sd = strip_prefix(sd)
     out: "dict[str, np.ndarray]" = {}
@@ -116,7 +116,7 @@ def save_arcface(path, sd: dict, mode: str) -> None:
 if __name__ == "__main__":
     import argparse
 
-    from oracle import synth_weights as sw
+    from tools import synth_weights as sw
 
     ap = argparse.ArgumentParser(description="pack a synthetic (seeded) or saved (.npz of a state dict) checkpoint")
     ap.add_argument("net", choices=["arcface_ir", "arcface_ir_se", "retina_trim", "retina_full"])

@@ -21,7 +21,7 @@ sys.path.insert(0, str(ROOT / "face-recognition-cpp-tensorrt_b200"))
 
 
 def make_ckpts(tmp: Path, arc_mode="ir_se"):
-    from oracle import synth_weights as sw
+    from tools import synth_weights as sw
     from tools import make_golden_retina as mgr
     from tools import pack_retina as pr
     from tools import pack_weights as pw

@@ -1,4 +1,5 @@
-"""ORACLE / TEST INFRASTRUCTURE: deterministic synthetic checkpoints for the two networks of the hot path.
+"""DATA GENERATOR (tests, benches, the weight packer; not an oracle, not part of the library): deterministic synthetic checkpoints
+for the two networks of the hot path.
 
 The reference ships no weights (weight/ and *.engine are git-ignored, /root/reference/.gitignore:6-9) and there is no
 network, so parity is defined on seeded synthetic checkpoints. They are generated with integer hashing + numpy only (no
