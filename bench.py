@@ -7,16 +7,17 @@ Workload (config.workload): the gallery-sharded cosine-similarity search of BASE
 embeddings against a synthetic 10M x 512 gallery, row-sharded over the N GPUs (strong scaling: the gallery is fixed, each rank scans
 10M/N rows), per-shard top-1 exchanged over NVLink peer memory and merged. One "step" = one query batch.
 
-Every phase below times EXACTLY --steps steps between a barrier + synchronize on both sides with CUDA events on the launching stream
-(max over ranks). Because one block of 20 steps lasts only milliseconds and the GPUs run under a 1 kW power cap whose clock oscillates,
-the blocks of all phases are repeated round-robin (`rounds`) until every phase has covered >= --min-phase-s, and the MEDIAN block is
-reported with min / max beside it: all phases share the same power state.
+Every timed BLOCK is EXACTLY --steps steps between a barrier + synchronize on both sides, CUDA events on the launching stream, max
+over ranks. One block of 20 steps lasts only milliseconds and the GPUs run under a 1 kW power cap (a phase needs ~0.1 s of its own load
+before its clock settles, and what ran just before it shifts that point), so every phase runs --passes continuous WINDOWS of
+back-to-back blocks covering >= --min-phase-s in total; the phase order rotates between passes, the first quarter of each window
+is run but not recorded, and the MEDIAN recorded block is reported with min / max beside it.
 
     value      queries/s, queries resident in HBM (CUDA-graph replay of the step), planted queries, headline scan copy
     e2e        queries/s through the public host-buffer API (fr_search_stream_submit / _collect: pinned staging -> H2D -> search ->
                cross-GPU merge -> D2H, two batches in flight), every step
-    roofline   the fused scan kernel (cosine_topk_coarse), timed by CUDA events around the kernel inside the eager phase of the SAME
-               rounds; algorithmic bytes = shard rows x 512 x s (s = 2 B fp16 copy, 1 B e4m3 copy; SURVEY 8d), flops = 2 x 256 x rows x 512;
+    roofline   the fused scan kernel (cosine_topk_coarse), timed by a fixed CUDA-event pair around the kernel INSIDE the replayed
+               steps of the same blocks (one sample per block); algorithmic bytes = shard rows x 512 x s (s = 2 B fp16 copy, 1 B e4m3 copy; SURVEY 8d), flops = 2 x 256 x rows x 512;
                the binding roof at Q = 256 (tensor for the fp16 copy, HBM for e4m3) is `roofline`, the other one sits beside it
     scans      both resident scan copies as first-class results: f16 (deterministically exact top-k; the library's and the C++ shim's
                default; the headline) and f8 (e4m3, stochastic rounding + per-query certificate: exact unless an event of
@@ -471,8 +472,8 @@ def run_b200(args):
                 raise SystemExit(f"bench.py: parity failure on {sc}/{kd} (top-1 mismatches: {int((gi != wi).sum())}, "
                                  f"max |dscore| {float(np.abs(gs - ws).max()):.3e})")
 
-    # ---- phases. Each is a function running ONE step; graph phases replay a captured step, eager ones launch it (with the library's
-    # event pairs around the fused scan kernel), e2e ones go through the host-buffer stream API.
+    # ---- phases. Each is a function running ONE step; graph phases replay a captured step (eager launches when capture is off),
+    # e2e ones go through the host-buffer stream API.
     graphs, graph_note = {}, None
     use_graph = not args.no_graph and (n_gpus == 1 or exchange is not None)  # NCCL collectives stay eager (capturing them across ranks hung)
 
@@ -488,6 +489,7 @@ def run_b200(args):
         search(kind)
         merge()
 
+    gal.set_timing(2)  # fixed event pair around the fused scan kernel: recorded by eager launches and by every graph replay
     if use_graph:
         try:
             for sc in scans:
@@ -514,7 +516,6 @@ def run_b200(args):
         phases.append((f"{sc}/planted/graph", sc, "planted", "graph"))
         if sstream is not None:
             phases.append((f"{sc}/planted/e2e", sc, "planted", "e2e"))
-        phases.append((f"{sc}/planted/eager", sc, "planted", "eager"))
         if "unknown" in kinds:
             phases.append((f"{sc}/unknown/graph", sc, "unknown", "graph"))
     ms = {name: [] for name, *_ in phases}
@@ -522,6 +523,7 @@ def run_b200(args):
     launches_per_step = {}
 
     def run_block(name, sc, kd, mode, steps, record=True):
+        """EXACTLY `steps` steps between barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks"""
         gal.set_scan(SCAN_ID[sc])
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if mode == "e2e":
@@ -538,23 +540,19 @@ def run_b200(args):
             if not np.array_equal(res_i[:, 0], want[kd][0]):
                 raise SystemExit(f"bench.py: e2e parity failure ({name})")
         else:
-            fn = graphs[(sc, kd)].replay if (mode == "graph" and (sc, kd) in graphs) else (lambda: lag_step(kd))
-            if mode == "eager":
-                gal.set_timing(True)
+            fn = graphs[(sc, kd)].replay if (sc, kd) in graphs else (lambda: lag_step(kd))
             prime(kd)
             barrier()
-            l0 = frb200.launch_count()
             ev0.record(stream)
             for _ in range(steps):
                 fn()
             ev1.record(stream)
             barrier()
-            if mode == "eager":
-                launches_per_step[sc] = (frb200.launch_count() - l0) / max(steps, 1)
-                t_k, n_k = gal.scan_time()
-                gal.set_timing(False)
-                if record and n_k:
-                    kern[sc].append(t_k / n_k)
+            if record and kd == "planted":
+                try:  # duration of the fused scan kernel of the LAST of these very steps (fixed event pair, re-recorded by every replay)
+                    kern[sc].append(gal.last_scan_ms(SCAN_ID[sc]))
+                except Exception:
+                    pass
             drain()
             torch.cuda.synchronize()
         t = max_over_ranks(ev0.elapsed_time(ev1)) / max(steps, 1)
@@ -562,30 +560,48 @@ def run_b200(args):
             ms[name].append(t)
         return t
 
-    # warm-up (>= 3 steps of every phase), then an untimed ramp so that the first timed round already sees steady-state clocks
+    # launches per step: one eager step per scan copy, counted by the library
+    for sc in scans:
+        gal.set_scan(SCAN_ID[sc])
+        prime("planted")
+        l0 = frb200.launch_count()
+        lag_step("planted")
+        launches_per_step[sc] = frb200.launch_count() - l0
+        drain()
+        barrier()
+    # warm-up (>= 3 steps of every phase), probe of every phase's step time
+    t_est = {}
     for ph in phases:
         run_block(*ph, steps=max(args.warmup, 3), record=False)
-    t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < args.ramp_s:
-        run_block(*phases[0], steps=KS, record=False)
-    t_probe = min(run_block(*ph, steps=KS, record=False) for ph in phases)  # the fastest phase needs the most blocks to cover min_phase_s
-    rounds = int(min(args.max_rounds, max(args.min_rounds, math.ceil(args.min_phase_s * 1e3 / max(t_probe * KS, 1e-3)))))
-    if n_gpus > 1:
-        rt = torch.tensor([rounds], dtype=torch.int64, device=dev)
-        dist.broadcast(rt, 0)
-        rounds = int(rt.item())
+        t_est[ph[0]] = run_block(*ph, steps=KS, record=False)
+    if n_gpus > 1:  # every rank must run the same number of blocks
+        tt = torch.tensor([t_est[ph[0]] for ph in phases], dtype=torch.float64, device=dev)
+        dist.broadcast(tt, 0)
+        t_est = {ph[0]: float(v) for ph, v in zip(phases, tt.tolist())}
 
+    # Timed region. The GPUs run under a 1 kW power cap: a phase needs ~0.1 s of its own load before its clock settles, and what ran
+    # just before it shifts that point. So every phase gets `passes` continuous WINDOWS of back-to-back blocks (>= min_phase_s in
+    # total), the order of the phases rotates from pass to pass, the first quarter of every window is run but not recorded, and the
+    # median block of the rest is reported with min / max. The fused kernel's duration is read from the same blocks.
+    passes = max(1, args.passes)
+    window_s = args.min_phase_s / passes * 4.0 / 3.0
     sampler = ClockSampler(local)
     sampler.start()
     sampler.ready.wait(timeout=10)
     sampler.recording.set()
     t_wall = time.perf_counter()
-    for _ in range(rounds):          # round-robin: every phase sees every moment of the power-cap oscillation
-        for ph in phases:
-            run_block(*ph, steps=KS)
+    blocks_run = 0
+    for ps in range(passes):
+        order = phases[ps % len(phases):] + phases[:ps % len(phases)]
+        for ph in order:
+            nb = int(min(args.max_blocks, max(4, math.ceil(window_s * 1e3 / max(t_est[ph[0]] * KS, 1e-3)))))
+            for b in range(nb):
+                run_block(*ph, steps=KS, record=b >= nb // 4)
+                blocks_run += 1
     timed_wall_s = time.perf_counter() - t_wall
     sampler.recording.clear()
     clocks = sampler.result()
+    rounds = passes
 
     hbm_peak, tf_burst, tf_sust, peak_src = peaks()
     bytes_per_row = {"f16": 1024, "f8": 512}
@@ -593,11 +609,11 @@ def run_b200(args):
     shard_rows = hi - lo
 
     def scan_report(sc):
-        g_ms, e_ms = stats(ms[f"{sc}/planted/graph"]), stats(ms[f"{sc}/planted/eager"])
+        g_ms = stats(ms[f"{sc}/planted/graph"])
         k_ms = stats(kern[sc]) if kern[sc] else None
         algo_bytes, flops = shard_rows * bytes_per_row[sc], 2 * nq_pad * shard_rows * 512
         rep = {"scan": sc, "value": Q / (g_ms["median"] * 1e-3), "unit": UNIT, "ms_per_step": g_ms["median"], "ms_per_step_min_max": [g_ms["min"], g_ms["max"]],
-               "eager_ms_per_step": e_ms["median"], "exactness": ("deterministic: |coarse - exact| <= 1.25e-3 |q||g| is a proven bound, the result is "
+               "blocks": g_ms["n"], "exactness": ("deterministic: |coarse - exact| <= 1.25e-3 |q||g| is a proven bound, the result is "
                                                                  "the exact fp32 top-1 always" if sc == "f16" else
                                                                  "certified: stochastic e4m3 rounding + per-query certificate, wrong top-1 with probability "
                                                                  "<= 1e-12 per query for arbitrary rows (DESIGN.md 4.1), else recomputed by the exact scan"),
@@ -619,9 +635,9 @@ def run_b200(args):
             # bound), 512 for e4m3 against an assumed 2x tensor peak (ridge 436): reported against HBM, the measured peak
             bind = tn if sc == "f16" else hb
             rep["roofline"] = dict(bind, kernel="cosine_topk_coarse", kernel_ms=k_ms["median"], kernel_ms_min_max=[k_ms["min"], k_ms["max"]],
-                                   kernel_share_of_step=k_ms["median"] / e_ms["median"], algorithmic_bytes_per_launch=int(algo_bytes),
-                                   flops_per_launch=int(flops), launches_timed=k_ms["n"] * KS, peak_source=peak_src, traffic=None,
-                                   timed_in="the eager phase of the same round-robin rounds as ms_per_step")
+                                   kernel_share_of_step=k_ms["median"] / g_ms["median"], algorithmic_bytes_per_launch=int(algo_bytes),
+                                   flops_per_launch=int(flops), launches_timed=k_ms["n"], peak_source=peak_src, traffic=None,
+                                   timed_in="the same blocks as ms_per_step: CUDA events around the kernel inside the replayed step (one sample per block)")
             rep["roofline_other"] = tn if bind is hb else hb
         return rep
 
@@ -638,13 +654,15 @@ def run_b200(args):
                             "pipelining": ("the merge of batch i is issued after the search of batch i+1 (lag 1, 4 mailbox slots); every timed step "
                                            "contains one full search and one merge" if lag else "none: each step merges its own batch"),
                             "cuda_graph": bool(graphs), "cuda_graph_error": graph_note},
-            "rounds": rounds, "timing": {"blocks_per_phase": rounds, "steps_per_block": KS, "statistic": "median over blocks of (block time / steps), max over ranks",
-                                         "ms_per_step_min_max": head["ms_per_step_min_max"], "timed_wall_s": timed_wall_s, "phases": [p[0] for p in phases]},
+            "timing": {"passes": rounds, "blocks_total": blocks_run, "steps_per_block": KS, "blocks_recorded_headline": head["blocks"],
+                       "statistic": "median over recorded blocks of (block time / steps), each block = exactly `steps` steps between barrier + "
+                                    "synchronize, max over ranks; every phase runs `passes` continuous windows (first quarter of each unrecorded: clock settling)",
+                       "ms_per_step_min_max": head["ms_per_step_min_max"], "timed_wall_s": timed_wall_s, "phases": [p[0] for p in phases]},
             "e2e": dict(head.get("e2e", {"value": None, "unit": UNIT}), h2d_bytes_per_step=Q * 512 * 4, d2h_bytes_per_step=Q * K * 12,
                         api="fr_search_stream_submit + fr_search_stream_collect (host buffers; pinned staging, H2D, search, cross-GPU merge, D2H inside), two batches in flight"),
-            "gpu_launches": int(round((launches_per_step.get(args.scan) or 0) * KS)),
+            "gpu_launches": int((launches_per_step.get(args.scan) or 0) * KS),
             "clocks": clocks,
-            "parity": head["parity"]["planted"], "eager_ms_per_step": head["eager_ms_per_step"],
+            "parity": head["parity"]["planted"],
             "unknown_queries": head.get("unknown_queries"),
             "scans": reports,
             "other_scan": reports[[s for s in scans if s != args.scan][0]] if len(scans) > 1 else None,
@@ -717,16 +735,15 @@ def main():
                     help="N>1: NVLink peer-memory push fused into the search + wait/merge kernel (default), or NCCL all-gather + merge kernel")
     ap.add_argument("--scan", default="f16", choices=["f16", "f8"],
                     help="headline scan copy: f16 (default; 1 KiB/row, deterministically exact top-k, the library's and the C++ shim's default) or "
-                         "f8 (e4m3, 512 B/row, certified with failure probability <= 1e-12 per query); the other one is measured in the same rounds")
+                         "f8 (e4m3, 512 B/row, certified with failure probability <= 1e-12 per query); the other one is measured in the same passes")
     ap.add_argument("--no-unknown", action="store_true", help="skip the phases with queries that have no match")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
     ap.add_argument("--no-lag", action="store_true", help="N>1: merge every batch right after its own search (latency form)")
     ap.add_argument("--no-alt-scan", action="store_true", help="measure the headline scan copy only")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the detect->embed->search faces/sec section")
-    ap.add_argument("--ramp-s", type=float, default=1.0, help="untimed busy period before the timed rounds (clock ramp)")
-    ap.add_argument("--min-phase-s", type=float, default=1.0, help="every phase is repeated until its timed blocks cover this long")
-    ap.add_argument("--min-rounds", type=int, default=5)
-    ap.add_argument("--max-rounds", type=int, default=400)
+    ap.add_argument("--min-phase-s", type=float, default=1.0, help="recorded blocks of every phase cover at least this long in total")
+    ap.add_argument("--passes", type=int, default=3, help="continuous windows per phase (the phase order rotates between passes)")
+    ap.add_argument("--max-blocks", type=int, default=2000, help="cap on the blocks of one window")
     ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.traffic_probe:

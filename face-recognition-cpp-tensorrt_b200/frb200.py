@@ -217,8 +217,16 @@ class Gallery:
     def sims_dev(self, q_t, out_t, stream: int = 0) -> None:
         check(lib().fr_gallery_sims_dev(self._h, _ptr(q_t), q_t.shape[0], _ptr(out_t), C.c_void_p(stream)))
 
-    def set_timing(self, enable: bool) -> None:
+    def set_timing(self, enable) -> None:
+        """False / True: pooled event pairs around every launch of the fused scan kernel (scan_time); 2: one fixed pair per scan
+        copy that also works inside CUDA-graph replays (last_scan_ms)"""
         check(lib().fr_gallery_set_timing(self._h, int(enable)))
+
+    def last_scan_ms(self, scan: int) -> float:
+        lib().fr_gallery_last_scan_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        ms = C.c_double()
+        check(lib().fr_gallery_last_scan_ms(self._h, scan, C.byref(ms)))
+        return ms.value
 
     def scan_time(self):
         """(summed ms, launches) of the fused scan kernel since timing was enabled / last read"""

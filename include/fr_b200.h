@@ -204,6 +204,10 @@ int fr_gallery_last_flagged(FrGallery *g, int *out);
  * the stream it is launched on; fr_gallery_scan_time waits for them, returns their summed duration and count, and resets. */
 int fr_gallery_set_timing(FrGallery *g, int enable);
 int fr_gallery_scan_time(FrGallery *g, double *total_ms, int *launches);
+/* enable == 2: one FIXED event pair per scan copy instead of a pool. Fixed events survive stream capture (a replayed CUDA graph
+ * re-records them), so the duration of the fused kernel's most recent launch — eager or inside a graph replay — can be read from
+ * the very steps that are being timed. Waits for that launch. */
+int fr_gallery_last_scan_ms(FrGallery *g, int scan, double *ms);
 
 /* =====================================================================================
  * Embedder  (replaces ArcFaceIR50's network half, src/arcface.{h,cpp})

@@ -560,9 +560,10 @@ def test_fp8_structured_galleries_top1_exact(kind):
     s, i = g.topk(q, 1)
     flagged = g.last_flagged()
     sim = so.sims(G, q)
-    oi, ov = so.get_outputs(sim)
-    assert np.array_equal(i[:, 0], oi), (kind, np.nonzero(i[:, 0] != oi)[0][:5])
-    assert np.abs(s[:, 0] - ov).max() <= SCORE_TOL
+    # binarised / grid rows tie EXACTLY in real arithmetic (scores are multiples of 2/512), so the winner among tied rows depends on
+    # the fp32 summation order: _check_topk accepts a different row only if its score equals the oracle's to fp32 rounding; the
+    # bit-for-bit comparison with the fp16 path below (same exact re-score arithmetic) is the strict check
+    _check_topk(s, i, sim, 1)
     assert flagged <= 1, (kind, flagged)
     g.set_scan(frb200.FR_SCAN_F16)
     s2, i2 = g.topk(q, 1)
