@@ -16,8 +16,8 @@ is run but not recorded, and the MEDIAN recorded block is reported with min / ma
     value      queries/s, queries resident in HBM (CUDA-graph replay of the step), planted queries, headline scan copy
     e2e        queries/s through the public host-buffer API (fr_search_stream_submit / _collect: pinned staging -> H2D -> search ->
                cross-GPU merge -> D2H, two batches in flight), every step
-    roofline   the fused scan kernel (cosine_topk_coarse), timed by a fixed CUDA-event pair around the kernel INSIDE the replayed
-               steps of the same blocks (one sample per block); algorithmic bytes = shard rows x 512 x s (s = 2 B fp16 copy, 1 B e4m3 copy; SURVEY 8d), flops = 2 x 256 x rows x 512;
+    roofline   the fused scan kernel (cosine_topk_coarse), timed by CUDA-event pairs around every launch of the kernel INSIDE the
+               replayed blocks (a block = one captured graph of --steps steps); algorithmic bytes = shard rows x 512 x s (s = 2 B fp16 copy, 1 B e4m3 copy; SURVEY 8d), flops = 2 x 256 x rows x 512;
                the binding roof at Q = 256 (tensor for the fp16 copy, HBM for e4m3) is `roofline`, the other one sits beside it
     scans      both resident scan copies as first-class results: f16 (deterministically exact top-k; the library's and the C++ shim's
                default; the headline) and f8 (e4m3, stochastic rounding + per-query certificate: exact unless an event of
@@ -489,17 +489,28 @@ def run_b200(args):
         search(kind)
         merge()
 
-    gal.set_timing(2)  # fixed event pair around the fused scan kernel: recorded by eager launches and by every graph replay
+    # A whole BLOCK (--steps steps) is captured into one CUDA graph while the library's pooled event pairs bracket every launch of the
+    # fused scan kernel: each replay re-records those pairs, so the kernel time is read from exactly the steps that are timed.
     if use_graph:
         try:
+            gal.set_timing(True)           # grow the event pool to --steps pairs outside any capture (event creation is host work)
+            prime("planted")
+            for _ in range(KS):
+                lag_step("planted")
+            drain()
+            gal.set_timing(False)
+            torch.cuda.synchronize()
             for sc in scans:
                 gal.set_scan(SCAN_ID[sc])
                 for kd in kinds:
                     prime(kd)
                     torch.cuda.synchronize()
+                    gal.set_timing(True)   # pool restarts at pair 0: every graph owns pairs 0 .. steps-1 (graphs never run concurrently)
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=stream):
-                        lag_step(kd)
+                        for _ in range(KS):
+                            lag_step(kd)
+                    gal.set_timing(False)
                     torch.cuda.synchronize()
                     g.replay()
                     drain()
@@ -509,6 +520,7 @@ def run_b200(args):
                     graphs[(sc, kd)] = g
         except Exception as e:
             graphs, graph_note = {}, f"{type(e).__name__}: {e}"
+            gal.set_timing(False)
             torch.cuda.synchronize()
 
     phases = []  # (name, scan, kind, mode)
@@ -540,19 +552,23 @@ def run_b200(args):
             if not np.array_equal(res_i[:, 0], want[kd][0]):
                 raise SystemExit(f"bench.py: e2e parity failure ({name})")
         else:
-            fn = graphs[(sc, kd)].replay if (sc, kd) in graphs else (lambda: lag_step(kd))
+            whole = (sc, kd) in graphs and steps == KS   # the captured block
+            if not whole:
+                gal.set_timing(True)
             prime(kd)
             barrier()
             ev0.record(stream)
-            for _ in range(steps):
-                fn()
+            if whole:
+                graphs[(sc, kd)].replay()
+            else:
+                for _ in range(steps):
+                    lag_step(kd)
             ev1.record(stream)
             barrier()
-            if record and kd == "planted":
-                try:  # duration of the fused scan kernel of the LAST of these very steps (fixed event pair, re-recorded by every replay)
-                    kern[sc].append(gal.last_scan_ms(SCAN_ID[sc]))
-                except Exception:
-                    pass
+            if record and kd == "planted":   # the fused scan kernel's launches of these very steps
+                kern[sc].append(gal.pool_time(steps) / steps)
+            if not whole:
+                gal.set_timing(False)
             drain()
             torch.cuda.synchronize()
         t = max_over_ranks(ev0.elapsed_time(ev1)) / max(steps, 1)
@@ -636,8 +652,8 @@ def run_b200(args):
             bind = tn if sc == "f16" else hb
             rep["roofline"] = dict(bind, kernel="cosine_topk_coarse", kernel_ms=k_ms["median"], kernel_ms_min_max=[k_ms["min"], k_ms["max"]],
                                    kernel_share_of_step=k_ms["median"] / g_ms["median"], algorithmic_bytes_per_launch=int(algo_bytes),
-                                   flops_per_launch=int(flops), launches_timed=k_ms["n"], peak_source=peak_src, traffic=None,
-                                   timed_in="the same blocks as ms_per_step: CUDA events around the kernel inside the replayed step (one sample per block)")
+                                   flops_per_launch=int(flops), launches_timed=k_ms["n"] * KS, peak_source=peak_src, traffic=None,
+                                   timed_in="the same blocks as ms_per_step: CUDA events around every launch of the kernel inside the replayed block (mean per block, median over blocks)")
             rep["roofline_other"] = tn if bind is hb else hb
         return rep
 

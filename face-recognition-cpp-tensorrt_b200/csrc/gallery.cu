@@ -697,6 +697,22 @@ int fr_gallery_set_timing(FrGallery* g, int enable) {
     });
 }
 
+int fr_gallery_pool_time(FrGallery* g, int count, double* total_ms) {
+    return guarded([&] {
+        if (!g || !total_ms) throw ArgError{"null argument"};
+        if (count < 0 || static_cast<size_t>(count) > g->ev_pool.size()) throw ArgError{"more launches than event pairs in the pool"};
+        DeviceGuard dg(g->device);
+        double sum = 0;
+        for (int i = 0; i < count; ++i) {
+            FRB_CUDA(cudaEventSynchronize(g->ev_pool[i].second));
+            float ms = 0;
+            FRB_CUDA(cudaEventElapsedTime(&ms, g->ev_pool[i].first, g->ev_pool[i].second));
+            sum += ms;
+        }
+        *total_ms = sum;
+    });
+}
+
 int fr_gallery_last_scan_ms(FrGallery* g, int scan, double* ms) {
     return guarded([&] {
         if (!g || !ms) throw ArgError{"null argument"};

@@ -222,6 +222,13 @@ class Gallery:
         copy that also works inside CUDA-graph replays (last_scan_ms)"""
         check(lib().fr_gallery_set_timing(self._h, int(enable)))
 
+    def pool_time(self, count: int) -> float:
+        """summed ms of the first `count` pooled event pairs (a captured block of `count` steps re-records them on every replay)"""
+        lib().fr_gallery_pool_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        ms = C.c_double()
+        check(lib().fr_gallery_pool_time(self._h, count, C.byref(ms)))
+        return ms.value
+
     def last_scan_ms(self, scan: int) -> float:
         lib().fr_gallery_last_scan_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         ms = C.c_double()

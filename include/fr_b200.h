@@ -208,6 +208,10 @@ int fr_gallery_scan_time(FrGallery *g, double *total_ms, int *launches);
  * re-records them), so the duration of the fused kernel's most recent launch — eager or inside a graph replay — can be read from
  * the very steps that are being timed. Waits for that launch. */
 int fr_gallery_last_scan_ms(FrGallery *g, int scan, double *ms);
+/* Summed duration of the first `count` event pairs of the pool WITHOUT resetting it. A block of `count` steps captured into one CUDA
+ * graph while timing mode 1 is on owns pairs 0 .. count-1: after every replay of that graph this returns the time its `count`
+ * launches of the fused kernel took — the same steps the caller times around the replay. */
+int fr_gallery_pool_time(FrGallery *g, int count, double *total_ms);
 
 /* =====================================================================================
  * Embedder  (replaces ArcFaceIR50's network half, src/arcface.{h,cpp})
