@@ -465,6 +465,7 @@ void fr_gallery_destroy(FrGallery* g) {
 
 int64_t fr_gallery_rows(const FrGallery* g) { return g ? g->n : -1; }
 int fr_gallery_device(const FrGallery* g) { return g ? g->device : FR_EINVAL; }
+int64_t fr_gallery_row_offset(const FrGallery* g) { return g ? g->row_offset : -1; }
 
 int fr_gallery_set_path(FrGallery* g, int path) {
     return guarded([&] {

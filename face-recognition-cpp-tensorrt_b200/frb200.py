@@ -264,6 +264,78 @@ def search_topk(gal: "Gallery", exchange, q, k: int = 1, scores_out=None, idx_ou
     return scores, idx
 
 
+class Roster:
+    """fr_roster_*: row -> userId table (the reference's classNames) in step with a row-sharded gallery; see include/fr_b200.h"""
+
+    def __init__(self, local_shard: "Gallery | None", world: int = 1, rank: int = 0):
+        L = lib()
+        L.fr_roster_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.fr_roster_destroy.restype = None
+        L.fr_roster_destroy.argtypes = [C.c_void_p]
+        L.fr_roster_rows.restype = C.c_int64
+        L.fr_roster_rows.argtypes = [C.c_void_p]
+        L.fr_roster_shard_rows.restype = C.c_int64
+        L.fr_roster_shard_rows.argtypes = [C.c_void_p, C.c_int]
+        L.fr_roster_load.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int64]
+        L.fr_roster_add.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64)]
+        L.fr_roster_remove.argtypes = [C.c_void_p, C.c_int64]
+        L.fr_roster_remove_user.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
+        L.fr_roster_clear.argtypes = [C.c_void_p]
+        L.fr_roster_user.restype = C.c_char_p
+        L.fr_roster_user.argtypes = [C.c_void_p, C.c_int64]
+        h = C.c_void_p()
+        check(L.fr_roster_create(local_shard._h if local_shard is not None else None, world, rank, C.byref(h)))
+        self._h, self.world, self.rank, self._keep = h, world, rank, local_shard
+
+    @property
+    def rows(self) -> int:
+        return int(lib().fr_roster_rows(self._h))
+
+    def shard_rows(self, shard: int) -> int:
+        return int(lib().fr_roster_shard_rows(self._h, shard))
+
+    def load(self, user_ids, blobs) -> None:
+        """rows of `SELECT * FROM FACE`: user_ids = USR_ID strings, blobs = EMBEDDING bytes objects (512 x f32 LE)"""
+        n = len(user_ids)
+        ids = (C.c_char_p * n)(*[u.encode() for u in user_ids])
+        keep = [bytes(b) for b in blobs]
+        ptrs = (C.c_void_p * n)(*[C.cast(C.c_char_p(b), C.c_void_p) for b in keep])
+        sizes = (C.c_int * n)(*[len(b) for b in keep])
+        check(lib().fr_roster_load(self._h, ids, ptrs, sizes, n))
+
+    def add(self, user_id: str, embedding) -> int:
+        e = _f32(embedding)
+        out = C.c_int64()
+        check(lib().fr_roster_add(self._h, user_id.encode(), _ptr(e), C.byref(out)))
+        return out.value
+
+    def remove(self, row_id: int) -> None:
+        check(lib().fr_roster_remove(self._h, row_id))
+
+    def remove_user(self, user_id: str) -> int:
+        n = C.c_int64()
+        check(lib().fr_roster_remove_user(self._h, user_id.encode(), C.byref(n)))
+        return n.value
+
+    def clear(self) -> None:
+        check(lib().fr_roster_clear(self._h))
+
+    def user(self, row_id: int):
+        u = lib().fr_roster_user(self._h, int(row_id))
+        return u.decode() if u is not None else None
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_roster_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SearchStream:
     """fr_search_stream_*: asynchronous host-buffer search with two batches in flight (the serving form of search_topk)"""
 

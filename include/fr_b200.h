@@ -70,8 +70,9 @@ int fr_gallery_create_dev(const float *rows_dev, int64_t n, int dim, int device,
 int fr_gallery_create_synthetic(int64_t n, int dim, uint64_t seed, int device, int64_t row_offset, FrGallery **out);
 void fr_gallery_destroy(FrGallery *g);
 int64_t fr_gallery_rows(const FrGallery *g);
-/* CUDA device the gallery (shard) lives on */
+/* CUDA device the gallery (shard) lives on; global row id of its local row 0 */
 int fr_gallery_device(const FrGallery *g);
+int64_t fr_gallery_row_offset(const FrGallery *g);
 /* copy rows [first, first+count) (f32) back to the host — test hook */
 int fr_gallery_read_rows(FrGallery *g, int64_t first, int64_t count, float *out_rows);
 
@@ -92,6 +93,30 @@ int fr_gallery_update(FrGallery *g, int64_t first, const float *rows, int64_t n)
 int fr_gallery_remove(FrGallery *g, int64_t row, int64_t *moved_from);
 int fr_gallery_clear(FrGallery *g);
 int64_t fr_gallery_capacity(const FrGallery *g);
+
+/* ---- Roster: the reference's row -> userId table (ArcFaceIR50::classNames, src/arcface.h:38-40) kept in step with a row-SHARDED
+ * gallery, so that enrolment, deletion and /reload (src/db.cpp:316-346, src/arcface.cpp:150-164,233-236, src/app.cpp:131-217,354-365)
+ * are incremental updates of the resident shards. SPMD: every rank owns one shard (a gallery created EMPTY with row_offset =
+ * rank << 32) and applies the same sequence of calls; the name table of all shards is replicated, device work touches the local
+ * shard only, no communication. Global row id = (shard << 32) | local row — exactly what the search / exchange return.
+ *   load         n FACE rows in `SELECT * FROM FACE` (rowid) order: user_ids[i] = USR_ID, blobs[i] = EMBEDDING (512 x f32 LE = 2048
+ *                bytes, else FR_EFORMAT); contiguous blocks, shard 0 first; replaces what was resident
+ *   add          one row to the least-loaded shard (addEmbedding); *out_id = its global id
+ *   remove       one row / every row of a user (move-last-row inside the shard, mirrored in the table)
+ *   clear        resetEmbeddings
+ *   user         classNames[argmax] (src/arcface.cpp:212); NULL for ids that name no resident row
+ * local_shard may be NULL (bookkeeping only). */
+typedef struct FrRoster FrRoster;
+int fr_roster_create(FrGallery *local_shard, int world, int rank, FrRoster **out);
+void fr_roster_destroy(FrRoster *r);
+int64_t fr_roster_rows(const FrRoster *r);
+int64_t fr_roster_shard_rows(const FrRoster *r, int shard);
+int fr_roster_load(FrRoster *r, const char *const *user_ids, const void *const *blobs, const int *blob_bytes, int64_t n);
+int fr_roster_add(FrRoster *r, const char *user_id, const float *embedding, int64_t *out_id);
+int fr_roster_remove(FrRoster *r, int64_t id);
+int fr_roster_remove_user(FrRoster *r, const char *user_id, int64_t *removed);
+int fr_roster_clear(FrRoster *r);
+const char *fr_roster_user(const FrRoster *r, int64_t id);
 
 /* MatMul::calculate (src/matmul.cpp:36-77): out[i*n_rows + j] = <q_i, row_j>, exact fp32
  * (CUDA_R_32F / CUBLAS_COMPUTE_32F, src/matmul.h:24-25). q: nq x dim host f32; out: nq x n_rows host f32. */

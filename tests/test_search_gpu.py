@@ -679,3 +679,121 @@ def test_gallery_starts_empty_then_appends():
     _check_topk(s, i, so.sims(G, q), 1)
     assert i[:, 0].tolist() == [5, 2999, 1234]
     g.close()
+
+
+def test_roster_lifecycle_on_sharded_gallery(tmp_path):
+    # SURVEY 8 f-2 on the device: FACE rows from an SQLite file with the reference's schema -> 3 shards (row_offset = shard << 32),
+    # searched shard by shard and merged; after every enrolment / deletion / reload the identities the sharded search returns equal
+    # those of a host model of the same rows, and the roster resolves the returned global ids to the right userId.
+    import sqlite3
+
+    rng = np.random.default_rng(12)
+    n, world = 3000, 3
+    emb = so.l2_normalise(rng.standard_normal((n, 512))).astype("<f4")
+    users = [f"u{int(u):04d}" for u in rng.integers(0, n // 2, n)]
+    con = sqlite3.connect(tmp_path / "face.db")
+    con.execute("CREATE TABLE FACE (IMG_ID INTEGER PRIMARY KEY AUTOINCREMENT, USR_ID TEXT, IMG_PATH TEXT, EMBEDDING BLOB, UNIQUE(IMG_ID, USR_ID))")
+    con.executemany("INSERT INTO FACE (USR_ID, IMG_PATH, EMBEDDING) VALUES (?, ?, ?)", [(u, "x.jpg", e.tobytes()) for u, e in zip(users, emb)])
+    con.commit()
+    rows = con.execute("SELECT * FROM FACE").fetchall()
+    con.close()
+    shards = [frb200.Gallery.from_rows(np.zeros((0, 512), np.float32), row_offset=g << 32) for g in range(world)]
+    for sh in shards:
+        sh.set_path(frb200.FR_PATH_EXACT)            # shards of ~1000 rows: the exact path (AUTO would choose it as well)
+    rosters = [frb200.Roster(shards[g], world, g) for g in range(world)]
+    model = {}                                        # global id -> (user, vector): host model of what is resident
+
+    def reload_model():
+        model.clear()
+        per = (n + world - 1) // world
+        for i in range(n):
+            model[((i // per) << 32) | (i % per)] = (users[i], emb[i])
+
+    def check(nq=40):
+        ids = sorted(model)
+        M = np.stack([model[i][1] for i in ids])
+        pick = rng.integers(0, len(ids), nq)
+        q = so.planted_queries(M[pick], 0.5, int(rng.integers(1 << 30)))
+        parts_s, parts_i = [], []
+        for sh in shards:
+            if sh.rows:
+                s_, i_ = sh.topk(q, 1)
+            else:
+                s_, i_ = np.full((nq, 1), -np.inf, np.float32), np.full((nq, 1), -1, np.int64)
+            parts_s.append(s_)
+            parts_i.append(i_)
+        ms, mi = so.merge_topk(parts_s, parts_i, 1)
+        assert [int(v) for v in mi[:, 0]] == [ids[p] for p in pick]
+        for ro in rosters:
+            assert [ro.user(int(v)) for v in mi[:, 0]] == [model[ids[p]][0] for p in pick]
+        assert sum(sh.rows for sh in shards) == len(model) == rosters[0].rows
+
+    for ro in rosters:
+        ro.load([r[1] for r in rows], [r[3] for r in rows])
+    reload_model()
+    check()
+    for j in range(5):                                # enrolment
+        v = so.l2_normalise(rng.standard_normal((1, 512)))[0]
+        got = {ro.add(f"new{j}", v) for ro in rosters}
+        assert len(got) == 1
+        model[got.pop()] = (f"new{j}", v)
+    check()
+    for _ in range(6):                                # deletion of single rows: the shard's last row moves into the slot
+        gid = sorted(model)[int(rng.integers(0, len(model)))]
+        shard = gid >> 32
+        last = max(i for i in model if i >> 32 == shard)
+        for ro in rosters:
+            ro.remove(gid)
+        model[gid] = model[last]
+        del model[last]
+    check()
+    victim = users[17]                                # deletion of a user
+    cnt = {ro.remove_user(victim) for ro in rosters}
+    assert cnt == {sum(1 for u, _ in model.values() if u == victim)}
+    ids_after = {}
+    for g in range(world):                            # rebuild the model from the rosters' tables + the shards' rows
+        R = shards[g].read_rows(0, shards[g].rows) if shards[g].rows else np.zeros((0, 512), np.float32)
+        for l in range(rosters[0].shard_rows(g)):
+            ids_after[(g << 32) | l] = (rosters[0].user((g << 32) | l), R[l])
+    assert victim not in {u for u, _ in ids_after.values()}
+    model.clear()
+    model.update(ids_after)
+    check()
+    for ro in rosters:                                # /reload: reset + read everything again
+        ro.load([r[1] for r in rows], [r[3] for r in rows])
+    reload_model()
+    check()
+    for o in rosters + shards:
+        o.close()
+
+
+@pytest.mark.parametrize("scan", [frb200.FR_SCAN_F16, frb200.FR_SCAN_F8])
+def test_search_stream_two_batches_in_flight(scan):
+    # fr_search_stream_*: the asynchronous host-buffer search (bench.py's e2e). Results come back in submission order, equal to the
+    # synchronous call, with up to two batches in flight; a third submit / an empty collect are refused.
+    rng = np.random.default_rng(44)
+    n = 80_000
+    G = so.l2_normalise(rng.standard_normal((n, 512)))
+    g = frb200.Gallery.from_rows(G, row_offset=5)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    g.set_scan(scan)
+    ss = frb200.SearchStream(g, None, 1)
+    batches = [so.planted_queries(G[rng.integers(0, n, nq)], 0.7, b) for b, nq in enumerate((256, 100, 256, 1, 37))]
+    want = [g.topk(q, 1) for q in batches]
+    s_out, i_out = np.empty((256, 1), np.float32), np.empty((256, 1), np.int64)
+    with pytest.raises(frb200.FrError):
+        ss.collect(s_out, i_out)
+    ss.submit(batches[0])
+    ss.submit(batches[1])
+    with pytest.raises(frb200.FrError) as e:
+        ss.submit(batches[2])
+    assert e.value.code == frb200.FR_ESTATE
+    for b in range(len(batches)):
+        nq = ss.collect(s_out, i_out)
+        assert nq == batches[b].shape[0]
+        assert np.array_equal(i_out[:nq], want[b][1]) and np.array_equal(s_out[:nq].view(np.uint32), want[b][0].view(np.uint32))
+        if b + 2 < len(batches):
+            batches[b + 2][:] = batches[b + 2]           # the caller's buffer is free again as soon as submit returns
+            ss.submit(batches[b + 2])
+    ss.close()
+    g.close()
