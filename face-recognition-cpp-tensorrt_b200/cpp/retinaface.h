@@ -41,7 +41,11 @@ class RetinaFace {
 
     // preprocess + doInference + postprocessing (src/retinaface.cpp:147-152); returns a copy like the reference
     std::vector<struct Bbox> findFace(cv::Mat &img) {
-        assert(img.rows == m_frameHeight && img.cols == m_frameWidth && img.type() == CV_8UC3);
+        // The reference's preprocess resizes whatever it is given (src/retinaface.cpp:106-125) with the scales fixed at construction;
+        // a frame of another size would be letterboxed wrongly there and read out of bounds here, so it is refused in every build
+        // type (an assert would vanish under NDEBUG).
+        if (img.empty() || img.rows != m_frameHeight || img.cols != m_frameWidth || img.type() != CV_8UC3)
+            throw std::logic_error("RetinaFace::findFace: frame must be CV_8UC3 of the input_frameWidth x input_frameHeight given to the constructor");
         int count = 0;
         frCheck(fr_detector_run(m_detector, img.data, static_cast<int>(img.step), 1, reinterpret_cast<FrBbox *>(m_boxes.data()), &count, nullptr));
         m_outputBbox.assign(m_boxes.begin(), m_boxes.begin() + count);

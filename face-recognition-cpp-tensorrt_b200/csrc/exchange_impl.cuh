@@ -266,7 +266,7 @@ int fr_gallery_topk_push_dev(FrGallery* g, FrExchange* x, const float* q_dev, in
             return;
         }
         g->first_chunk = true;
-        if (g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows)) {
+        if (g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows) || (g->scan == FR_SCAN_F16 && !g->f16_ok)) {
             // exact fp32 scan (tiny shards, FR_PATH_EXACT): no re-rank kernel to fuse with; deliver with the stand-alone push
             topk_chunk(g, q_dev, nq, k, local_scores_dev, reinterpret_cast<long long*>(local_idx_dev), st);
             exchange_push_kernel<<<nq, 64, 0, st>>>(make_push(x), nq, k, local_scores_dev, reinterpret_cast<const long long*>(local_idx_dev));

@@ -26,6 +26,8 @@ struct FrGallery {
     __half* rows_f16 = nullptr;
     uint8_t* rows_f8 = nullptr;       // optional e4m3 scan copy (FR_SCAN_F8), 512 B / row
     float* gmax = nullptr;
+    float* amax = nullptr;            // largest |component| of any row
+    bool f16_ok = true;               // rows fit fp16's normal range (amax <= 65504, gmax >= kF16MinNorm): else searches take the exact scan
     float* g4max = nullptr;           // largest sum of fourth powers of a row (set with the e4m3 copy): scales the fp8 margin
     float* w4max = nullptr;           // largest sum of fourth powers of a row's e4m3 rounding steps (same)
     uint64_t f8_seed = 0x5EEDF8B200ull;  // dither stream of the stochastic e4m3 rounding (FR_F8_SEED overrides)
@@ -103,6 +105,8 @@ void alloc_common(FrGallery* g) {
     FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
     FRB_CUDA(cudaMalloc(&g->g4max, sizeof(float)));
     FRB_CUDA(cudaMemsetAsync(g->g4max, 0, sizeof(float), g->stream));
+    FRB_CUDA(cudaMalloc(&g->amax, sizeof(float)));
+    FRB_CUDA(cudaMemsetAsync(g->amax, 0, sizeof(float), g->stream));
     FRB_CUDA(cudaMalloc(&g->w4max, sizeof(float)));
     FRB_CUDA(cudaMemsetAsync(g->w4max, 0, sizeof(float), g->stream));
 }
@@ -130,14 +134,23 @@ FrGallery* new_gallery(int64_t n, int dim, int device, int64_t row_offset) {
     return g;
 }
 
+// the fp16 scan copy's error bound needs rows in fp16's normal range (search_kernels.cuh, kF16MinNorm); the caller has synchronised
+void refresh_f16_ok(FrGallery* g) {
+    float b[2] = {0.f, 0.f};
+    FRB_CUDA(cudaMemcpy(&b[0], g->gmax, sizeof(float), cudaMemcpyDeviceToHost));
+    FRB_CUDA(cudaMemcpy(&b[1], g->amax, sizeof(float), cudaMemcpyDeviceToHost));
+    g->f16_ok = g->n == 0 || (b[1] <= 65504.f && b[0] >= kF16MinNorm);
+}
+
 // fp16 scan copy (unless the generator already wrote it) + largest row norm
 void finish_rows(FrGallery* g, bool write_f16) {
     if (g->n == 0) return;
     const int blocks = static_cast<int>(std::min<int64_t>((g->n + 7) / 8, g->sms * 16LL));
-    make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, write_f16 ? g->rows_f16 : nullptr, g->n, g->gmax);
+    make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(g->rows_f32, write_f16 ? g->rows_f16 : nullptr, g->n, g->gmax, g->amax);
     count_launch();
     FRB_CUDA(cudaGetLastError());
     FRB_CUDA(cudaStreamSynchronize(g->stream));
+    refresh_f16_ok(g);
 }
 
 // tensor maps follow the row count (rows past n are TMA zero fill) and the buffers' base addresses
@@ -275,7 +288,8 @@ void launch_exact(FrGallery* g, const float* q_dev, int nq, int k, const int* fl
 
 // one chunk (nq <= 256) of queries already on the device; results to scores_dev / idx_dev (device, nq x k)
 void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_dev, long long* idx_dev, cudaStream_t st) {
-    const bool exact = g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows);
+    // rows outside fp16's normal range void the fp16 copy's error bound (and the e4m3 copy only ever holds unit rows): exact scan
+    const bool exact = g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows) || (g->scan == FR_SCAN_F16 && !g->f16_ok);
     g->stats = FrSearchStats{};
     if (exact) {
         if (g->first_chunk) FRB_CUDA(cudaMemsetAsync(g->flagged_acc, 0, sizeof(int), st));  // nothing is ever flagged on this path
@@ -431,6 +445,7 @@ void fr_gallery_destroy(FrGallery* g) {
     cudaFree(g->rows_f8);
     cudaFree(g->gmax);
     cudaFree(g->g4max);
+    cudaFree(g->amax);
     cudaFree(g->w4max);
     cudaFree(g->q_gap);
     cudaFree(g->flagged_acc);
@@ -525,7 +540,7 @@ int fr_gallery_append(FrGallery* g, const float* rows, int64_t n) {
         FRB_CUDA(cudaMemcpyAsync(dst, rows, sizeof(float) * n * kDim, cudaMemcpyHostToDevice, g->stream));
         const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, g->sms * 16LL));
         // scan copies of the new rows only; gmax / g4max are running maxima (atomicMax), so they stay upper bounds
-        make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f16 + g->n * kDim, n, g->gmax);
+        make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f16 + g->n * kDim, n, g->gmax, g->amax);
         count_launch();
         if (g->rows_f8) {
             make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f8 + g->n * kDim, n, g->f8_seed, g->row_offset + g->n, g->g4max, g->w4max);
@@ -534,6 +549,7 @@ int fr_gallery_append(FrGallery* g, const float* rows, int64_t n) {
         FRB_CUDA(cudaGetLastError());
         FRB_CUDA(cudaStreamSynchronize(g->stream));
         g->n += n;
+        refresh_f16_ok(g);
         refresh_tmaps(g);
     });
 }
@@ -551,7 +567,7 @@ int fr_gallery_update(FrGallery* g, int64_t first, const float* rows, int64_t n)
         FRB_CUDA(cudaMemcpyAsync(dst, rows, sizeof(float) * n * kDim, cudaMemcpyHostToDevice, g->stream));
         const int blocks = static_cast<int>(std::min<int64_t>((n + 7) / 8, g->sms * 16LL));
         // the bounds (gmax, g4max, w4max) are running maxima: they keep the replaced rows' contribution and stay upper bounds
-        make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f16 + first * kDim, n, g->gmax);
+        make_scan_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f16 + first * kDim, n, g->gmax, g->amax);
         count_launch();
         if (g->rows_f8) {
             make_f8_copy_kernel<<<blocks, 256, 0, g->stream>>>(dst, g->rows_f8 + first * kDim, n, g->f8_seed, g->row_offset + first, g->g4max, g->w4max);
@@ -559,6 +575,7 @@ int fr_gallery_update(FrGallery* g, int64_t first, const float* rows, int64_t n)
         }
         FRB_CUDA(cudaGetLastError());
         FRB_CUDA(cudaStreamSynchronize(g->stream));
+        refresh_f16_ok(g);
     });
 }
 
@@ -591,7 +608,9 @@ int fr_gallery_clear(FrGallery* g) {
         FRB_CUDA(cudaMemsetAsync(g->gmax, 0, sizeof(float), g->stream));
         FRB_CUDA(cudaMemsetAsync(g->g4max, 0, sizeof(float), g->stream));
         FRB_CUDA(cudaMemsetAsync(g->w4max, 0, sizeof(float), g->stream));
+        FRB_CUDA(cudaMemsetAsync(g->amax, 0, sizeof(float), g->stream));
         FRB_CUDA(cudaStreamSynchronize(g->stream));
+        g->f16_ok = true;
     });
 }
 

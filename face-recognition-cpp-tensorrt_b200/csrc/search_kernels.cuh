@@ -40,6 +40,11 @@ constexpr int kLdCols = 16;                          // accumulator columns per 
 // |coarse - exact| <= kCoarseEps * |q| * |row|: fp16 round-to-nearest of both operands (2 * 2^-11) plus the tensor core's fp32
 // accumulation, bounded through Cauchy-Schwarz. Candidates within 2 eps of the k-th best coarse score are re-scored exactly.
 constexpr float kCoarseEps = 1.25e-3f;
+// ... which holds while operands stay in fp16's normal range. Subnormal components carry an ABSOLUTE error of 2^-25 each, i.e. up to
+// sqrt(512) 2^-25 |other operand| per score; that stays inside kCoarseEps |q| |g| while the norm is >= sqrt(512) 2^-25 / kCoarseEps =
+// 5.4e-4. Galleries whose largest row norm is below kF16MinNorm (or with a component beyond 65504) are searched by the exact fp32 scan,
+// such queries are recomputed by it.
+constexpr float kF16MinNorm = 1e-3f;
 
 // fp8 (e4m3) scan copy: rows and queries are multiplied by kF8Scale before the conversion (unit-norm components ~0.044 land in
 // e4m3's normal range), accumulators are kF8Scale^2 x the cosine. Round-to-nearest e4m3 has no useful error bound (2^-4 per operand
@@ -1176,10 +1181,19 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float* __restri
             q_gap[r] = sat ? -INFINITY : kF8GapFrac * E;
         }
     } else {  // scale = kCoarseEps: provable margin 2 eps |q| gmax
-        const float m = 2.f * scale * sqrtf(dot512(a, a)) * __ldg(gmax_ptr);
+        const float qn = sqrtf(dot512(a, a));
+        const float m = 2.f * scale * qn * __ldg(gmax_ptr);
+        // the bound assumes fp16's NORMAL range: a query component beyond 65504 (inf in the operand image) or a query so small that its
+        // components are fp16 subnormals (absolute error 2^-25 each instead of relative 2^-11) voids it -> always recomputed exactly
+        float cm = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cm = fmaxf(fmaxf(cm, fmaxf(fabsf(a[i].x), fabsf(a[i].y))), fmaxf(fabsf(a[i].z), fabsf(a[i].w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+        const bool ok = cm <= 65504.f && (qn >= kF16MinNorm || qn == 0.f) && qn == qn;
         if (lane == 0) {
             q_margin[r] = r < nq ? m : 0.f;
-            q_gap[r] = INFINITY;
+            q_gap[r] = (ok || r >= nq) ? INFINITY : -INFINITY;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1219,11 +1233,12 @@ __global__ void __launch_bounds__(256) make_f8_copy_kernel(const float* __restri
 }
 
 // scan copy + largest row norm (the margin of the coarse pass scales with it). One warp per row.
+// amax: largest |component| (the fp16 copy is only valid while it stays below 65504, checked by the host side).
 __global__ void __launch_bounds__(256) make_scan_copy_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n,
-                                                             float* __restrict__ gmax) {
+                                                             float* __restrict__ gmax, float* __restrict__ amax) {
     const int lane = threadIdx.x & 31;
     const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-    float wmax = 0.f;
+    float wmax = 0.f, cmax = 0.f;
     for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps) {
         float4 a[4];
         load512(src + static_cast<size_t>(r) * kDim, lane, a);
@@ -1238,9 +1253,12 @@ __global__ void __launch_bounds__(256) make_scan_copy_kernel(const float* __rest
             }
         }
         wmax = fmaxf(wmax, dot512(a, a));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(a[i].x), fabsf(a[i].y))), fmaxf(fabsf(a[i].z), fabsf(a[i].w)));
     }
-    // non-negative floats order like their bit patterns
+    // non-negative floats order like their bit patterns (a NaN / inf component ends up above every finite value: refused by the host)
     if (lane == 0 && wmax > 0.f) atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(sqrtf(wmax) * 1.0000002f));
+    if (amax && !(cmax == 0.f)) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(fabsf(cmax)));
 }
 
 }  // namespace frb

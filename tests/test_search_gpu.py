@@ -797,3 +797,33 @@ def test_search_stream_two_batches_in_flight(scan):
             ss.submit(batches[b + 2])
     ss.close()
     g.close()
+
+
+def test_rows_and_queries_outside_fp16_range_take_the_exact_scan():
+    # the reference's MatMul accepts arbitrary fp32 rows; the fp16 scan copy's bound only holds in fp16's normal range.
+    # Huge components (inf in fp16) or a gallery of tiny rows (fp16 subnormals) must still give the exact fp32 answer.
+    rng = np.random.default_rng(6)
+    n = 30_000
+    G = rng.standard_normal((n, 512)).astype(np.float32)
+    q = rng.standard_normal((16, 512)).astype(np.float32)
+    for scale in (1e5, 1e-6):
+        g = frb200.Gallery.from_rows(G * np.float32(scale))
+        g.set_path(frb200.FR_PATH_TENSOR)
+        s, i = g.topk(q, 3)
+        sim = so.sims(G * np.float32(scale), q)
+        o_s, o_i = so.topk(sim, 3)
+        assert np.array_equal(i, o_i) and np.allclose(s, o_s, rtol=2e-5)
+        assert g.last_stats().ctas == 0                      # the exact path ran (no fused-scan CTAs)
+        g.close()
+    # an ordinary gallery, extraordinary queries: recomputed by the exact scan one by one
+    Gn = so.l2_normalise(G)
+    g = frb200.Gallery.from_rows(Gn)
+    g.set_path(frb200.FR_PATH_TENSOR)
+    qq = so.l2_normalise(q).astype(np.float32)
+    qq[3] *= np.float32(1e-7)
+    qq[5] *= np.float32(3e5)
+    s, i = g.topk(qq, 1)
+    o_i, o_s = so.get_outputs(so.sims(Gn, qq))
+    assert np.array_equal(i[:, 0], o_i) and np.allclose(s[:, 0], o_s, rtol=2e-5)
+    assert g.last_flagged() == 2
+    g.close()
