@@ -821,7 +821,7 @@ def test_rows_and_queries_outside_fp16_range_take_the_exact_scan():
     g.set_path(frb200.FR_PATH_TENSOR)
     qq = so.l2_normalise(q).astype(np.float32)
     qq[3] *= np.float32(1e-7)
-    qq[5] *= np.float32(3e5)
+    qq[5] *= np.float32(3e6)
     s, i = g.topk(qq, 1)
     o_i, o_s = so.get_outputs(so.sims(Gn, qq))
     assert np.array_equal(i[:, 0], o_i) and np.allclose(s[:, 0], o_s, rtol=2e-5)
