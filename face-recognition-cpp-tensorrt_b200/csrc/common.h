@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler attaches (tracing)
+
 #include "../../include/fr_b200.h"
 
 namespace frb {
@@ -19,6 +21,14 @@ namespace frb {
 void set_error(const std::string& msg);
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+// NVTX range over a stage of the hot path (host-side scope: what nsys / ncu --nvtx show as detect / crop / embed / search / exchange)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct CudaError {
     std::string msg;

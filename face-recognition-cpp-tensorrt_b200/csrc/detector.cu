@@ -255,6 +255,7 @@ inline int blocks_for(long long threads, int per_block) { return static_cast<int
 
 // network: canvas (u8, net size) or preprocessed f32 planar input -> loc / conf / landm on the device
 void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const float* chw_dev, int batch, cudaStream_t st) {
+    NvtxRange nvtx("fr.detect.network");
     const Geo g1 = d->g[1];
     const long long px = static_cast<long long>(batch) * g1.H * g1.W;
     if (canvas_dev) det_stem_kernel<<<blocks_for(px, 256), 256, 0, st>>>(canvas_dev, stride_bytes, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
@@ -305,6 +306,7 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
 // slot0: results of image i go to result slot slot0 + i (the pipeline detects a large batch in sub-batches while later frames are
 // still in flight over PCIe)
 void run_post(FrDetector* d, const float* loc, const float* conf, const float* landm, int batch, cudaStream_t st, int slot0 = 0) {
+    NvtxRange nvtx("fr.detect.decode_nms");
     DetPostParams p;
     p.net_w = d->net_w;
     p.net_h = d->net_h;

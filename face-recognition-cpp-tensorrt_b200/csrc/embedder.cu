@@ -231,6 +231,7 @@ void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cud
 
 // complete forward, replayed from a CUDA graph per (batch, input kind)
 void forward_all(FrEmbedder* e, int batch, bool u8_input, cudaStream_t st = nullptr) {
+    NvtxRange nvtx("fr.embed.forward");
     if (!st) st = e->stream;
     e->graphs.run({static_cast<uint64_t>(batch), u8_input ? 1ull : 0ull, 0ull}, st, [&] { run_steps(e, batch, u8_input, kRunAll, st); });
 }

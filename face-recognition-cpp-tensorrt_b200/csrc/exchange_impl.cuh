@@ -141,6 +141,7 @@ void check_step(const FrExchange* x, int nq, int k) {
     if (nq < 1 || nq > x->nq_max || k < 1 || k > x->k_max) throw ArgError{"nq/k exceed the exchange's capacity"};
 }
 void launch_wait_merge(FrExchange* x, int nq, int k, float* scores_dev, long long* idx_dev, cudaStream_t st) {
+    NvtxRange nvtx("fr.exchange.wait_merge");
     exchange_wait_merge_kernel<<<nq, 64, 0, st>>>(x->peers, x->world, x->rank, x->nq_max, x->k_max, k, x->state_dev, x->timeout_ns, scores_dev, idx_dev);
     count_launch();
     FRB_CUDA(cudaGetLastError());

@@ -288,6 +288,7 @@ void launch_exact(FrGallery* g, const float* q_dev, int nq, int k, const int* fl
 
 // one chunk (nq <= 256) of queries already on the device; results to scores_dev / idx_dev (device, nq x k)
 void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_dev, long long* idx_dev, cudaStream_t st) {
+    NvtxRange nvtx("fr.search.topk");
     // rows outside fp16's normal range void the fp16 copy's error bound (and the e4m3 copy only ever holds unit rows): exact scan
     const bool exact = g->path == FR_PATH_EXACT || (g->path == FR_PATH_AUTO && g->n < kExactMaxRows) || (g->scan == FR_SCAN_F16 && !g->f16_ok);
     g->stats = FrSearchStats{};

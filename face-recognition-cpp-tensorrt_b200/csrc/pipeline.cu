@@ -186,6 +186,7 @@ void crop_into_embedder(FrPipeline* p, const uint8_t* frames_dev, int stride, co
 }
 
 void embed_chunk(FrPipeline* p, const uint8_t* frames_dev, int stride, int beg, int m, cudaStream_t st) {
+    NvtxRange nvtx("fr.pipeline.crop_embed");
     crop_into_embedder(p, frames_dev, stride, p->faces_dev, p->n_dev, beg, m, st);
     embedder_forward_u8(p->emb, m, st);
     FRB_CUDA(cudaMemcpyAsync(p->embeds_dev + static_cast<size_t>(beg) * 512, embedder_output(p->emb), sizeof(float) * m * 512,
@@ -194,6 +195,7 @@ void embed_chunk(FrPipeline* p, const uint8_t* frames_dev, int stride, int beg, 
 
 // frames: host. Fills the pinned host arrays of the pipeline; returns the number of faces.
 int run_batch(FrPipeline* p, const uint8_t* frames, int stride, int batch, float* embeddings_host) {
+    NvtxRange nvtx("fr.pipeline.batch");
     cudaStream_t st = p->stream, cs = p->copy_stream;
     uint8_t* fdev = detector_frames_buffer(p->det);
     const size_t row_bytes = static_cast<size_t>(p->frame_w) * 3, frame_bytes = row_bytes * p->frame_h;
