@@ -210,12 +210,20 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     count_launch();
     std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
     std::pair<cudaEvent_t, cudaEvent_t> fixed;
+    // inside a stream capture a plain cudaEventRecord only orders captured work; cudaEventRecordExternal makes it an event-record NODE,
+    // so every replay of the graph records (and times) the events for real
+    unsigned int ev_flags = cudaEventRecordDefault;
+    if (g->timing || g->timing_fixed) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        FRB_CUDA(cudaStreamIsCapturing(st, &cs));
+        if (cs == cudaStreamCaptureStatusActive) ev_flags = cudaEventRecordExternal;
+    }
     if (g->timing_fixed) {
         for (int j = 0; j < 2; ++j)
             if (!g->fixed_ev[F8][j]) FRB_CUDA(cudaEventCreate(&g->fixed_ev[F8][j]));
         fixed = {g->fixed_ev[F8][0], g->fixed_ev[F8][1]};
         ev = &fixed;
-        FRB_CUDA(cudaEventRecord(ev->first, st));
+        FRB_CUDA(cudaEventRecordWithFlags(ev->first, st, ev_flags));
     } else if (g->timing) {
         if (g->ev_used == g->ev_pool.size()) {
             cudaEvent_t a, b;
@@ -224,7 +232,7 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
             g->ev_pool.emplace_back(a, b);
         }
         ev = &g->ev_pool[g->ev_used++];
-        FRB_CUDA(cudaEventRecord(ev->first, st));
+        FRB_CUDA(cudaEventRecordWithFlags(ev->first, st, ev_flags));
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(units * CG);
@@ -248,7 +256,7 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
                                 static_cast<const float*>(g->q_margin), nq, static_cast<long long>(g->n), tiles, g->cand_s, g->cand_i, g->flags,
                                 g->gbest, g->app_buf, g->app_cnt));
     count_launch();
-    if (ev) FRB_CUDA(cudaEventRecord(ev->second, st));
+    if (ev) FRB_CUDA(cudaEventRecordWithFlags(ev->second, st, ev_flags));
 }
 
 void ensure_sims_ws(FrGallery* g, size_t floats) {

@@ -704,7 +704,9 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
     }
     // certificate of the e4m3 scan (see kF8LogP): the k-th best EXACT score must not fall more than the gap below the k-th best
     // coarse score, else a pruned row could belong to the top-k with probability > p. (+inf gap on the fp16 copy: always passes.)
-    if (threadIdx.x == 0 && sel_s[k - 1] < ck - __ldg(q_gap + qi)) overflow = 1;
+    // (a gap of -inf marks a query whose operand image is outside the scan copy's range: always recomputed, even when its coarse
+    // scores were NaN and nothing was kept)
+    if (threadIdx.x == 0 && (__ldg(q_gap + qi) == -INFINITY || sel_s[k - 1] < ck - __ldg(q_gap + qi))) overflow = 1;
     if (threadIdx.x == 0 && overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
     if (threadIdx.x == 0) gbest[qi] = 0;  // ready for the next search (0 = nothing published)
     if (push.enabled) {  // deliver this query to every peer now, unless the exact scan is going to recompute (and deliver) it
@@ -855,7 +857,8 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
         out_i[qi] = bi >= 0 ? bi + row_offset : -1;
         // certificate of the e4m3 scan (see kF8LogP): accept only if the best exact score is within the gap of the best coarse score;
         // then a pruned true best would need a rounding error beyond E. (+inf gap on the fp16 copy: always passes.)
-        if (bi >= 0 && bs < ck - __ldg(q_gap + qi)) overflow = 1;
+        // (a gap of -inf marks a query outside the scan copy's range: always recomputed, even if its coarse scores were NaN)
+        if (__ldg(q_gap + qi) == -INFINITY || (bi >= 0 && bs < ck - __ldg(q_gap + qi))) overflow = 1;
         if (overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
         gbest[qi] = 0;  // ready for the next search
         x_s[0] = bi >= 0 ? bs : -INFINITY;
