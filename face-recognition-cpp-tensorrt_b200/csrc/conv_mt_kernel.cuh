@@ -1,0 +1,323 @@
+// 3x3 stride-1 convolution on tcgen05, PERSISTENT, HALO-REUSING, MULTI-TILE (the body convs of ArcFace IR-(SE)50:
+// /root/reference conversion/arcface/model_irse.py:48-90). Same activation layout, tensor maps, parameters and epilogue arithmetic as
+// conv_gemm_kernel (conv_kernels.cuh); what changes is how the operands reach the tensor core:
+//
+//   * conv_gemm_kernel fetches, per 64-channel k-block, one [128 x 64] activation box AND one [BN x 64] weight box for 4 MMAs: at
+//     BN = 128 that is 32 KiB of L2 -> SM traffic per 256 tensor cycles = 128 B/cycle/SM, three times what the L2 delivers
+//     (~6300 B/cycle chip-wide = 42.5 B/cycle/SM): the kernel is L2-bound at a third of the tensor peak (measured 0.4-1.0 PFLOP/s).
+//   * here one work unit is MT adjacent 128-position tiles x BN channels. Per 64-channel block ONE halo tile (the MT*128 positions plus
+//     a row and a column of neighbours on each side) is fetched and all nine taps of all MT tiles are row-shifted UMMA descriptors
+//     into it; each weight box feeds MT*4 MMAs. BN = 128, MT = 2: (16 + 5.3) KiB per 512 tensor cycles = 43 B/cycle/SM.
+//     With 64 -> 64 channels the nine weight boxes (72 KiB) stay resident for the whole kernel (weight-stationary).
+//   * persistent: grid = min(units, SMs); two TMEM accumulator sets are ping-ponged so the epilogue of unit i (8 warps) overlaps the
+//     MMAs of unit i + 1; halo tiles are double buffered, weights stream through a ring.
+//   * optional SE pooling: per 32-position group the epilogue also writes the exact (fixed-point) channel sums of the conv output
+//     (warp shuffle tree), which se_gate_apply_kernel reduces per image - the separate pooling pass over the map disappears.
+#pragma once
+#include "conv_kernels.cuh"
+
+namespace frb {
+
+constexpr int kMtThreads = 128 + 8 * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int kMtMaxStages = 12;
+constexpr int kMtParamBytes = 4 * 512 * 4;  // bias, prelu, bn_s, bn_b for up to 512 output channels
+
+// The nine taps of a 64-channel block are organised in GROUPS that share one halo tile:
+//   stride 1: one group, halo tile = matrix rows p0 - Wp - 1 ... of the input, tap (dy, dx) starts dy*Wp + dx rows in;
+//   stride 2 (phase-split input, see conv_kernels.cuh): one group per phase map (1 + 2 + 2 + 4 taps), halo tile = rows
+//   p0 - Wp - 1 ... of that phase map, tap (dy, dx) starts Wp + 1 - (dy == 0 ? Wp : 0) - (dx == 0 ? 1 : 0) rows in.
+struct MtGroup {
+    int row0;    // the halo tile starts at matrix row p0 + row0
+    int ntaps;
+    int tap[4 + 5];  // weight tap index (dy*3 + dx)
+    int off[4 + 5];  // operand start row inside the halo tile
+};
+struct ConvMtExtra {
+    int units;        // ceil(P / (MT*128)) * (cout / BN)
+    int n_blocks;     // cout / BN
+    int stages;       // weight ring depth (<= kMtMaxStages)
+    int halo_chunks;  // 128-row boxes per halo tile
+    int stationary;   // 1: stride 1, cin_blocks == 1 && n_blocks == 1 && stages >= 9: weights loaded once per CTA
+    int ngroups;      // 1 (stride 1) or 4 (stride 2)
+    MtGroup grp[4];
+};
+
+// shared-memory bytes of one CTA
+inline int conv_mt_smem_bytes(int BN, int halo_chunks, int stages) {
+    return 1024 + 2 * halo_chunks * kConvBM * 128 + stages * BN * 128 + 512 + kMtParamBytes;
+}
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(kMtThreads, 1)
+conv3x3_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ ConvGemmParams prm, const __grid_constant__ ConvMtExtra ex) {
+    constexpr int kABytes = kConvBM * 128, kBBytes = BN * 128;
+    constexpr uint32_t kTmemCols = 2 * MT * BN;  // two accumulator sets
+    static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    // [2 halo tiles][weight ring][barriers][epilogue parameters of all cout channels]
+    const int halo_bytes = ex.halo_chunks * kABytes;
+    uint8_t* ring = smem + 2 * halo_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + ex.stages * kBBytes);
+    uint64_t* empty_bar = full_bar + kMtMaxStages;
+    uint64_t* hfull_bar = empty_bar + kMtMaxStages;  // [2] halo tile landed
+    uint64_t* hempty_bar = hfull_bar + 2;             // [2] halo tile consumed by all its MMAs
+    uint64_t* tfull_bar = hempty_bar + 2;             // [2] accumulator set complete
+    uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator set read out by the eight epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(ring + ex.stages * kBBytes + 512);
+    float* s_prelu = s_bias + 512;
+    float* s_bns = s_prelu + 512;
+    float* s_bnb = s_bns + 512;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int Wp = prm.W + 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kMtMaxStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&hfull_bar[b], 1);
+            mbar_init(&hempty_bar[b], 1);
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 8);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp >= 4) {
+        for (int i = threadIdx.x - 128; i < prm.cout; i += kMtThreads - 128) {
+            s_bias[i] = prm.bias ? __ldg(prm.bias + i) : 0.f;
+            s_prelu[i] = prm.prelu ? __ldg(prm.prelu + i) : 1.f;
+            s_bns[i] = prm.out_bn ? __ldg(prm.bn_s + i) : 1.f;
+            s_bnb[i] = prm.out_bn ? __ldg(prm.bn_b + i) : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0, hb = 0, hph = 0;
+            bool first = true;
+            for (int u = blockIdx.x; u < ex.units; u += gridDim.x) {
+                const int pt = u / ex.n_blocks, nb = u - pt * ex.n_blocks;
+                const int p0 = pt * (MT * kConvBM), n0 = nb * BN;
+                for (int cb = 0; cb < prm.cin_blocks; ++cb) {
+                    for (int g = 0; g < ex.ngroups; ++g) {
+                        const MtGroup& G = ex.grp[g];
+                        mbar_wait(&hempty_bar[hb], hph ^ 1);
+                        mbar_expect_tx(&hfull_bar[hb], halo_bytes);
+                        for (int ch = 0; ch < ex.halo_chunks; ++ch)
+                            tma_load_2d(smem + hb * halo_bytes + ch * kABytes, &tmap_a, &hfull_bar[hb], cb * 64, p0 + G.row0 + ch * kConvBM, kEvictNormal);
+                        if (++hb == 2) {
+                            hb = 0;
+                            hph ^= 1;
+                        }
+                        if (ex.stationary && !first) continue;
+                        for (int t = 0; t < G.ntaps; ++t) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            mbar_expect_tx(&full_bar[stage], kBBytes);
+                            tma_load_2d(ring + stage * kBBytes, &tmap_b, &full_bar[stage], (G.tap[t] * prm.cin_blocks + cb) * 64, n0, kEvictLast);
+                            if (++stage == static_cast<uint32_t>(ex.stages)) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                }
+                first = false;
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc(kConvBM, BN, 0, 0);
+            uint32_t stage = 0, phase = 0, hb = 0, hph = 0;
+            bool first = true;
+            int i = 0;
+            for (int u = blockIdx.x; u < ex.units; u += gridDim.x, ++i) {
+                const uint32_t buf = i & 1;
+                mbar_wait(&tempty_bar[buf], ((i >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * (MT * BN);
+                uint32_t acc = 0;  // 0 for the very first MMA into each accumulator of this unit
+                for (int cb = 0; cb < prm.cin_blocks; ++cb) {
+                    for (int g = 0; g < ex.ngroups; ++g) {
+                        const MtGroup& G = ex.grp[g];
+                        mbar_wait(&hfull_bar[hb], hph);
+                        tc_fence_after();
+                        const uint32_t halo_addr = smem_u32(smem + hb * halo_bytes);
+#pragma unroll 1
+                        for (int t = 0; t < G.ntaps; ++t) {
+                            if (!ex.stationary || first) {
+                                mbar_wait(&full_bar[stage], phase);
+                                tc_fence_after();
+                            }
+                            const uint32_t b_addr = smem_u32(ring + stage * kBBytes);
+                            // the tap's operand for tile m = 128 consecutive rows of the halo tile starting m*128 + off rows in (the swizzle acts
+                            // on absolute shared-memory address bits, so a 128-byte-row offset needs no descriptor base offset: measured)
+                            const uint32_t a_tap = halo_addr + static_cast<uint32_t>(G.off[t]) * 128u;
+#pragma unroll
+                            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f16_ss(d_tmem + m * BN, umma_desc_sw128(a_tap + m * kABytes + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                                (acc | k) ? 1u : 0u);
+                            }
+                            acc = 1;
+                            if (!ex.stationary) umma_commit(&empty_bar[stage]);
+                            if (++stage == static_cast<uint32_t>(ex.stages)) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                        umma_commit(&hempty_bar[hb]);
+                        if (++hb == 2) {
+                            hb = 0;
+                            hph ^= 1;
+                        }
+                    }
+                }
+                umma_commit(&tfull_bar[buf]);
+                first = false;
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue: lane = output position; warps 4-7 / 8-11 split the unit ----------------
+        const int ew = warp & 3;          // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;  // MT == 2: tile of the unit; MT == 1: column half
+        const int m = MT == 2 ? half : 0;
+        constexpr int kCols = MT == 2 ? BN : BN / 2;  // columns this warp handles
+        const int c0 = MT == 2 ? 0 : half * (BN / 2);
+        const int HpWp = (prm.H + 1) * Wp;
+        const int ldo = prm.ld_out ? prm.ld_out : prm.cout;
+        const int ldr = prm.ld_res ? prm.ld_res : prm.cout;
+        int i = 0;
+        for (int u = blockIdx.x; u < ex.units; u += gridDim.x, ++i) {
+            const uint32_t buf = i & 1;
+            const int pt = u / ex.n_blocks, nb = u - pt * ex.n_blocks;
+            const int n0 = nb * BN + c0;
+            const int pw = pt * (MT * kConvBM) + m * kConvBM + ew * 32;  // first position of this warp
+            const int p = pw + lane;
+            const int img = p / HpWp;
+            const int rem = p - img * HpWp;
+            const int r = rem / Wp;
+            const int c = rem - r * Wp;
+            const bool valid = p < prm.P && r < prm.H && c < prm.W;
+            size_t o_main = 0, o_sub = 0, o_res = 0;
+            bool sub_ok = false;
+            if (valid) {
+                if (prm.out_mode == kOutPhaseSplit) {
+                    const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                    const int phs = ((r & 1) << 1) | (c & 1);
+                    o_main = static_cast<size_t>(phs) * prm.out_phase_rows + static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
+                } else {
+                    o_main = static_cast<size_t>(p);
+                }
+                if (prm.out_sub && !(r & 1) && !(c & 1)) {
+                    const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                    o_sub = static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
+                    sub_ok = true;
+                }
+                if (prm.res_mode == kResSame) {
+                    o_res = static_cast<size_t>(p);
+                } else if (prm.res_mode == kResSubsample) {
+                    const int W2p = 2 * prm.W + 1, H2pW2p = (2 * prm.H + 1) * W2p;
+                    o_res = static_cast<size_t>(img) * H2pW2p + (2 * r) * W2p + 2 * c;
+                } else if (prm.res_mode == kResUpsample) {
+                    const int Wh = (prm.W >> 1) + 1, HhWh = ((prm.H >> 1) + 1) * Wh;
+                    o_res = static_cast<size_t>(img) * HhWh + (r >> 1) * Wh + (c >> 1);
+                }
+            }
+            const int img_w0 = pw / HpWp;
+            const bool straddles = (pw + 31) / HpWp != img_w0;
+            // the residual row of this position is fetched while the tensor pipe is still busy with this unit
+            uint4 resv[kCols / 8];
+            if (valid && prm.res_mode != kResNone) {
+                const uint4* rp = reinterpret_cast<const uint4*>(prm.res + o_res * ldr + n0);
+#pragma unroll
+                for (int j = 0; j < kCols / 8; j += 2) ld_global_nc_256(rp + j, resv[j], resv[j + 1]);
+            }
+            mbar_wait(&tfull_bar[buf], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * (MT * BN) + m * BN + c0;
+#pragma unroll
+            for (int cc = 0; cc < kCols; cc += 16) {
+                uint32_t raw[16];
+                tmem_ld_32x32b_x16(taddr + cc, raw);
+                tmem_ld_wait_x16(raw);
+                const int n = n0 + cc;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + s_bias[n + j];
+                if (prm.prelu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * s_prelu[n + j];
+                }
+                if (prm.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (prm.pool)  // warp-uniform: every lane takes part in the shuffles
+                    pool_store16(prm.pool, prm.cout, pw >> 5, n, v, valid, lane, straddles, img == img_w0);
+                if (!valid) continue;
+                if (prm.res_mode != kResNone) {
+                    const uint4 r0 = resv[cc / 8], r1 = resv[cc / 8 + 1];
+                    const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                    const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+                        v[2 * j] += a.x;
+                        v[2 * j + 1] += a.y;
+                        v[8 + 2 * j] += b.x;
+                        v[8 + 2 * j + 1] += b.y;
+                    }
+                }
+                uint4 pk[2];
+                __half2* hp = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hp[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                if (prm.out) {
+                    st_global_256(prm.out + o_main * ldo + n, pk[0], pk[1]);
+                }
+                if (sub_ok) {
+                    st_global_256(prm.out_sub + o_sub * ldo + n, pk[0], pk[1]);
+                }
+                if (prm.out_bn) {
+                    // the stored (fp16-rounded) value is what the next unit's shortcut sees; its BN input is the same value
+                    uint4 pb[2];
+                    __half2* hb2 = reinterpret_cast<__half2*>(pb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 y = __half22float2(hp[j]);
+                        hb2[j] = __floats2half2_rn(fmaf(y.x, s_bns[n + 2 * j], s_bnb[n + 2 * j]), fmaf(y.y, s_bns[n + 2 * j + 1], s_bnb[n + 2 * j + 1]));
+                    }
+                    st_global_256(prm.out_bn + o_main * ldo + n, pb[0], pb[1]);
+                }
+            }
+            // every tcgen05.ld of this warp has completed (tmem_ld_wait_x16 above): hand the accumulator set back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace frb

@@ -10,6 +10,7 @@
 #include <cstdint>
 
 #include "../../include/fr_b200.h"
+#include "ptx_sm100.cuh"
 
 namespace frb {
 
@@ -204,77 +205,113 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __half* __restrict__ i
     *reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * go.HpWp() + r * go.Wp() + c) * C + ch) = pk;
 }
 
-// ---- pointwise 1x1 + BN + ReLU for the early layers with fewer than 64 input channels (second half of conv_dw).
-//      One thread per pixel, all COUT outputs in registers. w: [CIN][COUT] f32.
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(128) pw_small_kernel(const __half* __restrict__ in, __half* __restrict__ out, Geo g, int batch,
-                                                       const float* __restrict__ w, const float* __restrict__ bias) {
-    __shared__ float4 ws[CIN][COUT / 4];
-    __shared__ float sb[COUT];
-    for (int i = threadIdx.x; i < CIN * COUT; i += blockDim.x) reinterpret_cast<float*>(&ws[0][0])[i] = w[i];
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+// ---- FUSED conv_dw block for the early layers (net.py:29-38): depthwise 3x3 (stride S, pad 1) + BN + ReLU, then pointwise 1x1 +
+//      BN + ReLU, CIN < 64. One thread per output pixel: the nine taps come straight from global memory through L1 (neighbouring
+//      pixels share them), the depthwise result stays in registers (fp32, never written to global memory) and feeds the CIN -> COUT
+//      pointwise product, whose weights are broadcast from shared memory. Grid-stride: the weights are staged once per CTA.
+//      Compared with dw3x3_kernel + pw_small_kernel this removes the write + re-read of the depthwise map and one launch per block.
+//      dw_w: [9][CIN] f32, pw_w: [CIN][COUT] f32.
+template <int CIN, int COUT, int S>
+__global__ void __launch_bounds__(256) dwpw_small_kernel(const __half* __restrict__ in, Geo gi, __half* __restrict__ out, Geo go, int batch,
+                                                         const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                         const float* __restrict__ pw_w, const float* __restrict__ pw_b) {
+    __shared__ float sdw[9][CIN];
+    __shared__ float sdb[CIN];
+    __shared__ float4 spw[CIN][COUT / 4];
+    __shared__ float spb[COUT];
+    for (int i = threadIdx.x; i < 9 * CIN; i += blockDim.x) reinterpret_cast<float*>(&sdw[0][0])[i] = dw_w[i];
+    for (int i = threadIdx.x; i < CIN * COUT; i += blockDim.x) reinterpret_cast<float*>(&spw[0][0])[i] = pw_w[i];
+    for (int i = threadIdx.x; i < CIN; i += blockDim.x) sdb[i] = dw_b[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) spb[i] = pw_b[i];
     __syncthreads();
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= static_cast<long long>(batch) * g.H * g.W) return;
-    const int img = static_cast<int>(t / (g.H * g.W));
-    const int rc = static_cast<int>(t - static_cast<long long>(img) * g.H * g.W);
-    const size_t pos = static_cast<size_t>(img) * g.HpWp() + (rc / g.W) * g.Wp() + rc % g.W;
-    float x[CIN];
+    const long long total = static_cast<long long>(batch) * go.H * go.W;
+    for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int img = static_cast<int>(t / (go.H * go.W));
+        const int rc = static_cast<int>(t - static_cast<long long>(img) * go.H * go.W);
+        const int r = rc / go.W, c = rc - r * go.W;
+        float x[CIN];
 #pragma unroll
-    for (int i = 0; i < CIN / 8; ++i) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + pos * CIN) + i);
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
+        for (int k = 0; k < CIN; ++k) x[k] = sdb[k];
+        const __half* ibase = in + static_cast<size_t>(img) * gi.HpWp() * CIN;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h[j]);
-            x[i * 8 + 2 * j] = f.x;
-            x[i * 8 + 2 * j + 1] = f.y;
-        }
-    }
-#pragma unroll 1
-    for (int n0 = 0; n0 < COUT; n0 += 16) {
-        float acc[16];
+        for (int ky = 0; ky < 3; ++ky) {
+            const int rr = r * S + ky - 1;
+            if (rr < 0) continue;  // rr == gi.H is the zero pad row
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = sb[n0 + j];
+            for (int kx = 0; kx < 3; ++kx) {
+                const int cc = c * S + kx - 1;
+                if (cc < 0) continue;  // cc == gi.W is the zero pad column
+                const uint4* src = reinterpret_cast<const uint4*>(ibase + (static_cast<size_t>(rr) * gi.Wp() + cc) * CIN);
 #pragma unroll
-        for (int k = 0; k < CIN; ++k) {
+                for (int ch = 0; ch < CIN / 8; ++ch) {
+                    const uint4 v = __ldg(src + ch);
+                    const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 wv = ws[k][n0 / 4 + j4];
-                acc[4 * j4 + 0] = fmaf(x[k], wv.x, acc[4 * j4 + 0]);
-                acc[4 * j4 + 1] = fmaf(x[k], wv.y, acc[4 * j4 + 1]);
-                acc[4 * j4 + 2] = fmaf(x[k], wv.z, acc[4 * j4 + 2]);
-                acc[4 * j4 + 3] = fmaf(x[k], wv.w, acc[4 * j4 + 3]);
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = __half22float2(h[q]);
+                        x[ch * 8 + 2 * q] = fmaf(f.x, sdw[ky * 3 + kx][ch * 8 + 2 * q], x[ch * 8 + 2 * q]);
+                        x[ch * 8 + 2 * q + 1] = fmaf(f.y, sdw[ky * 3 + kx][ch * 8 + 2 * q + 1], x[ch * 8 + 2 * q + 1]);
+                    }
+                }
             }
         }
-        uint4 pk[2];
-        __half2* hp = reinterpret_cast<__half2*>(pk);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) hp[j] = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-        uint4* dst = reinterpret_cast<uint4*>(out + pos * COUT + n0);
-        dst[0] = pk[0];
-        dst[1] = pk[1];
+        for (int k = 0; k < CIN; ++k) x[k] = fmaxf(x[k], 0.f);
+        __half* dst_px = out + (static_cast<size_t>(img) * go.HpWp() + static_cast<size_t>(r) * go.Wp() + c) * COUT;
+#pragma unroll 1
+        for (int n0 = 0; n0 < COUT; n0 += 16) {
+            float acc[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] = spb[n0 + q];
+#pragma unroll
+            for (int k = 0; k < CIN; ++k) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 wv = spw[k][n0 / 4 + j4];
+                    acc[4 * j4 + 0] = fmaf(x[k], wv.x, acc[4 * j4 + 0]);
+                    acc[4 * j4 + 1] = fmaf(x[k], wv.y, acc[4 * j4 + 1]);
+                    acc[4 * j4 + 2] = fmaf(x[k], wv.z, acc[4 * j4 + 2]);
+                    acc[4 * j4 + 3] = fmaf(x[k], wv.w, acc[4 * j4 + 3]);
+                }
+            }
+            uint4 pk[2];
+            __half2* hp = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hp[q] = __floats2half2_rn(fmaxf(acc[2 * q], 0.f), fmaxf(acc[2 * q + 1], 0.f));
+            st_global_256(dst_px + n0, pk[0], pk[1]);
+        }
     }
 }
 
 // ---- SSH 16 -> 16 3x3 conv + BN + ReLU (conv5X5_2, conv7X7_2, conv7x7_3, net.py:49-53; the ReLU is either the layer's own or
 //      the one applied to the concatenation, net.py:64-65). w: [9][16][16] f32 (tap, cin, cout). Output may be a channel slice
-//      of a wider map (ld_out, pre-offset pointer).
-__global__ void __launch_bounds__(128) conv3x3_c16_kernel(const __half* __restrict__ in, __half* __restrict__ out, int ld_out, Geo g,
-                                                          int batch, const float* __restrict__ w, const float* __restrict__ bias) {
-    __shared__ float4 ws[9 * 16][4];
-    __shared__ float sb[16];
-    for (int i = threadIdx.x; i < 9 * 16 * 16; i += blockDim.x) reinterpret_cast<float*>(&ws[0][0])[i] = w[i];
-    if (threadIdx.x < 16) sb[threadIdx.x] = bias[threadIdx.x];
+//      of a wider map (ld_out, pre-offset pointer). NCONV = 2: conv5X5_2 and conv7X7_2 read the same map (net.py:58-61), so one
+//      pass over it computes both (second weight set wB, second destination outB).
+template <int NCONV>
+__global__ void __launch_bounds__(128) conv3x3_c16_kernel(const __half* __restrict__ in, Geo g, int batch, const float* __restrict__ wA,
+                                                          const float* __restrict__ bA, __half* __restrict__ outA, int ldA,
+                                                          const float* __restrict__ wB, const float* __restrict__ bB,
+                                                          __half* __restrict__ outB, int ldB) {
+    constexpr int NO = 16 * NCONV;
+    __shared__ float4 ws[9 * 16][NO / 4];
+    __shared__ float sb[NO];
+    for (int i = threadIdx.x; i < 9 * 16 * 16; i += blockDim.x) {
+        reinterpret_cast<float*>(&ws[i / 16][0])[i % 16] = wA[i];
+        if (NCONV == 2) reinterpret_cast<float*>(&ws[i / 16][0])[16 + i % 16] = wB[i];
+    }
+    if (threadIdx.x < 16) {
+        sb[threadIdx.x] = bA[threadIdx.x];
+        if (NCONV == 2) sb[16 + threadIdx.x] = bB[threadIdx.x];
+    }
     __syncthreads();
     const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= static_cast<long long>(batch) * g.H * g.W) return;
     const int img = static_cast<int>(t / (g.H * g.W));
     const int rc = static_cast<int>(t - static_cast<long long>(img) * g.H * g.W);
     const int r = rc / g.W, c = rc % g.W;
-    float acc[16];
+    float acc[NO];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = sb[j];
+    for (int j = 0; j < NO; ++j) acc[j] = sb[j];
     const __half* ibase = in + static_cast<size_t>(img) * g.HpWp() * 16;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -301,7 +338,7 @@ __global__ void __launch_bounds__(128) conv3x3_c16_kernel(const __half* __restri
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
+                for (int j4 = 0; j4 < NO / 4; ++j4) {
                     const float4 wv = ws[tap * 16 + k][j4];
                     acc[4 * j4 + 0] = fmaf(x[k], wv.x, acc[4 * j4 + 0]);
                     acc[4 * j4 + 1] = fmaf(x[k], wv.y, acc[4 * j4 + 1]);
@@ -311,45 +348,14 @@ __global__ void __launch_bounds__(128) conv3x3_c16_kernel(const __half* __restri
             }
         }
     }
-    uint4 pk[2];
-    __half2* hp = reinterpret_cast<__half2*>(pk);
+    const size_t pos = static_cast<size_t>(img) * g.HpWp() + r * g.Wp() + c;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) hp[j] = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * g.HpWp() + r * g.Wp() + c) * ld_out);
-    dst[0] = pk[0];
-    dst[1] = pk[1];
-}
-
-// ---- heads: the three 1x1 head convs of a level were computed as one 64 -> 32 GEMM (fp32, no bias) into head[P][32]:
-//      channels 0-7 BboxHead (anchor*4 + k), 8-11 ClassHead (anchor*2 + class), 12-31 LandmarkHead (anchor*10 + k).
-//      This kernel adds the bias, applies the 2-way softmax (retinaface_trim.py:123-127) and scatters into the anchor-major
-//      outputs of RetinaFace.forward: permute(0,2,3,1).view(B,-1,k), levels concatenated (retinaface_trim.py:31-35,119-121).
-__global__ void __launch_bounds__(256) det_heads_kernel(const float* __restrict__ head, const float* __restrict__ bias, Geo g, int batch,
-                                                        int anchors_total, int level_offset, float* __restrict__ loc,
-                                                        float* __restrict__ conf, float* __restrict__ landm) {
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= static_cast<long long>(batch) * g.H * g.W * 2) return;
-    const int l = static_cast<int>(t & 1);
-    const long long cell = t >> 1;
-    const int img = static_cast<int>(cell / (g.H * g.W));
-    const int rc = static_cast<int>(cell - static_cast<long long>(img) * g.H * g.W);
-    const size_t pos = static_cast<size_t>(img) * g.HpWp() + (rc / g.W) * g.Wp() + rc % g.W;
-    const float* h = head + pos * 32;
-    const size_t a = static_cast<size_t>(img) * anchors_total + level_offset + rc * 2 + l;
-    float4 b4;
-    b4.x = h[l * 4 + 0] + bias[l * 4 + 0];
-    b4.y = h[l * 4 + 1] + bias[l * 4 + 1];
-    b4.z = h[l * 4 + 2] + bias[l * 4 + 2];
-    b4.w = h[l * 4 + 3] + bias[l * 4 + 3];
-    *reinterpret_cast<float4*>(loc + a * 4) = b4;
-    const float z0 = h[8 + l * 2] + bias[8 + l * 2], z1 = h[8 + l * 2 + 1] + bias[8 + l * 2 + 1];
-    const float m = fmaxf(z0, z1);
-    const float e0 = expf(z0 - m), e1 = expf(z1 - m);
-    const float inv = 1.f / (e0 + e1);
-    *reinterpret_cast<float2*>(conf + a * 2) = make_float2(e0 * inv, e1 * inv);
-    if (landm) {
+    for (int q = 0; q < NCONV; ++q) {
+        uint4 pk[2];
+        __half2* hp = reinterpret_cast<__half2*>(pk);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) landm[a * 10 + k] = h[12 + l * 10 + k] + bias[12 + l * 10 + k];
+        for (int j = 0; j < 8; ++j) hp[j] = __floats2half2_rn(fmaxf(acc[q * 16 + 2 * j], 0.f), fmaxf(acc[q * 16 + 2 * j + 1], 0.f));
+        st_global_256(q == 0 ? outA + pos * ldA : outB + pos * ldB, pk[0], pk[1]);
     }
 }
 
@@ -397,59 +403,74 @@ __device__ __forceinline__ void anchor_of(int id, int net_w, int net_h, float& c
 
 __device__ __forceinline__ int clipi(int a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
 
-__global__ void __launch_bounds__(256) det_decode_nms_kernel(const float* __restrict__ loc, const float* __restrict__ conf,
-                                                             const float* __restrict__ landm, DetPostParams prm, DetCand* __restrict__ ws,
-                                                             FrBbox* __restrict__ boxes, int* __restrict__ counts,
-                                                             float* __restrict__ out_landm, int* __restrict__ out_ids) {
-    __shared__ int n_cand;
+// decode of one anchor that passed the threshold (src/retinaface.cpp:163-200)
+__device__ __forceinline__ DetCand decode_candidate(const float4 b, float score, int a, const DetPostParams& prm, float scale_h, float scale_w) {
+    float cx, cy, sx, sy;
+    anchor_of(a, prm.net_w, prm.net_h, cx, cy, sx, sy);
+    const float tcx = static_cast<float>(__dadd_rn(static_cast<double>(cx), __dmul_rn(__dmul_rn(static_cast<double>(b.x), 0.1), static_cast<double>(sx))));
+    const float tcy = static_cast<float>(__dadd_rn(static_cast<double>(cy), __dmul_rn(__dmul_rn(static_cast<double>(b.y), 0.1), static_cast<double>(sy))));
+    const float tsx = static_cast<float>(__dmul_rn(static_cast<double>(sx), exp(__dmul_rn(static_cast<double>(b.z), 0.2))));
+    const float tsy = static_cast<float>(__dmul_rn(static_cast<double>(sy), exp(__dmul_rn(static_cast<double>(b.w), 0.2))));
+    const float hx = __fdiv_rn(tsx, 2.f), hy = __fdiv_rn(tsy, 2.f);
+    int y1 = static_cast<int>(__fmul_rn(__fsub_rn(tcx, hx), static_cast<float>(prm.net_w)));  // :171-174
+    int x1 = static_cast<int>(__fmul_rn(__fsub_rn(tcy, hy), static_cast<float>(prm.net_h)));
+    int y2 = static_cast<int>(__fmul_rn(__fadd_rn(tcx, hx), static_cast<float>(prm.net_w)));
+    int x2 = static_cast<int>(__fmul_rn(__fadd_rn(tcy, hy), static_cast<float>(prm.net_h)));
+    if (scale_h > scale_w) {  // :177-187
+        const float pad = __fdiv_rn(__fsub_rn(static_cast<float>(prm.net_h), __fmul_rn(scale_w, static_cast<float>(prm.frame_h))), 2.f);
+        y1 = static_cast<int>(__fdiv_rn(static_cast<float>(y1), scale_w));
+        y2 = static_cast<int>(__fdiv_rn(static_cast<float>(y2), scale_w));
+        x1 = static_cast<int>(__fdiv_rn(__fsub_rn(static_cast<float>(x1), pad), scale_w));
+        x2 = static_cast<int>(__fdiv_rn(__fsub_rn(static_cast<float>(x2), pad), scale_w));
+    } else {
+        const float pad = __fdiv_rn(__fsub_rn(static_cast<float>(prm.net_w), __fmul_rn(scale_h, static_cast<float>(prm.frame_w))), 2.f);
+        y1 = static_cast<int>(__fdiv_rn(__fsub_rn(static_cast<float>(y1), pad), scale_h));
+        y2 = static_cast<int>(__fdiv_rn(__fsub_rn(static_cast<float>(y2), pad), scale_h));
+        x1 = static_cast<int>(__fdiv_rn(static_cast<float>(x1), scale_h));
+        x2 = static_cast<int>(__fdiv_rn(static_cast<float>(x2), scale_h));
+    }
+    DetCand d;
+    d.y1 = clipi(y1, 0, prm.frame_w - 1);  // :190-193
+    d.x1 = clipi(x1, 0, prm.frame_h - 1);
+    d.y2 = clipi(y2, 0, prm.frame_w - 1);
+    d.x2 = clipi(x2, 0, prm.frame_h - 1);
+    d.score = score;
+    d.id = a;
+    return d;
+}
+
+// stage 1, grid (ceil(anchors / 256), batch): threshold + decode, one thread per anchor; survivors are appended to the image's
+// candidate list (order irrelevant: the NMS below picks by (score, anchor id)). n_cand[img] must be zero on entry; det_nms_kernel
+// leaves it zero again.
+__global__ void __launch_bounds__(256) det_decode_kernel(const float* __restrict__ loc, const float* __restrict__ conf, DetPostParams prm,
+                                                         DetCand* __restrict__ ws, int* __restrict__ n_cand) {
+    const int img = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= prm.anchors) return;
+    const float score = conf[(static_cast<size_t>(img) * prm.anchors + a) * 2 + 1];
+    if (!(score > prm.bbox_thr)) return;  // strict >, :160
+    const float scale_h = __fdiv_rn(static_cast<float>(prm.net_h), static_cast<float>(prm.frame_h));  // :21
+    const float scale_w = __fdiv_rn(static_cast<float>(prm.net_w), static_cast<float>(prm.frame_w));  // :22
+    const float4 b = *reinterpret_cast<const float4*>(loc + (static_cast<size_t>(img) * prm.anchors + a) * 4);
+    ws[static_cast<size_t>(img) * prm.anchors + atomicAdd(&n_cand[img], 1)] = decode_candidate(b, score, a, prm, scale_h, scale_w);
+}
+
+// stage 2, one block per image: greedy NMS over the image's candidates
+__global__ void __launch_bounds__(256) det_nms_kernel(const float* __restrict__ landm, DetPostParams prm, DetCand* __restrict__ ws,
+                                                      int* __restrict__ n_cand_g, FrBbox* __restrict__ boxes, int* __restrict__ counts,
+                                                      float* __restrict__ out_landm, int* __restrict__ out_ids) {
     __shared__ float red_s[8];
     __shared__ int red_i[8], red_p[8];
     __shared__ DetCand kept;
     __shared__ int kept_pos;
+    __shared__ int n_cand;
     const int img = blockIdx.x;
-    const float* L = loc + static_cast<size_t>(img) * prm.anchors * 4;
-    const float* Cf = conf + static_cast<size_t>(img) * prm.anchors * 2;
     DetCand* cand = ws + static_cast<size_t>(img) * prm.anchors;
-    if (threadIdx.x == 0) n_cand = 0;
-    __syncthreads();
     const float scale_h = __fdiv_rn(static_cast<float>(prm.net_h), static_cast<float>(prm.frame_h));  // :21
     const float scale_w = __fdiv_rn(static_cast<float>(prm.net_w), static_cast<float>(prm.frame_w));  // :22
-    for (int a = threadIdx.x; a < prm.anchors; a += blockDim.x) {
-        const float score = Cf[a * 2 + 1];
-        if (!(score > prm.bbox_thr)) continue;  // strict >, :160
-        float cx, cy, sx, sy;
-        anchor_of(a, prm.net_w, prm.net_h, cx, cy, sx, sy);
-        const float4 b = *reinterpret_cast<const float4*>(L + a * 4);
-        const float tcx = static_cast<float>(__dadd_rn(static_cast<double>(cx), __dmul_rn(__dmul_rn(static_cast<double>(b.x), 0.1), static_cast<double>(sx))));
-        const float tcy = static_cast<float>(__dadd_rn(static_cast<double>(cy), __dmul_rn(__dmul_rn(static_cast<double>(b.y), 0.1), static_cast<double>(sy))));
-        const float tsx = static_cast<float>(__dmul_rn(static_cast<double>(sx), exp(__dmul_rn(static_cast<double>(b.z), 0.2))));
-        const float tsy = static_cast<float>(__dmul_rn(static_cast<double>(sy), exp(__dmul_rn(static_cast<double>(b.w), 0.2))));
-        const float hx = __fdiv_rn(tsx, 2.f), hy = __fdiv_rn(tsy, 2.f);
-        int y1 = static_cast<int>(__fmul_rn(__fsub_rn(tcx, hx), static_cast<float>(prm.net_w)));  // :171-174
-        int x1 = static_cast<int>(__fmul_rn(__fsub_rn(tcy, hy), static_cast<float>(prm.net_h)));
-        int y2 = static_cast<int>(__fmul_rn(__fadd_rn(tcx, hx), static_cast<float>(prm.net_w)));
-        int x2 = static_cast<int>(__fmul_rn(__fadd_rn(tcy, hy), static_cast<float>(prm.net_h)));
-        if (scale_h > scale_w) {  // :177-187
-            const float pad = __fdiv_rn(__fsub_rn(static_cast<float>(prm.net_h), __fmul_rn(scale_w, static_cast<float>(prm.frame_h))), 2.f);
-            y1 = static_cast<int>(__fdiv_rn(static_cast<float>(y1), scale_w));
-            y2 = static_cast<int>(__fdiv_rn(static_cast<float>(y2), scale_w));
-            x1 = static_cast<int>(__fdiv_rn(__fsub_rn(static_cast<float>(x1), pad), scale_w));
-            x2 = static_cast<int>(__fdiv_rn(__fsub_rn(static_cast<float>(x2), pad), scale_w));
-        } else {
-            const float pad = __fdiv_rn(__fsub_rn(static_cast<float>(prm.net_w), __fmul_rn(scale_h, static_cast<float>(prm.frame_w))), 2.f);
-            y1 = static_cast<int>(__fdiv_rn(__fsub_rn(static_cast<float>(y1), pad), scale_h));
-            y2 = static_cast<int>(__fdiv_rn(__fsub_rn(static_cast<float>(y2), pad), scale_h));
-            x1 = static_cast<int>(__fdiv_rn(static_cast<float>(x1), scale_h));
-            x2 = static_cast<int>(__fdiv_rn(static_cast<float>(x2), scale_h));
-        }
-        DetCand d;
-        d.y1 = clipi(y1, 0, prm.frame_w - 1);  // :190-193
-        d.x1 = clipi(x1, 0, prm.frame_h - 1);
-        d.y2 = clipi(y2, 0, prm.frame_w - 1);
-        d.x2 = clipi(x2, 0, prm.frame_h - 1);
-        d.score = score;
-        d.id = a;
-        cand[atomicAdd(&n_cand, 1)] = d;
+    if (threadIdx.x == 0) {
+        n_cand = n_cand_g[img];
+        n_cand_g[img] = 0;  // ready for the next batch
     }
     __syncthreads();
     const int n = n_cand;

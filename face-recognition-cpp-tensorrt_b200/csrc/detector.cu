@@ -7,6 +7,7 @@
 // -> bias + softmax + anchor-major scatter -> decode + NMS, one block per image. Convs with >= 64 input channels are
 // conv_gemm_kernel launches (tcgen05); the rest are the CUDA-core kernels of det_kernels.cuh.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -15,6 +16,7 @@
 #include "common.h"
 #include "conv_kernels.cuh"
 #include "det_kernels.cuh"
+#include "det_dwpw_gemm.cuh"
 #include "weights.h"
 
 using namespace frb;
@@ -29,7 +31,7 @@ struct DBuf {
     bool has_map = false;
 };
 
-enum StepKind { kDw, kPwSmall, kGemm, kC16, kHeads };
+enum StepKind { kDw, kDwPwSmall, kDwPwGemm, kGemm, kC16 };
 
 struct DStep {
     StepKind kind;
@@ -40,13 +42,17 @@ struct DStep {
     int stride = 1, cin = 0, cout = 0, ld_out = 0;
     const float* w = nullptr;
     const float* b = nullptr;
+    const float* w2 = nullptr;  // fused blocks: pointwise weights / bias; c16: second conv on the same input
+    const float* b2 = nullptr;
+    __half* out2 = nullptr;
+    int ld_out2 = 0;
     // gemm
     CUtensorMap ta{}, tb{};
     ConvGemmParams prm{};
     int bn = 64;
-    // heads
-    const float* head = nullptr;
-    int level_offset = 0;
+    bool heads = false;  // gemm: HEADS epilogue
+    int lane = 0;        // 0: main chain; 1, 2: side chains (SSH of level 3 / level 2) that only depend on what the main chain produced so far
+    DwPwGemmParams dp{};  // fused depthwise + pointwise GEMM (tb = pointwise weights)
 };
 
 }  // namespace
@@ -57,6 +63,8 @@ struct FrDetector {
     float nms_thr = 0.4f, bbox_thr = 0.6f;
     bool landmarks = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};      // side chains of the network (see build_plan)
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
     std::vector<void*> allocs;
     float *stem_w = nullptr, *stem_b = nullptr;
     uint8_t* frames_dev = nullptr;   // max_batch x frame_h x frame_w x 3
@@ -67,6 +75,7 @@ struct FrDetector {
     std::vector<DStep> steps;
     float *loc = nullptr, *conf = nullptr, *landm = nullptr;
     DetCand* cand = nullptr;
+    int* n_cand = nullptr;           // per image: candidates appended by det_decode_kernel (zero between batches)
     FrBbox* boxes = nullptr;
     int* counts = nullptr;
     float* out_landm = nullptr;
@@ -102,6 +111,19 @@ DBuf mkbuf(FrDetector* d, Geo g, int C) {
         b.has_map = true;
     }
     return b;
+}
+
+// FR_DET_LANES=0: the SSH blocks of levels 2 and 3 run in the main chain instead of as parallel graph branches (A/B)
+const bool g_det_lanes = std::getenv("FR_DET_LANES") == nullptr || std::atoi(std::getenv("FR_DET_LANES")) != 0;
+// FR_DET_FUSED_GEMM=0: conv_dw blocks with >= 64 input channels run as dw3x3_kernel + conv_gemm_kernel instead of dwpw_gemm_kernel (A/B)
+const bool g_fused_dwpw = std::getenv("FR_DET_FUSED_GEMM") != nullptr && std::atoi(std::getenv("FR_DET_FUSED_GEMM")) != 0;
+
+template <int BN>
+void launch_dwpw_gemm(const DStep& s, int batch, cudaStream_t st) {
+    DwPwGemmParams p = s.dp;
+    p.P = batch * s.go.HpWp();
+    dwpw_gemm_kernel<BN><<<(p.P + kConvBM - 1) / kConvBM, 256, DwPwGemmCfg<BN>::smem_bytes(p.cin), st>>>(s.tb, p);
+    count_launch();
 }
 
 void build_plan(FrDetector* d, const WeightFile& wf) {
@@ -155,32 +177,55 @@ void build_plan(FrDetector* d, const WeightFile& wf) {
     for (int n = 0; n < 13; ++n) {
         const std::string id = std::to_string(n + 1);
         if (dw_stride[n] == 2) ++level;
-        DBuf dwo = mkbuf(d, d->g[level], dw_cin[n]);
-        DStep s{};
-        s.kind = kDw;
-        s.in = cur.p;
-        s.out = dwo.p;
-        s.gi = cur.g;
-        s.go = dwo.g;
-        s.stride = dw_stride[n];
-        s.cin = dw_cin[n];
-        s.w = f32("dw" + id + ".w", 9 * dw_cin[n]);
-        s.b = f32("dw" + id + ".b", dw_cin[n]);
-        d->steps.push_back(s);
         DBuf pwo = mkbuf(d, d->g[level], dw_cout[n]);
-        if (dw_cin[n] >= 64) {
-            add_gemm(dwo, dw_cin[n], 1, dw_cout[n], "pw" + id + ".w", "pw" + id + ".b", true, pwo.p, 0, nullptr, kResNone, nullptr);
+        if (dw_cin[n] < 64) {
+            // fused depthwise + pointwise on CUDA cores (dwpw_small_kernel)
+            DStep s{};
+            s.kind = kDwPwSmall;
+            s.in = cur.p;
+            s.out = pwo.p;
+            s.gi = cur.g;
+            s.go = pwo.g;
+            s.stride = dw_stride[n];
+            s.cin = dw_cin[n];
+            s.cout = dw_cout[n];
+            s.w = f32("dw" + id + ".w", 9 * dw_cin[n]);
+            s.b = f32("dw" + id + ".b", dw_cin[n]);
+            s.w2 = f32("pw" + id + ".w", static_cast<int64_t>(dw_cin[n]) * dw_cout[n]);
+            s.b2 = f32("pw" + id + ".b", dw_cout[n]);
+            d->steps.push_back(s);
+        } else if (g_fused_dwpw) {
+            // fused depthwise (CUDA cores, straight into the tensor core's shared-memory operand) + pointwise GEMM (dwpw_gemm_kernel)
+            DStep s{};
+            s.kind = kDwPwGemm;
+            s.bn = dw_cout[n];
+            __half* w = f16("pw" + id + ".w", static_cast<int64_t>(dw_cout[n]) * dw_cin[n]);
+            s.tb = make_tmap_2d_f16(w, dw_cout[n], dw_cin[n], dw_cout[n], 64);
+            s.go = pwo.g;
+            s.dp.in = cur.p;
+            s.dp.gi = cur.g;
+            s.dp.go = pwo.g;
+            s.dp.stride = dw_stride[n];
+            s.dp.cin = dw_cin[n];
+            s.dp.dw_w = f32("dw" + id + ".w", 9 * dw_cin[n]);
+            s.dp.dw_b = f32("dw" + id + ".b", dw_cin[n]);
+            s.dp.pw_b = f32("pw" + id + ".b", dw_cout[n]);
+            s.dp.out = pwo.p;
+            d->steps.push_back(s);
         } else {
-            DStep p{};
-            p.kind = kPwSmall;
-            p.in = dwo.p;
-            p.out = pwo.p;
-            p.go = dwo.g;
-            p.cin = dw_cin[n];
-            p.cout = dw_cout[n];
-            p.w = f32("pw" + id + ".w", static_cast<int64_t>(dw_cin[n]) * dw_cout[n]);
-            p.b = f32("pw" + id + ".b", dw_cout[n]);
-            d->steps.push_back(p);
+            DBuf dwo = mkbuf(d, d->g[level], dw_cin[n]);
+            DStep s{};
+            s.kind = kDw;
+            s.in = cur.p;
+            s.out = dwo.p;
+            s.gi = cur.g;
+            s.go = dwo.g;
+            s.stride = dw_stride[n];
+            s.cin = dw_cin[n];
+            s.w = f32("dw" + id + ".w", 9 * dw_cin[n]);
+            s.b = f32("dw" + id + ".b", dw_cin[n]);
+            d->steps.push_back(s);
+            add_gemm(dwo, dw_cin[n], 1, dw_cout[n], "pw" + id + ".w", "pw" + id + ".b", true, pwo.p, 0, nullptr, kResNone, nullptr);
         }
         cur = pwo;
         if (n == 4) c1 = cur;
@@ -202,39 +247,109 @@ void build_plan(FrDetector* d, const WeightFile& wf) {
     d->landm = d->landmarks ? dalloc<float>(d, static_cast<size_t>(B) * d->anchors * 10, false) : nullptr;
     const DBuf* fpn[3] = {&o1, &o2, &o3};
     int level_offset = 0;
+    std::vector<DStep> ssh_steps[4];  // per level; spliced into the plan below
     for (int lvl = 1; lvl <= 3; ++lvl) {
+        const size_t first_step = d->steps.size();
         const DBuf& x = *fpn[lvl - 1];
         const std::string p = "ssh" + std::to_string(lvl) + ".";
         DBuf F = mkbuf(d, x.g, 64), T = mkbuf(d, x.g, 16), U = mkbuf(d, x.g, 16);
-        add_gemm(x, 64, 9, 32, p + "a.w", p + "a.b", true, F.p, 64, nullptr, kResNone, nullptr);
-        add_gemm(x, 64, 9, 16, p + "t.w", p + "t.b", true, T.p, 16, nullptr, kResNone, nullptr);
-        const char* names[3] = {"b", "u", "c"};
-        const __half* ins[3] = {T.p, T.p, U.p};
-        __half* outs[3] = {F.p + 32, U.p, F.p + 48};
-        const int lds[3] = {64, 16, 64};
-        for (int q = 0; q < 3; ++q) {
+        {   // conv3X3 (64 -> 32, into F[0:32]) and conv5X5_1 (64 -> 16, into T) read the same map: ONE 64 -> 48 GEMM with two destinations
             DStep s{};
-            s.kind = kC16;
-            s.in = ins[q];
-            s.out = outs[q];
-            s.ld_out = lds[q];
+            s.kind = kGemm;
+            s.bn = 48;
+            const HostTensor wa = wf.get(p + "a.w", 1, 32ll * 9 * 64), wt = wf.get(p + "t.w", 1, 16ll * 9 * 64);
+            const HostTensor ba = wf.get(p + "a.b", 0, 32), bt = wf.get(p + "t.b", 0, 16);
+            __half* w = dalloc<__half>(d, 48ull * 9 * 64, false);
+            float* b = dalloc<float>(d, 48, false);
+            FRB_CUDA(cudaMemcpyAsync(w, wa.data, wa.nbytes, cudaMemcpyHostToDevice, d->stream));
+            FRB_CUDA(cudaMemcpyAsync(w + 32ull * 9 * 64, wt.data, wt.nbytes, cudaMemcpyHostToDevice, d->stream));
+            FRB_CUDA(cudaMemcpyAsync(b, ba.data, ba.nbytes, cudaMemcpyHostToDevice, d->stream));
+            FRB_CUDA(cudaMemcpyAsync(b + 32, bt.data, bt.nbytes, cudaMemcpyHostToDevice, d->stream));
+            s.ta = x.tmap;
+            s.tb = make_tmap_2d_f16(w, 48, 9ull * 64, 48, 64);
             s.go = x.g;
-            s.w = f32(p + names[q] + ".w", 9 * 16 * 16);
-            s.b = f32(p + names[q] + ".b", 16);
+            s.prm.H = x.g.H;
+            s.prm.W = x.g.W;
+            s.prm.cin_blocks = 1;
+            s.prm.taps = 9;
+            s.prm.cout = 48;
+            s.prm.kb_per_split = 9;
+            s.prm.bias = b;
+            s.prm.relu = 1;
+            s.prm.out = F.p;
+            s.prm.ld_out = 64;
+            s.prm.out2 = T.p;
+            s.prm.out2_from = 32;
+            s.prm.ld_out2 = 16;
             d->steps.push_back(s);
         }
-        float* head = dalloc<float>(d, static_cast<size_t>(B) * x.g.HpWp() * 32, false);
-        add_gemm(F, 64, 1, 32, "head" + std::to_string(lvl) + ".w", "", false, nullptr, 0, nullptr, kResNone, head);
-        DStep h{};
-        h.kind = kHeads;
-        h.head = head;
-        h.b = f32("head" + std::to_string(lvl) + ".b", 32);
-        h.go = x.g;
-        h.level_offset = level_offset;
-        d->steps.push_back(h);
+        {   // conv5X5_2 (T -> F[32:48]) and conv7X7_2 (T -> U) in one pass over T; then conv7x7_3 (U -> F[48:64])
+            DStep s{};
+            s.kind = kC16;
+            s.in = T.p;
+            s.go = x.g;
+            s.w = f32(p + "b.w", 9 * 16 * 16);
+            s.b = f32(p + "b.b", 16);
+            s.out = F.p + 32;
+            s.ld_out = 64;
+            s.w2 = f32(p + "u.w", 9 * 16 * 16);
+            s.b2 = f32(p + "u.b", 16);
+            s.out2 = U.p;
+            s.ld_out2 = 16;
+            d->steps.push_back(s);
+            DStep c{};
+            c.kind = kC16;
+            c.in = U.p;
+            c.go = x.g;
+            c.w = f32(p + "c.w", 9 * 16 * 16);
+            c.b = f32(p + "c.b", 16);
+            c.out = F.p + 48;
+            c.ld_out = 64;
+            d->steps.push_back(c);
+        }
+        {   // the three 1x1 heads as one 64 -> 32 GEMM whose epilogue adds the bias, applies the softmax and scatters anchor-major
+            DStep s{};
+            s.kind = kGemm;
+            s.bn = 32;
+            s.heads = true;
+            __half* w = f16("head" + std::to_string(lvl) + ".w", 32ll * 64);
+            s.ta = F.tmap;
+            s.tb = make_tmap_2d_f16(w, 32, 64, 32, 64);
+            s.go = x.g;
+            s.prm.H = x.g.H;
+            s.prm.W = x.g.W;
+            s.prm.cin_blocks = 1;
+            s.prm.taps = 1;
+            s.prm.cout = 32;
+            s.prm.kb_per_split = 1;
+            s.prm.bias = f32("head" + std::to_string(lvl) + ".b", 32);
+            s.prm.head_loc = d->loc;
+            s.prm.head_conf = d->conf;
+            s.prm.head_landm = d->landm;
+            s.prm.anchors_total = d->anchors;
+            s.prm.level_offset = level_offset;
+            d->steps.push_back(s);
+        }
         level_offset += x.g.H * x.g.W * 2;
+        ssh_steps[lvl].assign(d->steps.begin() + first_step, d->steps.end());
+        d->steps.resize(first_step);
+    }
+    // Order of execution: the SSH + heads of a level only need that level's FPN output, so levels 3 and 2 run as side chains (own
+    // streams = parallel branches of the captured graph) next to the rest of the FPN and level 1; everything joins before decode.
+    {
+        std::vector<DStep> plan;
+        for (const DStep& s : d->steps) {
+            plan.push_back(s);
+            if (s.kind == kGemm && s.prm.out == o3.p)
+                for (DStep t : ssh_steps[3]) { t.lane = g_det_lanes ? 1 : 0; plan.push_back(t); }
+            if (s.kind == kGemm && s.prm.out == o2.p)
+                for (DStep t : ssh_steps[2]) { t.lane = g_det_lanes ? 2 : 0; plan.push_back(t); }
+        }
+        for (const DStep& t : ssh_steps[1]) plan.push_back(t);
+        d->steps.swap(plan);
     }
     d->cand = dalloc<DetCand>(d, static_cast<size_t>(B) * d->anchors, false);
+    d->n_cand = dalloc<int>(d, B, true);
     d->boxes = dalloc<FrBbox>(d, static_cast<size_t>(B) * d->max_faces, true);
     d->counts = dalloc<int>(d, B, true);
     d->out_landm = dalloc<float>(d, static_cast<size_t>(B) * d->max_faces * 10, true);
@@ -242,12 +357,12 @@ void build_plan(FrDetector* d, const WeightFile& wf) {
     FRB_CUDA(cudaStreamSynchronize(d->stream));
 }
 
-template <int BN>
+template <int BN, bool HEADS = false>
 void launch_det_gemm(const DStep& s, int batch, cudaStream_t st) {
     ConvGemmParams prm = s.prm;
     prm.P = batch * s.go.HpWp();
     dim3 grid((prm.P + kConvBM - 1) / kConvBM, prm.cout / BN, 1);
-    conv_gemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
+    conv_gemm_kernel<BN, false, HEADS><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
     count_launch();
 }
 
@@ -261,7 +376,19 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
     if (canvas_dev) det_stem_kernel<<<blocks_for(px, 256), 256, 0, st>>>(canvas_dev, stride_bytes, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
     else det_stem_f32_kernel<<<blocks_for(px, 256), 256, 0, st>>>(chw_dev, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
     count_launch();
+    bool forked[2] = {false, false};
+    cudaStream_t main_st = st;
     for (const DStep& s : d->steps) {
+        st = main_st;
+        if (s.lane > 0) {
+            const int l = s.lane - 1;
+            if (!forked[l]) {  // the side chain starts after everything the main chain has enqueued so far
+                FRB_CUDA(cudaEventRecord(d->ev_fork[l], main_st));
+                FRB_CUDA(cudaStreamWaitEvent(d->side[l], d->ev_fork[l], 0));
+                forked[l] = true;
+            }
+            st = d->side[l];
+        }
         switch (s.kind) {
             case kDw: {
                 const long long t = static_cast<long long>(batch) * s.go.H * s.go.W * (s.cin / 8);
@@ -269,37 +396,47 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
                 count_launch();
                 break;
             }
-            case kPwSmall: {
+            case kDwPwSmall: {
                 const long long t = static_cast<long long>(batch) * s.go.H * s.go.W;
-                const int nb = blocks_for(t, 128);
-                if (s.cin == 8 && s.cout == 16) pw_small_kernel<8, 16><<<nb, 128, 0, st>>>(s.in, s.out, s.go, batch, s.w, s.b);
-                else if (s.cin == 16 && s.cout == 32) pw_small_kernel<16, 32><<<nb, 128, 0, st>>>(s.in, s.out, s.go, batch, s.w, s.b);
-                else if (s.cin == 32 && s.cout == 32) pw_small_kernel<32, 32><<<nb, 128, 0, st>>>(s.in, s.out, s.go, batch, s.w, s.b);
-                else if (s.cin == 32 && s.cout == 64) pw_small_kernel<32, 64><<<nb, 128, 0, st>>>(s.in, s.out, s.go, batch, s.w, s.b);
-                else throw StateError{"unexpected pointwise shape"};
+                const int nb = static_cast<int>(std::min<long long>((t + 255) / 256, 3LL * d->sms));  // grid-stride inside the kernel
+                auto launch = [&](auto kern) { kern<<<nb, 256, 0, st>>>(s.in, s.gi, s.out, s.go, batch, s.w, s.b, s.w2, s.b2); };
+                if (s.cin == 8 && s.cout == 16 && s.stride == 1) launch(dwpw_small_kernel<8, 16, 1>);
+                else if (s.cin == 16 && s.cout == 32 && s.stride == 2) launch(dwpw_small_kernel<16, 32, 2>);
+                else if (s.cin == 32 && s.cout == 32 && s.stride == 1) launch(dwpw_small_kernel<32, 32, 1>);
+                else if (s.cin == 32 && s.cout == 64 && s.stride == 2) launch(dwpw_small_kernel<32, 64, 2>);
+                else throw StateError{"unexpected fused conv_dw shape"};
                 count_launch();
                 break;
             }
+            case kDwPwGemm:
+                if (s.bn == 64) launch_dwpw_gemm<64>(s, batch, st);
+                else if (s.bn == 128) launch_dwpw_gemm<128>(s, batch, st);
+                else if (s.bn == 256) launch_dwpw_gemm<256>(s, batch, st);
+                else throw StateError{"unexpected fused conv_dw width"};
+                break;
             case kGemm:
-                if (s.bn == 16) launch_det_gemm<16>(s, batch, st);
-                else if (s.bn == 32) launch_det_gemm<32>(s, batch, st);
+                if (s.heads) launch_det_gemm<32, true>(s, batch, st);
+                else if (s.bn == 48) launch_det_gemm<48>(s, batch, st);
                 else if (s.bn == 64) launch_det_gemm<64>(s, batch, st);
-                else launch_det_gemm<128>(s, batch, st);
+                else if (s.bn == 128) launch_det_gemm<128>(s, batch, st);
+                else throw StateError{"unexpected GEMM tile width"};
                 break;
             case kC16: {
                 const long long t = static_cast<long long>(batch) * s.go.H * s.go.W;
-                conv3x3_c16_kernel<<<blocks_for(t, 128), 128, 0, st>>>(s.in, s.out, s.ld_out, s.go, batch, s.w, s.b);
-                count_launch();
-                break;
-            }
-            case kHeads: {
-                const long long t = static_cast<long long>(batch) * s.go.H * s.go.W * 2;
-                det_heads_kernel<<<blocks_for(t, 256), 256, 0, st>>>(s.head, s.b, s.go, batch, d->anchors, s.level_offset, d->loc, d->conf, d->landm);
+                if (s.w2)
+                    conv3x3_c16_kernel<2><<<blocks_for(t, 128), 128, 0, st>>>(s.in, s.go, batch, s.w, s.b, s.out, s.ld_out, s.w2, s.b2, s.out2, s.ld_out2);
+                else
+                    conv3x3_c16_kernel<1><<<blocks_for(t, 128), 128, 0, st>>>(s.in, s.go, batch, s.w, s.b, s.out, s.ld_out, nullptr, nullptr, nullptr, 0);
                 count_launch();
                 break;
             }
         }
     }
+    for (int l = 0; l < 2; ++l)
+        if (forked[l]) {
+            FRB_CUDA(cudaEventRecord(d->ev_join[l], d->side[l]));
+            FRB_CUDA(cudaStreamWaitEvent(main_st, d->ev_join[l], 0));
+        }
     FRB_CUDA(cudaGetLastError());
 }
 
@@ -316,10 +453,11 @@ void run_post(FrDetector* d, const float* loc, const float* conf, const float* l
     p.bbox_thr = d->bbox_thr;
     p.max_faces = d->max_faces;
     p.anchors = d->anchors;
-    det_decode_nms_kernel<<<batch, 256, 0, st>>>(loc, conf, landm, p, d->cand, d->boxes + static_cast<size_t>(slot0) * d->max_faces, d->counts + slot0,
-                                                 d->out_landm + static_cast<size_t>(slot0) * d->max_faces * 10,
-                                                 d->out_ids + static_cast<size_t>(slot0) * d->max_faces);
-    count_launch();
+    det_decode_kernel<<<dim3((d->anchors + 255) / 256, batch), 256, 0, st>>>(loc, conf, p, d->cand, d->n_cand);
+    det_nms_kernel<<<batch, 256, 0, st>>>(landm, p, d->cand, d->n_cand, d->boxes + static_cast<size_t>(slot0) * d->max_faces, d->counts + slot0,
+                                          d->out_landm + static_cast<size_t>(slot0) * d->max_faces * 10,
+                                          d->out_ids + static_cast<size_t>(slot0) * d->max_faces);
+    count_launch(2);
     FRB_CUDA(cudaGetLastError());
 }
 
@@ -445,8 +583,16 @@ int fr_detector_create(const char* weights_path, int net_h, int net_w, int frame
         d->landmarks = with_landmarks != 0;
         try {
             FRB_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<16>::kSmemBytes));
-            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
+            for (int l = 0; l < 2; ++l) {
+                FRB_CUDA(cudaStreamCreateWithFlags(&d->side[l], cudaStreamNonBlocking));
+                FRB_CUDA(cudaEventCreateWithFlags(&d->ev_fork[l], cudaEventDisableTiming));
+                FRB_CUDA(cudaEventCreateWithFlags(&d->ev_join[l], cudaEventDisableTiming));
+            }
+            FRB_CUDA(cudaFuncSetAttribute(dwpw_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPwGemmCfg<64>::smem_bytes(256)));
+            FRB_CUDA(cudaFuncSetAttribute(dwpw_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPwGemmCfg<128>::smem_bytes(256)));
+            FRB_CUDA(cudaFuncSetAttribute(dwpw_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPwGemmCfg<256>::smem_bytes(256)));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<48>::kSmemBytes));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<32>::kSmemBytes));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
             build_plan(d.get(), wf);
@@ -465,6 +611,12 @@ void fr_detector_destroy(FrDetector* d) {
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (void* p : d->allocs) cudaFree(p);
+    for (int l = 0; l < 2; ++l) {
+        if (d->side[l]) cudaStreamSynchronize(d->side[l]);
+        if (d->ev_fork[l]) cudaEventDestroy(d->ev_fork[l]);
+        if (d->ev_join[l]) cudaEventDestroy(d->ev_join[l]);
+        if (d->side[l]) cudaStreamDestroy(d->side[l]);
+    }
     if (d->stream) cudaStreamDestroy(d->stream);
     if (prev >= 0) cudaSetDevice(prev);
     delete d;

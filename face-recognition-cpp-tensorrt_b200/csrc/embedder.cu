@@ -7,6 +7,7 @@
 //   writes y, BN_next(y), y[::2,::2]) }  ->  folded Linear as split-K GEMM  ->  partial reduce + bias + L2 normalise.
 // Every GEMM is conv_gemm_kernel (tcgen05, csrc/conv_kernels.cuh). Activations are fp16 in the shared-halo flat layout.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -15,6 +16,7 @@
 
 #include "common.h"
 #include "conv_kernels.cuh"
+#include "conv_mt_kernel.cuh"
 #include "embed_kernels.cuh"
 #include "weights.h"
 
@@ -81,7 +83,7 @@ struct FrEmbedder {
     float* in_f32 = nullptr;         // max_batch x 3 x 112 x 112
     uint8_t* in_u8 = nullptr;        // max_batch x 112 x 112 x 3
     float* gate = nullptr;           // max_batch x 512
-    float* se_pool = nullptr;        // max_batch x kSeChunks x 512
+    int* se_pool = nullptr;          // SE pooling partials written by conv2: [rows / 32 groups][2 segments][C], largest stage
     float* fc_partial = nullptr;     // kFcSplits x max_batch x 512
     float* fc_bias = nullptr;
     float* out_dev = nullptr;        // max_batch x 512
@@ -124,51 +126,116 @@ DevBuf make_buf(FrEmbedder* e, size_t rows, int C) {
     return b;
 }
 
-// conv3x3_halo_kernel (one halo tile per channel block instead of nine per-tap loads) policy, FR_HALO: 0 = never, 1 (default) = only the
-// 64-input-channel layers (one channel block: the layers that are most L2-bound per tap, and the halo tile + weight ring still let two
-// CTAs share an SM), 2 = every stride-1 3x3 conv, 3 = experimental persistent weight-stationary kernel on the 64 -> 64 layers (others as 1), 4 = that kernel on small grids only (others as 1). Measured on B200 (IR-SE-50) for FR_HALO=2: 1.55 vs 1.64 ms at batch 32 but 8.65 vs
-// 7.54 ms at batch 256 (with two halo buffers only one CTA fits per SM on the 128..512-channel layers); FR_HALO=1: 1.576 vs 1.601 ms
-// at batch 32 and 7.43 vs 7.52 ms at batch 256 (gpurun_out/halo_policy.txt, two interleaved runs each).
-// The tap operands start at 128-byte-row offsets inside the 1024-byte swizzle atom; the hardware swizzles on absolute shared-memory
-// address bits, so the descriptor's base-offset field must stay 0 (setting it to (addr >> 7) & 7 breaks parity: measured).
-const int g_halo_level = std::getenv("FR_HALO") ? std::atoi(std::getenv("FR_HALO")) : 1;
-const int g_halo_baseoff = 0;
+// Stride-1 3x3 convs run on conv3x3_mt_kernel (persistent, halo-reusing, MT tiles per work unit; conv_mt_kernel.cuh). FR_CONV_MT=0 sends
+// them to conv_gemm_kernel instead (A/B); FR_MT_FORCE="bn,mt" pins the tile shape.
+const bool g_use_mt = std::getenv("FR_CONV_MT") == nullptr || std::atoi(std::getenv("FR_CONV_MT")) != 0;
 int g_conv_sms = 148;  // SM count of the embedder's device (set at create): grid of the persistent conv
+
+constexpr int kSmemBudget = 227 * 1024;
+
+template <int BN, int MT>
+void launch_mt(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) {
+    ConvMtExtra ex{};
+    ex.n_blocks = prm.cout / BN;
+    ex.units = ((prm.P + MT * kConvBM - 1) / (MT * kConvBM)) * ex.n_blocks;
+    const int Wp = prm.W + 1;
+    if (prm.tap_phase) {
+        // stride 2 over a phase-split input: tap (dy, dx) reads phase map (dy != 1, dx != 1) shifted by (dy == 0 ? -1 : 0, dx == 0 ? -1 : 0)
+        ex.ngroups = 4;
+        ex.halo_chunks = (MT * kConvBM + Wp + 1 + kConvBM - 1) / kConvBM;
+        for (int ph = 0; ph < 4; ++ph) {
+            MtGroup& G = ex.grp[ph];
+            G.row0 = ph * prm.phase_rows - Wp - 1;
+            G.ntaps = 0;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3, dx = tap % 3;
+                if (((dy != 1 ? 2 : 0) + (dx != 1 ? 1 : 0)) != ph) continue;
+                G.tap[G.ntaps] = tap;
+                G.off[G.ntaps] = Wp + 1 + (dy == 0 ? -Wp : 0) + (dx == 0 ? -1 : 0);
+                ++G.ntaps;
+            }
+        }
+    } else {
+        ex.ngroups = 1;
+        ex.halo_chunks = (MT * kConvBM + 2 * Wp + 2 + kConvBM - 1) / kConvBM;
+        MtGroup& G = ex.grp[0];
+        G.row0 = -Wp - 1;
+        G.ntaps = 9;
+        for (int tap = 0; tap < 9; ++tap) {
+            G.tap[tap] = tap;
+            G.off[tap] = (tap / 3) * Wp + tap % 3;
+        }
+    }
+    const int fixed = conv_mt_smem_bytes(BN, ex.halo_chunks, 0);
+    ex.stages = std::min(kMtMaxStages, (kSmemBudget - fixed) / (BN * 128));
+    if (ex.stages < 2) throw StateError{"conv3x3_mt_kernel: halo tile does not fit in shared memory"};
+    if (!prm.tap_phase && prm.cin_blocks == 1 && ex.n_blocks == 1 && ex.stages >= 9) {
+        ex.stationary = 1;
+        ex.stages = 9;  // stage index == tap
+    }
+    const int smem = conv_mt_smem_bytes(BN, ex.halo_chunks, ex.stages);
+    const int ctas = std::min(ex.units, g_conv_sms);
+    conv3x3_mt_kernel<BN, MT><<<ctas, kMtThreads, smem, st>>>(s.ta, BN == 64 && s.bn != 64 ? s.tb64 : s.tb, prm, ex);
+}
+
+// tile shape of the persistent conv: the largest unit that still gives every SM one; small grids take the smallest
+bool pick_mt(const GemmStep& s, const ConvGemmParams& prm, int& bn, int& mt) {
+    if (!g_use_mt || prm.taps != 9 || s.splits != 1 || prm.partial || prm.cout > 512) return false;
+    static const bool mt_s2 = std::getenv("FR_MT_S2") == nullptr || std::atoi(std::getenv("FR_MT_S2")) != 0;  // stride-2 convs too (A/B)
+    if (prm.tap_phase && !mt_s2) return false;
+    static const char* force = std::getenv("FR_MT_FORCE");
+    if (force) {
+        int fb = 0, fm = 0;
+        if (std::sscanf(force, "%d,%d", &fb, &fm) == 2 && (fb == 64 || fb == 128) && (fm == 1 || fm == 2) && prm.cout % fb == 0 &&
+            (fb == 64 ? s.has64 || s.bn == 64 : s.bn == 128)) {
+            bn = fb;
+            mt = fm;
+            return true;
+        }
+    }
+    const int cand[4][2] = {{128, 2}, {128, 1}, {64, 2}, {64, 1}};
+    for (const auto& c : cand) {
+        if (c[0] == 128 && (s.bn != 128 || prm.cout % 128)) continue;
+        if (c[0] == 64 && !(s.bn == 64 || s.has64)) continue;
+        bn = c[0];
+        mt = c[1];
+        const long long units = static_cast<long long>((prm.P + mt * kConvBM - 1) / (mt * kConvBM)) * (prm.cout / bn);
+        if (units >= g_conv_sms) return true;
+    }
+    return bn != 0;
+}
 
 template <int BN>
 void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
     ConvGemmParams prm = s.prm;
     prm.P = P;
     dim3 grid((P + kConvBM - 1) / kConvBM, prm.cout / BN, s.splits);
-    // level 3: always; level 4 ("auto", not yet run on hardware): only while the layer has at most 24 position tiles per SM, where the
-    // kernel's fixed costs (weights once per CTA, 148 CTAs) win over its latency-bound steady state; other layers as level 1
-    const bool ws_ok = BN == 64 && prm.taps == 9 && !prm.tap_phase && s.splits == 1 && prm.cin_blocks == 1 && prm.cout == 64 && !prm.partial;
-    if (ws_ok && (g_halo_level == 3 || (g_halo_level == 4 && static_cast<int>(grid.x) <= 24 * g_conv_sms))) {
-        // experimental: persistent weight-stationary 64 -> 64 conv (conv3x3_ws_kernel): weights loaded once per CTA, halo tiles streamed
-        // Measured on B200 with 2 halo buffers and 8 epilogue warps (parity green), in a build where every OTHER stride-1 3x3 layer ran
-        // conv3x3_halo_kernel (the FR_HALO=2 behaviour: 8.65 ms at batch 256): 1.45 vs 1.56 ms (FR_HALO=1) at batch 32, 8.06 vs 7.29 ms
-        // at batch 256 - i.e. about -0.6 ms against FR_HALO=2, not yet isolated against FR_HALO=1. With one 32-48 KiB halo load in
-        // flight per SM the steady state is bound by that load's latency; FR_WS_BUFS=3/4 keeps more in flight (not yet run).
-        static const int ws_bufs = std::getenv("FR_WS_BUFS") ? std::atoi(std::getenv("FR_WS_BUFS")) : 2;
-        prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
-        const int halo_bytes = prm.halo_chunks * kConvBM * 128;
-        prm.halo_bufs = std::max(2, std::min({4, ws_bufs, (227 * 1024 - 1024 - kWsWeightBytes - 256 - 4 * kWsBN * 4) / halo_bytes}));
-        const int smem = 1024 + prm.halo_bufs * halo_bytes + kWsWeightBytes + 256 + 4 * kWsBN * 4;
-        const int ctas = std::min<int>(static_cast<int>(grid.x), g_conv_sms);
-        conv3x3_ws_kernel<<<ctas, kWsThreads, smem, st>>>(s.ta, s.tb, prm);
-    } else if (prm.taps == 9 && !prm.tap_phase && s.splits == 1 &&
-               (g_halo_level == 2 || (g_halo_level != 0 && prm.cin_blocks == 1))) {
-        // 3x3 stride-1 conv: one halo tile per 64-channel block feeds all nine taps (conv3x3_halo_kernel)
-        prm.halo_chunks = (kConvBM + 2 * (prm.W + 1) + 2 + kConvBM - 1) / kConvBM;
-        prm.halo_bufs = prm.cin_blocks > 1 ? 2 : 1;
-        prm.halo_base_offset = g_halo_baseoff;
-        const int smem = 1024 + prm.halo_bufs * prm.halo_chunks * ConvCfg<BN>::kABytes + ConvCfg<BN>::kConvStages * ConvCfg<BN>::kBBytes + 256 +
-                         ConvCfg<BN>::kParamBytes;
-        conv3x3_halo_kernel<BN><<<grid, kConvThreads, smem, st>>>(s.ta, s.tb, prm);
-    } else {
-        conv_gemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
-    }
+    if (prm.pool) conv_gemm_kernel<BN, true><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
+    else conv_gemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
     count_launch();
+}
+
+void launch_conv(const GemmStep& g0, int P, int sms, cudaStream_t st) {
+    GemmStep g = g0;
+    g.prm.P = P;
+    int bn = 0, mt = 0;
+    if (pick_mt(g, g.prm, bn, mt)) {
+        if (bn == 128 && mt == 2) launch_mt<128, 2>(g, g.prm, st);
+        else if (bn == 128) launch_mt<128, 1>(g, g.prm, st);
+        else if (mt == 2) launch_mt<64, 2>(g, g.prm, st);
+        else launch_mt<64, 1>(g, g.prm, st);
+        count_launch();
+        return;
+    }
+    // 128-wide channel tiles only when they still give every SM two CTAs' worth of work; otherwise 64-wide tiles (two CTAs
+    // fit per SM, so one CTA's epilogue overlaps another's main loop)
+    const long long tiles128 = static_cast<long long>((P + kConvBM - 1) / kConvBM) * (g.prm.cout / 128);
+    if (g.bn == 128 && g.has64 && tiles128 < 2LL * sms) {
+        g.bn = 64;
+        g.tb = g.tb64;
+    }
+    if (g.bn == 64) launch_gemm<64>(g, P, st);
+    else launch_gemm<128>(g, P, st);
 }
 
 void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cudaStream_t st = nullptr) {
@@ -178,7 +245,18 @@ void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cud
     static const bool stem_pair = std::getenv("FR_STEM_PAIR") == nullptr || std::atoi(std::getenv("FR_STEM_PAIR")) != 0;
     const long long work = static_cast<long long>(batch) * 112 * (stem_pair ? 56 : 112);
     const int blocks = static_cast<int>(std::min<long long>((work + 127) / 128, 148LL * 16));  // grid-stride inside the kernels
-    if (stem_pair) {
+    static const bool stem_tc = std::getenv("FR_STEM_TC") == nullptr || std::atoi(std::getenv("FR_STEM_TC")) != 0;
+    if (stem_tc) {
+        // tensor-core stem (arcface_stem_tc_kernel): persistent, a few CTAs per SM
+        const int tiles = (batch * hpwp(0) + 127) / 128;
+        const int ctas = std::min(tiles, e->sms * 6);
+        if (u8_input)
+            arcface_stem_tc_kernel<true><<<ctas, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
+                                                               e->stem_y.p, e->stem_yb.p);
+        else
+            arcface_stem_tc_kernel<false><<<ctas, 128, 0, st>>>(e->in_f32, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
+                                                                e->stem_y.p, e->stem_yb.p);
+    } else if (stem_pair) {
         if (u8_input)
             arcface_stem_pair_kernel<true><<<blocks, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
                                                                    e->stem_y.p, e->stem_yb.p);
@@ -202,24 +280,16 @@ void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cud
                 g.prm.W = batch;
                 g.prm.H = 1;
             }
-            // 128-wide channel tiles only when they still give every SM two CTAs' worth of work; otherwise 64-wide tiles (two CTAs
-            // fit per SM, so one CTA's epilogue overlaps another's main loop)
-            const long long tiles128 = static_cast<long long>((P + kConvBM - 1) / kConvBM) * (g.prm.cout / 128);
-            if (g.bn == 128 && g.has64 && tiles128 < 2LL * e->sms) {
-                g.bn = 64;
-                g.tb = g.tb64;
-            }
-            if (g.bn == 64) launch_gemm<64>(g, P, st);
-            else launch_gemm<128>(g, P, st);
+            launch_conv(g, P, e->sms, st);
         } else {
             const SeStep& q = s.se;
             const int H = kGeo[q.geo], P = batch * hpwp(q.geo);
-            se_pool_kernel<<<dim3(batch, kSeChunks), 256, 0, st>>>(q.u, hpwp(q.geo), q.C, e->se_pool);
-            se_gate_kernel<<<batch, 256, 0, st>>>(e->se_pool, H * H, q.C, q.fc1, q.fc2, e->gate);
-            const long long threads = static_cast<long long>(P) * (q.C / 8);
-            se_apply_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(q.u, e->gate, P, H, H, q.C, q.res, q.res_mode, q.y, q.y_bn,
-                                                                                    q.bn_s, q.bn_b, q.y_sub);
-            count_launch(3);
+            se_gate_kernel<<<batch, 512, 0, st>>>(e->se_pool, H, H, q.C, q.fc1, q.fc2, e->gate);
+            const long long items = static_cast<long long>(P) * (q.C / 8);
+            const int blocks = static_cast<int>(std::min<long long>((items + 511) / 512, 8LL * e->sms));  // 2 items per thread per pass
+            se_apply_kernel<<<blocks, 256, 0, st>>>(q.u, e->gate, P, H, H, q.C, q.res, q.res_mode, q.y, q.y_bn, q.bn_s, q.bn_b, q.y_sub);
+            count_launch();
+            count_launch();
         }
     }
     if (stop_after_unit == kRunAll) {
@@ -247,8 +317,13 @@ void build_plan(FrEmbedder* e, const WeightFile& wf) {
     e->stem_prelu = f32("stem.prelu", 64);
     e->in_f32 = dev_alloc<float>(e, static_cast<size_t>(B) * 3 * 112 * 112, false);
     e->in_u8 = dev_alloc<uint8_t>(e, static_cast<size_t>(B) * 112 * 112 * 3, false);
-    e->gate = dev_alloc<float>(e, static_cast<size_t>(B) * 512, false);
-    e->se_pool = dev_alloc<float>(e, static_cast<size_t>(B) * kSeChunks * 512, false);
+    if (se) {
+        e->gate = dev_alloc<float>(e, static_cast<size_t>(B) * 512, false);
+        size_t pool_floats = 0;
+        for (int g = 1; g <= 4; ++g)
+            pool_floats = std::max(pool_floats, (static_cast<size_t>(B) * hpwp(g) / 32 + 8) * 2 * kStageC[g]);
+        e->se_pool = dev_alloc<int>(e, pool_floats, true);
+    }
     e->fc_partial = dev_alloc<float>(e, static_cast<size_t>(kFcSplits) * B * 512, false);
     e->out_dev = dev_alloc<float>(e, static_cast<size_t>(B) * 512, false);
     e->stem_y = make_buf(e, static_cast<size_t>(B) * hpwp(0), 64);
@@ -415,6 +490,7 @@ void build_plan(FrEmbedder* e, const WeightFile& wf) {
                 }
                 if (se) {
                     s.g.prm.out = sb[stage].u.p;
+                    s.g.prm.pool = e->se_pool;
                 } else {
                     s.g.prm.res = res;
                     s.g.prm.res_mode = res_mode;
@@ -533,10 +609,13 @@ int fr_embedder_create(const char* weights_path, int max_batch, int device, FrEm
             FRB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
             FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmemBytes));
+            FRB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmemBytes));
             g_conv_sms = e->sms;
-            FRB_CUDA(cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            FRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            FRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_mt_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_mt_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_mt_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_mt_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
             build_plan(e.get(), wf);
         } catch (...) {
             fr_embedder_destroy(e.release());
