@@ -20,7 +20,7 @@ namespace frb {
 
 constexpr int kMtThreads = 128 + 8 * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 constexpr int kMtMaxStages = 12;
-constexpr int kMtParamBytes = 4 * 512 * 4;  // bias, prelu, bn_s, bn_b for up to 512 output channels
+constexpr int kMtParamBytes = 4 * 512 * 4 + 256;  // bias, prelu, bn_s, bn_b for up to 512 output channels + the tap tables
 
 // The nine taps of a 64-channel block are organised in GROUPS that share one halo tile:
 //   stride 1: one group, halo tile = matrix rows p0 - Wp - 1 ... of the input, tap (dy, dx) starts dy*Wp + dx rows in;
@@ -71,6 +71,9 @@ conv3x3_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     float* s_prelu = s_bias + 512;
     float* s_bns = s_prelu + 512;
     float* s_bnb = s_bns + 512;
+    // tap tables of the MMA issuer (the issue loop must stay far below the 256-512 tensor cycles of a tap: no indexed constant loads)
+    uint32_t* s_off8 = reinterpret_cast<uint32_t*>(s_bnb + 512);  // [4][9] operand start inside the halo tile, in 16-byte units
+    uint32_t* s_ntaps = s_off8 + 36;                               // [4]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -94,6 +97,10 @@ conv3x3_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == 3) {
+        for (int i = lane; i < 36; i += 32) s_off8[i] = static_cast<uint32_t>(ex.grp[i / 9].off[i % 9]) * 8u;
+        if (lane < 4) s_ntaps[lane] = static_cast<uint32_t>(ex.grp[lane].ntaps);
+    }
     if (warp >= 4) {
         for (int i = threadIdx.x - 128; i < prm.cout; i += kMtThreads - 128) {
             s_bias[i] = prm.bias ? __ldg(prm.bias + i) : 0.f;
@@ -145,6 +152,14 @@ conv3x3_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ---------------- MMA issuer ----------------
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(kConvBM, BN, 0, 0);
+            // shared-memory matrix descriptors (umma_desc_sw128) as (hi, lo) words: hi is constant, lo = flags | (address >> 4); stepping
+            // to another tap / tile / k-slice / ring stage is an add on the low word
+            constexpr uint32_t kDescHi = 0x40004040u;  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+            constexpr uint32_t kDescLo = 0x10000u;     // LBO = 1
+            auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+            const uint32_t a_lo0 = kDescLo | ((smem_u32(smem) & 0x3FFFFu) >> 4);
+            const uint32_t a_lo_step = static_cast<uint32_t>(halo_bytes) >> 4;
+            const uint32_t b_lo0 = kDescLo | ((smem_u32(ring) & 0x3FFFFu) >> 4);
             uint32_t stage = 0, phase = 0, hb = 0, hph = 0;
             bool first = true;
             int i = 0;
@@ -156,26 +171,26 @@ conv3x3_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 uint32_t acc = 0;  // 0 for the very first MMA into each accumulator of this unit
                 for (int cb = 0; cb < prm.cin_blocks; ++cb) {
                     for (int g = 0; g < ex.ngroups; ++g) {
-                        const MtGroup& G = ex.grp[g];
+                        const uint32_t ntaps = s_ntaps[g];
+                        const uint32_t* off8 = s_off8 + g * 9;
                         mbar_wait(&hfull_bar[hb], hph);
                         tc_fence_after();
-                        const uint32_t halo_addr = smem_u32(smem + hb * halo_bytes);
+                        const uint32_t a_lo_h = a_lo0 + hb * a_lo_step;
 #pragma unroll 1
-                        for (int t = 0; t < G.ntaps; ++t) {
+                        for (uint32_t t = 0; t < ntaps; ++t) {
                             if (!ex.stationary || first) {
                                 mbar_wait(&full_bar[stage], phase);
                                 tc_fence_after();
                             }
-                            const uint32_t b_addr = smem_u32(ring + stage * kBBytes);
                             // the tap's operand for tile m = 128 consecutive rows of the halo tile starting m*128 + off rows in (the swizzle acts
                             // on absolute shared-memory address bits, so a 128-byte-row offset needs no descriptor base offset: measured)
-                            const uint32_t a_tap = halo_addr + static_cast<uint32_t>(G.off[t]) * 128u;
+                            const uint32_t a_lo = a_lo_h + off8[t];
+                            const uint32_t b_lo = b_lo0 + stage * (kBBytes >> 4);
 #pragma unroll
                             for (int m = 0; m < MT; ++m) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    umma_f16_ss(d_tmem + m * BN, umma_desc_sw128(a_tap + m * kABytes + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                                (acc | k) ? 1u : 0u);
+                                    umma_f16_ss(d_tmem + m * BN, desc(a_lo + m * (kABytes >> 4) + k * 2), desc(b_lo + k * 2), idesc, (acc | k) ? 1u : 0u);
                             }
                             acc = 1;
                             if (!ex.stationary) umma_commit(&empty_bar[stage]);
