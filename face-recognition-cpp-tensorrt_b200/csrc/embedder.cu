@@ -133,16 +133,13 @@ int g_conv_sms = 148;  // SM count of the embedder's device (set at create): gri
 
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int BN, int MT>
-void launch_mt(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) {
-    ConvMtExtra ex{};
-    ex.n_blocks = prm.cout / BN;
-    ex.units = ((prm.P + MT * kConvBM - 1) / (MT * kConvBM)) * ex.n_blocks;
+// tap groups + halo geometry of a conv for `tiles` 128-position tiles per CTA (conv_mt_kernel.cuh)
+void fill_groups(ConvMtExtra& ex, const ConvGemmParams& prm, int tiles) {
     const int Wp = prm.W + 1;
     if (prm.tap_phase) {
         // stride 2 over a phase-split input: tap (dy, dx) reads phase map (dy != 1, dx != 1) shifted by (dy == 0 ? -1 : 0, dx == 0 ? -1 : 0)
         ex.ngroups = 4;
-        ex.halo_chunks = (MT * kConvBM + Wp + 1 + kConvBM - 1) / kConvBM;
+        ex.halo_chunks = (tiles * kConvBM + Wp + 1 + kConvBM - 1) / kConvBM;
         for (int ph = 0; ph < 4; ++ph) {
             MtGroup& G = ex.grp[ph];
             G.row0 = ph * prm.phase_rows - Wp - 1;
@@ -157,7 +154,7 @@ void launch_mt(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) {
         }
     } else {
         ex.ngroups = 1;
-        ex.halo_chunks = (MT * kConvBM + 2 * Wp + 2 + kConvBM - 1) / kConvBM;
+        ex.halo_chunks = (tiles * kConvBM + 2 * Wp + 2 + kConvBM - 1) / kConvBM;
         MtGroup& G = ex.grp[0];
         G.row0 = -Wp - 1;
         G.ntaps = 9;
@@ -166,6 +163,14 @@ void launch_mt(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) {
             G.off[tap] = (tap / 3) * Wp + tap % 3;
         }
     }
+}
+
+template <int BN, int MT>
+void launch_mt(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) {
+    ConvMtExtra ex{};
+    ex.n_blocks = prm.cout / BN;
+    ex.units = ((prm.P + MT * kConvBM - 1) / (MT * kConvBM)) * ex.n_blocks;
+    fill_groups(ex, prm, MT);
     const int fixed = conv_mt_smem_bytes(BN, ex.halo_chunks, 0);
     ex.stages = std::min(kMtMaxStages, (kSmemBudget - fixed) / (BN * 128));
     if (ex.stages < 2) throw StateError{"conv3x3_mt_kernel: halo tile does not fit in shared memory"};
@@ -176,6 +181,45 @@ void launch_mt(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) {
     const int smem = conv_mt_smem_bytes(BN, ex.halo_chunks, ex.stages);
     const int ctas = std::min(ex.units, g_conv_sms);
     conv3x3_mt_kernel<BN, MT><<<ctas, kMtThreads, smem, st>>>(s.ta, BN == 64 && s.bn != 64 ? s.tb64 : s.tb, prm, ex);
+}
+
+// CTA-pair version (conv3x3_pair_kernel<BN>): unit = 256 positions x BN channels, weight boxes of BN / 2 rows per CTA
+template <int BN>
+void launch_pair(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) {
+    ConvMtExtra ex{};
+    ex.n_blocks = prm.cout / BN;
+    ex.units = ((prm.P + 2 * kConvBM - 1) / (2 * kConvBM)) * ex.n_blocks;
+    fill_groups(ex, prm, 1);
+    const int fixed = conv_mt_smem_bytes(BN / 2, ex.halo_chunks, 0);
+    ex.stages = std::min(kMtMaxStages, (kSmemBudget - fixed) / ((BN / 2) * 128));
+    if (ex.stages < 2) throw StateError{"conv3x3_pair_kernel: halo tile does not fit in shared memory"};
+    const int smem = conv_mt_smem_bytes(BN / 2, ex.halo_chunks, ex.stages);
+    const int pairs = std::min(ex.units, g_conv_sms / 2);
+    conv3x3_pair_kernel<BN><<<2 * pairs, kMtThreads, smem, st>>>(s.ta, BN == 128 ? s.tb64 : s.tb, prm, ex);
+}
+
+// FR_PAIR=0: never use the CTA-pair kernel; FR_PAIR_BN=128|256 pins its tile width (A/B)
+int pick_pair(const GemmStep& s, const ConvGemmParams& prm) {
+    static const bool on = std::getenv("FR_PAIR") == nullptr || std::atoi(std::getenv("FR_PAIR")) != 0;
+    static const int force = std::getenv("FR_PAIR_BN") ? std::atoi(std::getenv("FR_PAIR_BN")) : 0;
+    if (!on || !g_use_mt || prm.taps != 9 || s.splits != 1 || prm.partial || prm.cout > 512 || s.bn != 128 || !s.has64) return 0;
+    const int pairs = g_conv_sms / 2;
+    const long long tiles = (prm.P + 2 * kConvBM - 1) / (2 * kConvBM);
+    double best = 1e30;
+    int best_bn = 0;
+    for (int bn : {256, 128}) {
+        if (prm.cout % bn || (force && bn != force)) continue;
+        const long long units = tiles * (prm.cout / bn);
+        if (units < pairs) continue;  // cannot fill the GPU: the single-CTA kernel has smaller units
+        // rounds x unit cost. Measured (IR-SE-50, batch 256, B200): the N = 128 MMAs (64 tensor cycles each) keep the tensor pipe 62-66 %
+        // busy, the N = 256 ones pay for a worse last round (225 units on 74 pairs) and still win: 4.90 vs 5.20 ms per forward
+        const double cost = static_cast<double>((units + pairs - 1) / pairs) * bn / (bn == 256 ? 1.0 : 0.75);
+        if (cost < best) {
+            best = cost;
+            best_bn = bn;
+        }
+    }
+    return best_bn;
 }
 
 // tile shape of the persistent conv: the largest unit that still gives every SM one; small grids take the smallest
@@ -219,6 +263,12 @@ void launch_conv(const GemmStep& g0, int P, int sms, cudaStream_t st) {
     GemmStep g = g0;
     g.prm.P = P;
     int bn = 0, mt = 0;
+    if (const int pbn = pick_pair(g, g.prm)) {
+        if (pbn == 256) launch_pair<256>(g, g.prm, st);
+        else launch_pair<128>(g, g.prm, st);
+        count_launch();
+        return;
+    }
     if (pick_mt(g, g.prm, bn, mt)) {
         if (bn == 128 && mt == 2) launch_mt<128, 2>(g, g.prm, st);
         else if (bn == 128) launch_mt<128, 1>(g, g.prm, st);
@@ -616,6 +666,8 @@ int fr_embedder_create(const char* weights_path, int max_batch, int device, FrEm
             FRB_CUDA(cudaFuncSetAttribute(conv3x3_mt_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
             FRB_CUDA(cudaFuncSetAttribute(conv3x3_mt_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
             FRB_CUDA(cudaFuncSetAttribute(conv3x3_mt_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+            FRB_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
             build_plan(e.get(), wf);
         } catch (...) {
             fr_embedder_destroy(e.release());
