@@ -39,6 +39,9 @@ struct ConvMtExtra {
     int halo_chunks;  // 128-row boxes per halo tile
     int stationary;   // 1: stride 1, cin_blocks == 1 && n_blocks == 1 && stages >= 9: weights loaded once per CTA
     int ngroups;      // 1 (stride 1) or 4 (stride 2)
+    // conv3x3_pair_kernel only: work items [0, full_units) are whole units; the units of a short last round are split into two
+    // half-width items each (channels [0, BN/2) and [BN/2, BN) of the unit), so that the round costs half a unit's time
+    int full_units, half_items;
     MtGroup grp[4];
 };
 
@@ -362,7 +365,8 @@ conv3x3_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMtThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ ConvGemmParams prm, const __grid_constant__ ConvMtExtra ex) {
+                    const __grid_constant__ CUtensorMap tmap_b_half, const __grid_constant__ ConvGemmParams prm,
+                    const __grid_constant__ ConvMtExtra ex) {
     constexpr int kABytes = kConvBM * 128, kBHalf = (BN / 2) * 128;
     constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator sets
     static_assert(kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
@@ -391,10 +395,19 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int Wp = prm.W + 1;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int items = ex.full_units + ex.half_items;
+    // work item w -> (unit, first channel, width): whole units first, then the half-width items of the short last round
+    auto decode = [&](int w, int& pt, int& n_base, bool& half) {
+        half = w >= ex.full_units;
+        const int u = half ? ex.full_units + ((w - ex.full_units) >> 1) : w;
+        pt = u / ex.n_blocks;
+        n_base = (u - pt * ex.n_blocks) * BN + (half ? ((w - ex.full_units) & 1) * (BN / 2) : 0);
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        tma_prefetch_desc(&tmap_b_half);
     }
     if (warp == 1 && lane == 0) {
         for (int s2 = 0; s2 < kMtMaxStages; ++s2) {
@@ -434,10 +447,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t leader_full0 = mapa_u32(smem_u32(&full_bar[0]), 0);
             const uint32_t leader_hfull0 = mapa_u32(smem_u32(&hfull_bar[0]), 0);
             uint32_t stage = 0, phase = 0, hb = 0, hph = 0;
-            for (int u = pair; u < ex.units; u += num_pairs) {
-                const int pt = u / ex.n_blocks, nb = u - pt * ex.n_blocks;
-                const int p0 = pt * (2 * kConvBM) + static_cast<int>(rank) * kConvBM;  // this CTA's 128 positions
-                const int n0 = nb * BN + static_cast<int>(rank) * (BN / 2);            // this CTA's half of the weight rows
+            for (int w = pair; w < items; w += num_pairs) {
+                int pt, n_base;
+                bool half;
+                decode(w, pt, n_base, half);
+                const int p0 = pt * (2 * kConvBM) + static_cast<int>(rank) * kConvBM;        // this CTA's 128 positions
+                const int n0 = n_base + static_cast<int>(rank) * (half ? BN / 4 : BN / 2);  // this CTA's half of the item's weight rows
+                const CUtensorMap* tb = half ? &tmap_b_half : &tmap_b;
+                const uint32_t b_bytes = half ? kBHalf / 2 : kBHalf;
                 for (int cb = 0; cb < prm.cin_blocks; ++cb) {
                     for (int g = 0; g < ex.ngroups; ++g) {
                         const MtGroup& G = ex.grp[g];
@@ -452,8 +469,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                         for (int t = 0; t < G.ntaps; ++t) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
-                            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kBHalf);
-                            tma_load_2d_pair(ring + stage * kBHalf, &tmap_b, leader_full0 + stage * 8, (G.tap[t] * prm.cin_blocks + cb) * 64, n0,
+                            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * b_bytes);
+                            tma_load_2d_pair(ring + stage * kBHalf, tb, leader_full0 + stage * 8, (G.tap[t] * prm.cin_blocks + cb) * 64, n0,
                                              kEvictLast);
                             if (++stage == static_cast<uint32_t>(ex.stages)) {
                                 stage = 0;
@@ -467,7 +484,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA, one thread) ----------------
         if (rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = umma_idesc(2 * kConvBM, BN, 0, 0);
+            constexpr uint32_t idesc_full = umma_idesc(2 * kConvBM, BN, 0, 0), idesc_half = umma_idesc(2 * kConvBM, BN / 2, 0, 0);
             constexpr uint32_t kDescHi = 0x40004040u;  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
             constexpr uint32_t kDescLo = 0x10000u;     // LBO = 1
             auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
@@ -476,8 +493,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t b_lo0 = kDescLo | ((smem_u32(ring) & 0x3FFFFu) >> 4);
             uint32_t stage = 0, phase = 0, hb = 0, hph = 0;
             int i = 0;
-            for (int u = pair; u < ex.units; u += num_pairs, ++i) {
+            for (int w = pair; w < items; w += num_pairs, ++i) {
                 const uint32_t buf = i & 1;
+                const uint32_t idesc = w >= ex.full_units ? idesc_half : idesc_full;
                 mbar_wait(&tempty_bar[buf], ((i >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
@@ -518,16 +536,23 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp >= 4) {
         // ---------------- epilogue (both CTAs): lane = output position; warps 4-7 / 8-11 take the two column halves ----------------
         const int ew = warp & 3;
-        const int c0 = ((warp - 4) >> 2) * (BN / 2);
+        const int colhalf = (warp - 4) >> 2;
         const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
         int i = 0;
-        for (int u = pair; u < ex.units; u += num_pairs, ++i) {
+        for (int w = pair; w < items; w += num_pairs, ++i) {
             const uint32_t buf = i & 1;
-            const int pt = u / ex.n_blocks, nb = u - pt * ex.n_blocks;
-            const int n0 = nb * BN + c0;
+            int pt, n_base;
+            bool half;
+            decode(w, pt, n_base, half);
             const int pw = pt * (2 * kConvBM) + static_cast<int>(rank) * kConvBM + ew * 32;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN + c0;
-            conv_epilogue_rows<BN / 2>(prm, s_bias, s_prelu, s_bns, s_bnb, taddr, pw, n0, lane, &tfull_bar[buf], (i >> 1) & 1);
+            const uint32_t tlane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * BN;
+            if (!half) {
+                const int c0 = colhalf * (BN / 2);
+                conv_epilogue_rows<BN / 2>(prm, s_bias, s_prelu, s_bns, s_bnb, tlane + c0, pw, n_base + c0, lane, &tfull_bar[buf], (i >> 1) & 1);
+            } else {
+                const int c0 = colhalf * (BN / 4);
+                conv_epilogue_rows<BN / 4>(prm, s_bias, s_prelu, s_bns, s_bnb, tlane + c0, pw, n_base + c0, lane, &tfull_bar[buf], (i >> 1) & 1);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader0 + buf * 8);

@@ -194,8 +194,18 @@ void launch_pair(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) 
     ex.stages = std::min(kMtMaxStages, (kSmemBudget - fixed) / ((BN / 2) * 128));
     if (ex.stages < 2) throw StateError{"conv3x3_pair_kernel: halo tile does not fit in shared memory"};
     const int smem = conv_mt_smem_bytes(BN / 2, ex.halo_chunks, ex.stages);
-    const int pairs = std::min(ex.units, g_conv_sms / 2);
-    conv3x3_pair_kernel<BN><<<2 * pairs, kMtThreads, smem, st>>>(s.ta, BN == 128 ? s.tb64 : s.tb, prm, ex);
+    const int all_pairs = g_conv_sms / 2;
+    // a short last round (at most half the pairs busy) is split into half-width items: it then costs half a unit's time
+    static const bool split_tail = std::getenv("FR_PAIR_SPLIT") == nullptr || std::atoi(std::getenv("FR_PAIR_SPLIT")) != 0;
+    const int rem = ex.units % all_pairs;
+    ex.full_units = ex.units;
+    ex.half_items = 0;
+    if (split_tail && BN == 256 && s.has64 && ex.units > all_pairs && rem > 0 && 2 * rem <= all_pairs) {
+        ex.full_units = ex.units - rem;
+        ex.half_items = 2 * rem;
+    }
+    const int pairs = std::min(ex.full_units + ex.half_items, all_pairs);
+    conv3x3_pair_kernel<BN><<<2 * pairs, kMtThreads, smem, st>>>(s.ta, BN == 128 ? s.tb64 : s.tb, s.tb64, prm, ex);
 }
 
 // FR_PAIR=0: never use the CTA-pair kernel; FR_PAIR_BN=128|256 pins its tile width (A/B)
