@@ -733,22 +733,19 @@ int fr_embedder_run_dev(FrEmbedder* e, const float* chw_dev, int batch, float* o
         check_batch(e, chw_dev, batch, out512_dev);
         DeviceGuard dg(e->device);
         // the plan runs on the handle's stream; order it after / before the caller's stream with events
+        // (stream == NULL is the legacy default stream: the handle's stream is non-blocking and does not synchronise with it implicitly)
         cudaStream_t user = static_cast<cudaStream_t>(stream);
         cudaEvent_t ev;
         FRB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        if (user) {
-            FRB_CUDA(cudaEventRecord(ev, user));
-            FRB_CUDA(cudaStreamWaitEvent(e->stream, ev, 0));
-        }
+        FRB_CUDA(cudaEventRecord(ev, user));
+        FRB_CUDA(cudaStreamWaitEvent(e->stream, ev, 0));
         FRB_CUDA(cudaMemcpyAsync(e->in_f32, chw_dev, sizeof(float) * batch * 3 * 112 * 112, cudaMemcpyDeviceToDevice, e->stream));
         e->last_batch = batch;
         e->last_u8 = false;
         forward_all(e, batch, false);
         FRB_CUDA(cudaMemcpyAsync(out512_dev, e->out_dev, sizeof(float) * batch * 512, cudaMemcpyDeviceToDevice, e->stream));
-        if (user) {
-            FRB_CUDA(cudaEventRecord(ev, e->stream));
-            FRB_CUDA(cudaStreamWaitEvent(user, ev, 0));
-        }
+        FRB_CUDA(cudaEventRecord(ev, e->stream));
+        FRB_CUDA(cudaStreamWaitEvent(user, ev, 0));
         cudaEventDestroy(ev);
     });
 }

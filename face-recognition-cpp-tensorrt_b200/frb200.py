@@ -561,6 +561,10 @@ class Pipeline:
         L.fr_pipeline_destroy.restype = None
         L.fr_pipeline_destroy.argtypes = [C.c_void_p]
         L.fr_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fr_pipeline_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.fr_pipeline_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fr_pipeline_in_flight.argtypes = [C.c_void_p]
+        self._pending = []  # (frames kept alive, n, want_embeddings) per submitted batch
         h = C.c_void_p()
         check(L.fr_pipeline_create(det._h, emb._h, gal._h if gal is not None else None, C.byref(h)))
         self._h, self.det, self.emb, self.gal = h, det, emb, gal
@@ -595,6 +599,38 @@ class Pipeline:
         if want_embeddings:
             res["embeddings"] = emb
         return res
+
+    def submit(self, frames, want_embeddings: bool = False) -> None:
+        """enqueue a batch without waiting for the GPU (at most two in flight); `frames` is kept alive until it is collected"""
+        if isinstance(frames, np.ndarray):
+            f = np.ascontiguousarray(frames, dtype=np.uint8)
+            n, w = f.shape[0], f.shape[2]
+        else:
+            f, n, w = frames, frames.shape[0], frames.shape[2]
+        check(lib().fr_pipeline_submit(self._h, _ptr(f), w * 3, n, 1 if want_embeddings else 0))
+        self._pending.append((f, n, want_embeddings))
+
+    def collect(self, out=None):
+        """results of the oldest submitted batch (same dict as run)"""
+        if not self._pending:
+            raise RuntimeError("nothing was submitted")
+        _, n, want_embeddings = self._pending[0]
+        mf = self.det.max_faces
+        o = out or {}
+        boxes = o.get("boxes") if out else np.zeros((n, mf), BOX_DTYPE)
+        counts = o.get("counts") if out else np.zeros(n, np.int32)
+        idx = o.get("idx") if out else np.zeros((n, mf), np.int64)
+        score = o.get("score") if out else np.zeros((n, mf), np.float32)
+        emb = np.zeros((n, mf, 512), np.float32) if want_embeddings else None
+        check(lib().fr_pipeline_collect(self._h, _ptr(boxes), _ptr(counts), _ptr(idx), _ptr(score), _ptr(emb)))
+        self._pending.pop(0)
+        res = {"boxes": boxes, "counts": counts, "idx": idx, "score": score}
+        if want_embeddings:
+            res["embeddings"] = emb
+        return res
+
+    def in_flight(self) -> int:
+        return int(lib().fr_pipeline_in_flight(self._h))
 
 
 class Exchange:

@@ -323,6 +323,15 @@ void fr_pipeline_destroy(FrPipeline *p);
  * slots or when there is no gallery), embeddings (optional) [f*max_faces+j][512]. */
 int fr_pipeline_run(FrPipeline *p, const uint8_t *frames, int stride, int batch, FrBbox *boxes, int *counts, int64_t *top1_idx,
                     float *top1_score, float *embeddings);
+/* The same with two batches in flight: submit enqueues a batch (H2D in sub-batches on a copy stream, detection, device-side face-list
+ * compaction, crop + embed + search for as many faces as the previous batch had) and returns without waiting for the GPU; collect waits
+ * for the OLDEST submitted batch and fills the outputs of fr_pipeline_run. While batch i computes, batch i + 1's frames cross PCIe and
+ * the host prepares batch i + 2: the request-batching loop a server runs (src/app.cpp:293-352 handles one request at a time under a
+ * lock, :367). `frames` must stay valid and unchanged until the batch is collected. At most two batches may be in flight (FR_ESTATE
+ * otherwise); fr_pipeline_run requires none. embeddings may only be collected from a batch submitted with want_embeddings != 0. */
+int fr_pipeline_submit(FrPipeline *p, const uint8_t *frames, int stride, int batch, int want_embeddings);
+int fr_pipeline_collect(FrPipeline *p, FrBbox *boxes, int *counts, int64_t *top1_idx, float *top1_score, float *embeddings);
+int fr_pipeline_in_flight(const FrPipeline *p);
 
 #ifdef __cplusplus
 }

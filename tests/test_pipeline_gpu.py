@@ -138,3 +138,39 @@ def test_end_to_end_identities(nets):
     pipe.close()
     pipe2.close()
     gal.close()
+
+
+def test_two_batches_in_flight_equal_synchronous_runs(nets):
+    """fr_pipeline_submit / fr_pipeline_collect (two batches in flight, speculative face count) return exactly what the synchronous
+    call returns for the same frames — including a batch with MORE faces than the one before it (the guess is too small and the rest is
+    embedded at collect time), a batch with fewer, and the error cases of the ring."""
+    det, emb, arc_sd = nets
+    frames = mgr.det_frames(6, 640, 640, seed=13)
+    blank = np.full((2, 640, 640, 3), 128, np.uint8)  # no detections
+    batches = [frames[:2], blank, frames[:6], frames[2:3], blank[:1], frames[1:5]]
+    G = so.synth_rows(np.arange(30_000), seed=5)
+    gal = frb200.Gallery.from_rows(G)
+    pipe = frb200.Pipeline(det, emb, gal)
+    want = [pipe.run(b, want_embeddings=True) for b in batches]
+    assert [int(w["counts"].sum()) for w in want] == [8, 0, 24, 4, 0, 16]
+    got = []
+    pipe.submit(batches[0], want_embeddings=True)
+    for b in batches[1:]:
+        pipe.submit(b, want_embeddings=True)
+        assert pipe.in_flight() == 2
+        with pytest.raises(frb200.FrError) as e:
+            pipe.submit(b)
+        assert e.value.code == frb200.FR_ESTATE
+        got.append(pipe.collect())
+    got.append(pipe.collect())
+    assert pipe.in_flight() == 0
+    with pytest.raises((frb200.FrError, RuntimeError)):
+        pipe.collect()
+    for w, g in zip(want, got):
+        for key in ("counts", "idx"):
+            assert np.array_equal(w[key], g[key]), key
+        assert np.array_equal(w["boxes"], g["boxes"])
+        assert np.array_equal(w["score"].view(np.uint32), g["score"].view(np.uint32))
+        assert np.array_equal(w["embeddings"].view(np.uint32), g["embeddings"].view(np.uint32))
+    pipe.close()
+    gal.close()
