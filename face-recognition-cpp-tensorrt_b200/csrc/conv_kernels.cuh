@@ -164,6 +164,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float* s_bns = s_prelu + BN;
     float* s_bnb = s_bns + BN;
 
+    griddep_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int p0 = blockIdx.x * kConvBM;
@@ -199,6 +200,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();  // everything above touched only this CTA's state and static parameters
 
     if (warp == 0) {
         if (elect_one()) {

@@ -165,6 +165,7 @@ template <int BN, int MT>
 __global__ void __launch_bounds__(kMtThreads, 1)
 conv3x3_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ ConvGemmParams prm, const __grid_constant__ ConvMtExtra ex) {
+    griddep_launch_dependents();
     constexpr int kABytes = kConvBM * 128, kBBytes = BN * 128;
     constexpr uint32_t kTmemCols = 2 * MT * BN;  // two accumulator sets
     static_assert(kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
@@ -227,6 +228,7 @@ conv3x3_mt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();  // everything above touched only this CTA's state and static parameters
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
@@ -367,6 +369,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMtThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_b_half, const __grid_constant__ ConvGemmParams prm,
                     const __grid_constant__ ConvMtExtra ex) {
+    griddep_launch_dependents();
     constexpr int kABytes = kConvBM * 128, kBHalf = (BN / 2) * 128;
     constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator sets
     static_assert(kTmemCols == 256 || kTmemCols == 512, "TMEM allocation must be a power of two <= 512");
@@ -440,6 +443,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();
 
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs) ----------------

@@ -77,10 +77,12 @@ __global__ void __launch_bounds__(256) dwpw_gemm_kernel(const __grid_constant__ 
         for (int i = t; i < prm.cin; i += 128) s_db[i] = __ldg(prm.dw_b + i);
         for (int i = t; i < BN; i += 128) s_pb[i] = __ldg(prm.pw_b + i);
     }
+    griddep_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();
 
     if (warp == 0) {
         if (elect_one()) {

@@ -44,6 +44,8 @@ __device__ __forceinline__ void lin_coef(int d, double scale, int ssize, int& s0
 __global__ void __launch_bounds__(256) det_letterbox_kernel(const uint8_t* __restrict__ frames, int frame_h, int frame_w, int stride,
                                                             int batch, int Hn, int Wn, int rw, int rh, int ox, int oy,
                                                             uint8_t* __restrict__ canvas) {
+    griddep_launch_dependents();
+    griddep_wait();
     const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= static_cast<long long>(batch) * Hn * Wn) return;
     const int img = static_cast<int>(t / (Hn * Wn));
@@ -79,12 +81,14 @@ __global__ void __launch_bounds__(256) det_stem_kernel(const uint8_t* __restrict
     __shared__ float sb[8];
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) ws[i % 27][i / 27] = w[i];
     if (threadIdx.x < 8) sb[threadIdx.x] = bias[threadIdx.x];
+    griddep_launch_dependents();
     __syncthreads();
+    griddep_wait();  // the weights staged above are static; the frames and the output map are not
     const Geo g{Hn / 2, Wn / 2};
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= static_cast<long long>(batch) * g.H * g.W) return;
-    const int img = static_cast<int>(t / (g.H * g.W));
-    const int rc = static_cast<int>(t - static_cast<long long>(img) * g.H * g.W);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // pixels of a batch < 2^31 (checked by the host)
+    if (t >= batch * g.H * g.W) return;
+    const int img = t / (g.H * g.W);
+    const int rc = t - img * (g.H * g.W);
     const int r = rc / g.W, c = rc % g.W;
     const float mean[3] = {104.f, 117.f, 123.f};
     float acc[8];
@@ -124,12 +128,14 @@ __global__ void __launch_bounds__(256) det_stem_f32_kernel(const float* __restri
     __shared__ float sb[8];
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) ws[i % 27][i / 27] = w[i];
     if (threadIdx.x < 8) sb[threadIdx.x] = bias[threadIdx.x];
+    griddep_launch_dependents();
     __syncthreads();
+    griddep_wait();  // the weights staged above are static; the frames and the output map are not
     const Geo g{Hn / 2, Wn / 2};
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= static_cast<long long>(batch) * g.H * g.W) return;
-    const int img = static_cast<int>(t / (g.H * g.W));
-    const int rc = static_cast<int>(t - static_cast<long long>(img) * g.H * g.W);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // pixels of a batch < 2^31 (checked by the host)
+    if (t >= batch * g.H * g.W) return;
+    const int img = t / (g.H * g.W);
+    const int rc = t - img * (g.H * g.W);
     const int r = rc / g.W, c = rc % g.W;
     float acc[8];
 #pragma unroll
@@ -163,13 +169,15 @@ __global__ void __launch_bounds__(256) det_stem_f32_kernel(const float* __restri
 //      (output pixel, 8 channels). w: [9][C] f32.
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __half* __restrict__ in, Geo gi, __half* __restrict__ out, Geo go, int stride,
                                                     int C, int batch, const float* __restrict__ w, const float* __restrict__ bias) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int chunks = C / 8;
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= static_cast<long long>(batch) * go.H * go.W * chunks) return;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // (pixels x chunks) of a batch < 2^32 (checked by the host)
+    if (t >= static_cast<unsigned>(batch) * go.H * go.W * chunks) return;
     const int ch = static_cast<int>(t % chunks) * 8;
-    const long long pix = t / chunks;
-    const int img = static_cast<int>(pix / (go.H * go.W));
-    const int rc = static_cast<int>(pix - static_cast<long long>(img) * go.H * go.W);
+    const int pix = static_cast<int>(t / chunks);
+    const int img = pix / (go.H * go.W);
+    const int rc = pix - img * (go.H * go.W);
     const int r = rc / go.W, c = rc % go.W;
     float acc[8];
 #pragma unroll
@@ -205,157 +213,297 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __half* __restrict__ i
     *reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * go.HpWp() + r * go.Wp() + c) * C + ch) = pk;
 }
 
+// fp32 weights as mma.sync B fragments: {b0, b1} rounded to fp16 (x, y) and the fp16 of what the rounding lost (z, w)
+__device__ __forceinline__ uint4 split_weight_frag(float w0, float w1, float w8, float w9) {
+    const __half2 h0 = __floats2half2_rn(w0, w1), h1 = __floats2half2_rn(w8, w9);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(w0 - f0.x, w1 - f0.y), l1 = __floats2half2_rn(w8 - f1.x, w9 - f1.y);
+    return make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1), *reinterpret_cast<const uint32_t*>(&l0),
+                      *reinterpret_cast<const uint32_t*>(&l1));
+}
+
 // ---- FUSED conv_dw block for the early layers (net.py:29-38): depthwise 3x3 (stride S, pad 1) + BN + ReLU, then pointwise 1x1 +
-//      BN + ReLU, CIN < 64. One thread per output pixel: the nine taps come straight from global memory through L1 (neighbouring
-//      pixels share them), the depthwise result stays in registers (fp32, never written to global memory) and feeds the CIN -> COUT
-//      pointwise product, whose weights are broadcast from shared memory. Grid-stride: the weights are staged once per CTA.
-//      Compared with dw3x3_kernel + pw_small_kernel this removes the write + re-read of the depthwise map and one launch per block.
-//      dw_w: [9][CIN] f32, pw_w: [CIN][COUT] f32.
+//      BN + ReLU, CIN < 64. A warp owns 32 output pixels per pass:
+//        1. depthwise: lane = pixel, the nine taps come straight from global memory through L1 (neighbouring pixels share them), fp32
+//           accumulation in registers; the result (fp16, as the unfused pair of kernels stored it) goes to the warp's tile in shared
+//           memory and never to global memory;
+//        2. pointwise: the [32 pixels x CIN] tile times the [CIN x COUT] weights on the tensor cores with warp-level mma.sync
+//           (m16n8k16 / m16n8k8 fragments via ldmatrix; the weight fragments are laid out once per CTA) instead of CIN * COUT FFMAs per
+//           thread - the CUDA-core version was instruction-bound at 3x the time of its memory traffic;
+//        3. bias + ReLU on the accumulator fragments, staged through shared memory and written back as whole rows (a lane-per-pixel
+//           store would touch 32 different lines per instruction).
+//      Grid-stride over groups of 32 pixels. dw_w: [9][CIN] f32, pw_w: [CIN][COUT] f32 (rounded to fp16 here, like every GEMM layer's).
 template <int CIN, int COUT, int S>
 __global__ void __launch_bounds__(256) dwpw_small_kernel(const __half* __restrict__ in, Geo gi, __half* __restrict__ out, Geo go, int batch,
                                                          const float* __restrict__ dw_w, const float* __restrict__ dw_b,
                                                          const float* __restrict__ pw_w, const float* __restrict__ pw_b) {
+    constexpr int KS = CIN >= 16 ? CIN / 16 : 1;  // k-steps (k16, or one k8 step for CIN = 8)
+    constexpr int NT = COUT / 8;                  // 8-column output tiles
+    constexpr int kInStride = CIN * 2 + 16;       // bytes per pixel row of the depthwise tile (padded: conflict-free ldmatrix)
+    constexpr int kOutStride = COUT * 2 + 16;     // bytes per pixel row of the output tile
+    constexpr int kTileBytes = 32 * (kInStride > kOutStride ? kInStride : kOutStride);
     __shared__ float sdw[9][CIN];
     __shared__ float sdb[CIN];
-    __shared__ float4 spw[CIN][COUT / 4];
     __shared__ float spb[COUT];
+    // weight fragments {b0, b1} of lane l for k-step ks, column tile nt, as fp16 hi + fp16 lo (w = hi + lo to ~22 bits: two MMAs per
+    // fragment keep the fp32 weights' accuracy - with single fp16 weights the raw heads drifted past 1e-2 of the fp32 oracle)
+    __shared__ uint4 sbf[KS][NT][32];
+    __shared__ __align__(16) uint8_t tiles[8][kTileBytes];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
     for (int i = threadIdx.x; i < 9 * CIN; i += blockDim.x) reinterpret_cast<float*>(&sdw[0][0])[i] = dw_w[i];
-    for (int i = threadIdx.x; i < CIN * COUT; i += blockDim.x) reinterpret_cast<float*>(&spw[0][0])[i] = pw_w[i];
     for (int i = threadIdx.x; i < CIN; i += blockDim.x) sdb[i] = dw_b[i];
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) spb[i] = pw_b[i];
+    for (int i = threadIdx.x; i < KS * NT * 32; i += blockDim.x) {
+        const int l = i & 31, nt = (i >> 5) % NT, ks = i / (32 * NT);
+        const int n = nt * 8 + (l >> 2), k0 = ks * 16 + (l & 3) * 2;
+        auto w = [&](int k) { return k < CIN ? pw_w[k * COUT + n] : 0.f; };
+        sbf[ks][nt][l] = split_weight_frag(w(k0), w(k0 + 1), w(k0 + 8), w(k0 + 9));
+    }
+    griddep_launch_dependents();
     __syncthreads();
-    const long long total = static_cast<long long>(batch) * go.H * go.W;
-    for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int img = static_cast<int>(t / (go.H * go.W));
-        const int rc = static_cast<int>(t - static_cast<long long>(img) * go.H * go.W);
-        const int r = rc / go.W, c = rc - r * go.W;
-        float x[CIN];
+    griddep_wait();  // weights are static; the input map belongs to the kernel before this one
+    uint8_t* tile = tiles[warp];
+    const uint32_t tile_addr = smem_u32(tile);
+    const int hw = go.H * go.W;
+    const int total = batch * hw;  // < 2^31 (checked by the host): 32-bit index arithmetic, no 64-bit divisions per pixel
+    const int groups = (total + 31) / 32;
+    for (int grp = blockIdx.x * 8 + warp; grp < groups; grp += gridDim.x * 8) {
+        // ---------------- 1. depthwise, lane = pixel ----------------
+        const int t = grp * 32 + lane;
+        const bool live = t < total;
+        int pos = 0;  // matrix row of this lane's output pixel
+        {
+            uint4 packed[CIN / 8];
+            if (live) {
+                const int img = t / hw;
+                const int rc = t - img * hw;
+                const int r = rc / go.W, c = rc - r * go.W;
+                pos = img * go.HpWp() + r * go.Wp() + c;
+                float x[CIN];
 #pragma unroll
-        for (int k = 0; k < CIN; ++k) x[k] = sdb[k];
-        const __half* ibase = in + static_cast<size_t>(img) * gi.HpWp() * CIN;
+                for (int k = 0; k < CIN; ++k) x[k] = sdb[k];
+                const __half* ibase = in + static_cast<size_t>(img) * gi.HpWp() * CIN;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int rr = r * S + ky - 1;
-            if (rr < 0) continue;  // rr == gi.H is the zero pad row
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int rr = r * S + ky - 1;
+                    if (rr < 0) continue;  // rr == gi.H is the zero pad row
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int cc = c * S + kx - 1;
-                if (cc < 0) continue;  // cc == gi.W is the zero pad column
-                const uint4* src = reinterpret_cast<const uint4*>(ibase + (static_cast<size_t>(rr) * gi.Wp() + cc) * CIN);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int cc = c * S + kx - 1;
+                        if (cc < 0) continue;  // cc == gi.W is the zero pad column
+                        const uint4* src = reinterpret_cast<const uint4*>(ibase + (static_cast<size_t>(rr) * gi.Wp() + cc) * CIN);
+                        uint4 v[CIN / 8];
+                        if (CIN >= 16) {  // 32 bytes per load: half the L1 wavefronts of 16-byte loads at this stride
+#pragma unroll
+                            for (int ch = 0; ch < CIN / 8; ch += 2) ld_global_nc_256(src + ch, v[ch], v[ch + 1 < CIN / 8 ? ch + 1 : ch]);
+                        } else {
+                            v[0] = __ldg(src);
+                        }
+#pragma unroll
+                        for (int ch = 0; ch < CIN / 8; ++ch) {
+                            const __half2* h = reinterpret_cast<const __half2*>(&v[ch]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 f = __half22float2(h[q]);
+                                x[ch * 8 + 2 * q] = fmaf(f.x, sdw[ky * 3 + kx][ch * 8 + 2 * q], x[ch * 8 + 2 * q]);
+                                x[ch * 8 + 2 * q + 1] = fmaf(f.y, sdw[ky * 3 + kx][ch * 8 + 2 * q + 1], x[ch * 8 + 2 * q + 1]);
+                            }
+                        }
+                    }
+                }
 #pragma unroll
                 for (int ch = 0; ch < CIN / 8; ++ch) {
-                    const uint4 v = __ldg(src + ch);
-                    const __half2* h = reinterpret_cast<const __half2*>(&v);
+                    __half2* hp = reinterpret_cast<__half2*>(&packed[ch]);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 f = __half22float2(h[q]);
-                        x[ch * 8 + 2 * q] = fmaf(f.x, sdw[ky * 3 + kx][ch * 8 + 2 * q], x[ch * 8 + 2 * q]);
-                        x[ch * 8 + 2 * q + 1] = fmaf(f.y, sdw[ky * 3 + kx][ch * 8 + 2 * q + 1], x[ch * 8 + 2 * q + 1]);
+                    for (int q = 0; q < 4; ++q) hp[q] = __floats2half2_rn(fmaxf(x[ch * 8 + 2 * q], 0.f), fmaxf(x[ch * 8 + 2 * q + 1], 0.f));
+                }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < CIN / 8; ++ch) packed[ch] = make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int ch = 0; ch < CIN / 8; ++ch) *reinterpret_cast<uint4*>(tile + lane * kInStride + ch * 16) = packed[ch];
+        }
+        __syncwarp();
+        // ---------------- 2. pointwise on the tensor cores: [32 x CIN] x [CIN x COUT] ----------------
+        float acc[2][NT][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                if (CIN >= 16) {
+                    // ldmatrix x4: lanes 0-7 / 8-15 / 16-23 / 24-31 address the rows of the (rows 0-7, k 0-7) / (rows 8-15, k 0-7) /
+                    // (rows 0-7, k 8-15) / (rows 8-15, k 8-15) 8x8 blocks = fragments a0..a3
+                    uint32_t a[4];
+                    const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
+                    ldmatrix_x4(a, tile_addr + row * kInStride + col * 2);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const uint4 b = sbf[ks][nt][lane];
+                        mma_m16n8k16(acc[mt][nt], a, b.x, b.y);
+                        mma_m16n8k16(acc[mt][nt], a, b.z, b.w);
+                    }
+                } else {
+                    uint32_t a[2];
+                    const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;  // lanes 16-31: addresses unused by x2 (kept valid)
+                    ldmatrix_x2(a, tile_addr + row * kInStride);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const uint4 b = sbf[0][nt][lane];
+                        mma_m16n8k8(acc[mt][nt], a, b.x);
+                        mma_m16n8k8(acc[mt][nt], a, b.z);
                     }
                 }
             }
         }
+        __syncwarp();  // every lane has read its A fragments: the tile may be overwritten with the outputs
+        // ---------------- 3. bias + ReLU, staged rows, whole-row stores ----------------
 #pragma unroll
-        for (int k = 0; k < CIN; ++k) x[k] = fmaxf(x[k], 0.f);
-        __half* dst_px = out + (static_cast<size_t>(img) * go.HpWp() + static_cast<size_t>(r) * go.Wp() + c) * COUT;
-#pragma unroll 1
-        for (int n0 = 0; n0 < COUT; n0 += 16) {
-            float acc[16];
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) acc[q] = spb[n0 + q];
-#pragma unroll
-            for (int k = 0; k < CIN; ++k) {
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 wv = spw[k][n0 / 4 + j4];
-                    acc[4 * j4 + 0] = fmaf(x[k], wv.x, acc[4 * j4 + 0]);
-                    acc[4 * j4 + 1] = fmaf(x[k], wv.y, acc[4 * j4 + 1]);
-                    acc[4 * j4 + 2] = fmaf(x[k], wv.z, acc[4 * j4 + 2]);
-                    acc[4 * j4 + 3] = fmaf(x[k], wv.w, acc[4 * j4 + 3]);
-                }
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = nt * 8 + t4 * 2;
+                const float b0 = spb[col], b1 = spb[col + 1];
+                const __half2 lo = __floats2half2_rn(fmaxf(acc[mt][nt][0] + b0, 0.f), fmaxf(acc[mt][nt][1] + b1, 0.f));
+                const __half2 hi = __floats2half2_rn(fmaxf(acc[mt][nt][2] + b0, 0.f), fmaxf(acc[mt][nt][3] + b1, 0.f));
+                *reinterpret_cast<__half2*>(tile + (mt * 16 + g) * kOutStride + col * 2) = lo;
+                *reinterpret_cast<__half2*>(tile + (mt * 16 + g + 8) * kOutStride + col * 2) = hi;
             }
-            uint4 pk[2];
-            __half2* hp = reinterpret_cast<__half2*>(pk);
+        __syncwarp();
+        constexpr int CPR = COUT * 2 / 16;  // 16-byte chunks per output row
+        constexpr int RPI = 32 / CPR;       // rows per store instruction
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) hp[q] = __floats2half2_rn(fmaxf(acc[2 * q], 0.f), fmaxf(acc[2 * q + 1], 0.f));
-            st_global_256(dst_px + n0, pk[0], pk[1]);
+        for (int i = 0; i < CPR; ++i) {
+            const int q = i * RPI + lane / CPR, chunk = lane % CPR;
+            const int pos_q = __shfl_sync(0xffffffffu, pos, q);
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + q * kOutStride + chunk * 16);
+            if ((live_mask >> q) & 1u) *reinterpret_cast<uint4*>(out + static_cast<size_t>(pos_q) * COUT + chunk * 8) = v;
         }
+        __syncwarp();  // the tile is rewritten by the next pass
     }
 }
 
 // ---- SSH 16 -> 16 3x3 conv + BN + ReLU (conv5X5_2, conv7X7_2, conv7x7_3, net.py:49-53; the ReLU is either the layer's own or
-//      the one applied to the concatenation, net.py:64-65). w: [9][16][16] f32 (tap, cin, cout). Output may be a channel slice
-//      of a wider map (ld_out, pre-offset pointer). NCONV = 2: conv5X5_2 and conv7X7_2 read the same map (net.py:58-61), so one
-//      pass over it computes both (second weight set wB, second destination outB).
+//      the one applied to the concatenation, net.py:64-65). Output may be a channel slice of a wider map (ld_out, pre-offset pointer).
+//      NCONV = 2: conv5X5_2 and conv7X7_2 read the same map (net.py:58-61), so one pass over it computes both (second weight set wB,
+//      second destination outB). w: [9][16][16] f32 (tap, cin, cout), rounded to fp16 here.
+//      A warp owns 32 pixels per pass; per kernel row ky every lane stages its pixel's three taps (3 x 32 bytes, zero outside the map)
+//      in the warp's shared-memory tile, and the [32 pixels x 16 channels] x [16 x 16*NCONV] product of each tap runs on the tensor
+//      cores (mma.sync m16n8k16, fragments via ldmatrix): 36 / 72 MMAs per pass instead of 2304 / 4608 FFMAs per thread.
 template <int NCONV>
-__global__ void __launch_bounds__(128) conv3x3_c16_kernel(const __half* __restrict__ in, Geo g, int batch, const float* __restrict__ wA,
+__global__ void __launch_bounds__(NCONV == 2 ? 128 : 256) conv3x3_c16_kernel(const __half* __restrict__ in, Geo g, int batch, const float* __restrict__ wA,
                                                           const float* __restrict__ bA, __half* __restrict__ outA, int ldA,
                                                           const float* __restrict__ wB, const float* __restrict__ bB,
                                                           __half* __restrict__ outB, int ldB) {
-    constexpr int NO = 16 * NCONV;
-    __shared__ float4 ws[9 * 16][NO / 4];
-    __shared__ float sb[NO];
-    for (int i = threadIdx.x; i < 9 * 16 * 16; i += blockDim.x) {
-        reinterpret_cast<float*>(&ws[i / 16][0])[i % 16] = wA[i];
-        if (NCONV == 2) reinterpret_cast<float*>(&ws[i / 16][0])[16 + i % 16] = wB[i];
+    constexpr int NT = 2 * NCONV;   // 8-column output tiles
+    constexpr int kRow = 32 + 16;   // bytes per staged pixel (16 channels + pad: conflict-free ldmatrix)
+    constexpr int kWarps = NCONV == 2 ? 4 : 8;  // 48 KiB of static shared memory: fragments (hi + lo) + one tile per warp
+    __shared__ uint4 sbf[9][NT][32];  // weight fragments {b0, b1} as fp16 hi + lo (split_weight_frag) per tap / column tile / lane
+    __shared__ float sb[16 * NCONV];
+    __shared__ __align__(16) uint8_t tiles[kWarps][3 * 32 * kRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, t4 = lane & 3;
+    for (int i = threadIdx.x; i < 9 * NT * 32; i += blockDim.x) {
+        const int l = i & 31, nt = (i >> 5) % NT, tap = i / (32 * NT);
+        const float* w = nt < 2 ? wA : wB;
+        const int n = (nt & 1) * 8 + (l >> 2), k0 = (l & 3) * 2;
+        auto wv = [&](int k) { return w[(tap * 16 + k) * 16 + n]; };
+        sbf[tap][nt][l] = split_weight_frag(wv(k0), wv(k0 + 1), wv(k0 + 8), wv(k0 + 9));
     }
-    if (threadIdx.x < 16) {
-        sb[threadIdx.x] = bA[threadIdx.x];
-        if (NCONV == 2) sb[16 + threadIdx.x] = bB[threadIdx.x];
-    }
+    if (threadIdx.x < 16 * NCONV) sb[threadIdx.x] = threadIdx.x < 16 ? bA[threadIdx.x] : bB[threadIdx.x - 16];
+    griddep_launch_dependents();
     __syncthreads();
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= static_cast<long long>(batch) * g.H * g.W) return;
-    const int img = static_cast<int>(t / (g.H * g.W));
-    const int rc = static_cast<int>(t - static_cast<long long>(img) * g.H * g.W);
-    const int r = rc / g.W, c = rc % g.W;
-    float acc[NO];
+    griddep_wait();
+    uint8_t* tile = tiles[warp];
+    const uint32_t tile_addr = smem_u32(tile);
+    const int hw = g.H * g.W;
+    const int total = batch * hw;  // < 2^31 (checked by the host)
+    const int groups = (total + 31) / 32;
+    for (int grp = blockIdx.x * kWarps + warp; grp < groups; grp += gridDim.x * kWarps) {
+        const int t = grp * 32 + lane;
+        const bool live = t < total;
+        int img = 0, r = 0, c = 0, pos = 0;
+        if (live) {
+            img = t / hw;
+            const int rc = t - img * hw;
+            r = rc / g.W;
+            c = rc - r * g.W;
+            pos = img * g.HpWp() + r * g.Wp() + c;
+        }
+        float acc[2][NT][4];
 #pragma unroll
-    for (int j = 0; j < NO; ++j) acc[j] = sb[j];
-    const __half* ibase = in + static_cast<size_t>(img) * g.HpWp() * 16;
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int rr = r + ky - 1;
-        if (rr < 0) continue;
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int cc = c + kx - 1;
-            if (cc < 0) continue;
-            const uint4* src = reinterpret_cast<const uint4*>(ibase + (static_cast<size_t>(rr) * g.Wp() + cc) * 16);
-            const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
-            float x[16];
-            const __half2* h0 = reinterpret_cast<const __half2*>(&v0);
-            const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
+                for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.f;
+        const __half* ibase = in + static_cast<size_t>(img) * g.HpWp() * 16;
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ++ky) {
+            // stage this lane's three taps of kernel row ky (row g.H / column g.W are the layout's zero pads, read as stored)
+            const int rr = r + ky - 1;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-                x[2 * j] = a.x;
-                x[2 * j + 1] = a.y;
-                x[8 + 2 * j] = b.x;
-                x[8 + 2 * j + 1] = b.y;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int cc = c + kx - 1;
+                uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+                if (live && rr >= 0 && cc >= 0) ld_global_nc_256(ibase + (static_cast<size_t>(rr) * g.Wp() + cc) * 16, v0, v1);
+                uint4* dst = reinterpret_cast<uint4*>(tile + (kx * 32 + lane) * kRow);
+                dst[0] = v0;
+                dst[1] = v1;
             }
-            const int tap = ky * 3 + kx;
+            __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
+            for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                for (int j4 = 0; j4 < NO / 4; ++j4) {
-                    const float4 wv = ws[tap * 16 + k][j4];
-                    acc[4 * j4 + 0] = fmaf(x[k], wv.x, acc[4 * j4 + 0]);
-                    acc[4 * j4 + 1] = fmaf(x[k], wv.y, acc[4 * j4 + 1]);
-                    acc[4 * j4 + 2] = fmaf(x[k], wv.z, acc[4 * j4 + 2]);
-                    acc[4 * j4 + 3] = fmaf(x[k], wv.w, acc[4 * j4 + 3]);
+                for (int mt = 0; mt < 2; ++mt) {
+                    uint32_t a[4];
+                    const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = (lane >> 4) * 8;
+                    ldmatrix_x4(a, tile_addr + (kx * 32 + row) * kRow + col * 2);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const uint4 b = sbf[ky * 3 + kx][nt][lane];
+                        mma_m16n8k16(acc[mt][nt], a, b.x, b.y);
+                        mma_m16n8k16(acc[mt][nt], a, b.z, b.w);
+                    }
                 }
+            __syncwarp();  // all fragments are in registers: the tile may be restaged
+        }
+        // bias + ReLU -> staged rows [32 pixels][16 * NCONV channels] -> row stores (conv A: channels 0-15, conv B: 16-31)
+        constexpr int kOut = 32 * NCONV + 16;  // bytes per staged output row
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = nt * 8 + t4 * 2;
+                const float b0 = sb[col], b1 = sb[col + 1];
+                const __half2 lo = __floats2half2_rn(fmaxf(acc[mt][nt][0] + b0, 0.f), fmaxf(acc[mt][nt][1] + b1, 0.f));
+                const __half2 hi = __floats2half2_rn(fmaxf(acc[mt][nt][2] + b0, 0.f), fmaxf(acc[mt][nt][3] + b1, 0.f));
+                *reinterpret_cast<__half2*>(tile + (mt * 16 + gq) * kOut + col * 2) = lo;
+                *reinterpret_cast<__half2*>(tile + (mt * 16 + gq + 8) * kOut + col * 2) = hi;
+            }
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+#pragma unroll
+        for (int cv = 0; cv < NCONV; ++cv) {
+            __half* o = cv == 0 ? outA : outB;
+            const int ld = cv == 0 ? ldA : ldB;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {  // 16 pixels x 2 chunks per instruction
+                const int q = i * 16 + (lane >> 1), chunk = lane & 1;
+                const int pos_q = __shfl_sync(0xffffffffu, pos, q);
+                const uint4 v = *reinterpret_cast<const uint4*>(tile + q * kOut + cv * 32 + chunk * 16);
+                if ((live_mask >> q) & 1u) *reinterpret_cast<uint4*>(o + static_cast<size_t>(pos_q) * ld + chunk * 8) = v;
             }
         }
-    }
-    const size_t pos = static_cast<size_t>(img) * g.HpWp() + r * g.Wp() + c;
-#pragma unroll
-    for (int q = 0; q < NCONV; ++q) {
-        uint4 pk[2];
-        __half2* hp = reinterpret_cast<__half2*>(pk);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hp[j] = __floats2half2_rn(fmaxf(acc[q * 16 + 2 * j], 0.f), fmaxf(acc[q * 16 + 2 * j + 1], 0.f));
-        st_global_256(q == 0 ? outA + pos * ldA : outB + pos * ldB, pk[0], pk[1]);
+        __syncwarp();
     }
 }
 
@@ -444,6 +592,8 @@ __device__ __forceinline__ DetCand decode_candidate(const float4 b, float score,
 // leaves it zero again.
 __global__ void __launch_bounds__(256) det_decode_kernel(const float* __restrict__ loc, const float* __restrict__ conf, DetPostParams prm,
                                                          DetCand* __restrict__ ws, int* __restrict__ n_cand) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int img = blockIdx.y;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= prm.anchors) return;
@@ -464,6 +614,8 @@ __global__ void __launch_bounds__(256) det_nms_kernel(const float* __restrict__ 
     __shared__ DetCand kept;
     __shared__ int kept_pos;
     __shared__ int n_cand;
+    griddep_launch_dependents();
+    griddep_wait();
     const int img = blockIdx.x;
     DetCand* cand = ws + static_cast<size_t>(img) * prm.anchors;
     const float scale_h = __fdiv_rn(static_cast<float>(prm.net_h), static_cast<float>(prm.frame_h));  // :21

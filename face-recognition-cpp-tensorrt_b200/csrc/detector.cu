@@ -122,7 +122,7 @@ template <int BN>
 void launch_dwpw_gemm(const DStep& s, int batch, cudaStream_t st) {
     DwPwGemmParams p = s.dp;
     p.P = batch * s.go.HpWp();
-    dwpw_gemm_kernel<BN><<<(p.P + kConvBM - 1) / kConvBM, 256, DwPwGemmCfg<BN>::smem_bytes(p.cin), st>>>(s.tb, p);
+    launch_k(dwpw_gemm_kernel<BN>, dim3((p.P + kConvBM - 1) / kConvBM), dim3(256), DwPwGemmCfg<BN>::smem_bytes(p.cin), st, true, s.tb, p);
     count_launch();
 }
 
@@ -362,7 +362,7 @@ void launch_det_gemm(const DStep& s, int batch, cudaStream_t st) {
     ConvGemmParams prm = s.prm;
     prm.P = batch * s.go.HpWp();
     dim3 grid((prm.P + kConvBM - 1) / kConvBM, prm.cout / BN, 1);
-    conv_gemm_kernel<BN, false, HEADS><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
+    launch_k(conv_gemm_kernel<BN, false, HEADS>, grid, dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, st, true, s.ta, s.tb, prm);
     count_launch();
 }
 
@@ -373,8 +373,11 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
     NvtxRange nvtx("fr.detect.network");
     const Geo g1 = d->g[1];
     const long long px = static_cast<long long>(batch) * g1.H * g1.W;
-    if (canvas_dev) det_stem_kernel<<<blocks_for(px, 256), 256, 0, st>>>(canvas_dev, stride_bytes, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
-    else det_stem_f32_kernel<<<blocks_for(px, 256), 256, 0, st>>>(chw_dev, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
+    if (canvas_dev)
+        launch_k(det_stem_kernel, dim3(blocks_for(px, 256)), dim3(256), 0, st, true, canvas_dev, stride_bytes, batch, d->net_h, d->net_w, d->stem_w,
+                 d->stem_b, d->a0);
+    else
+        launch_k(det_stem_f32_kernel, dim3(blocks_for(px, 256)), dim3(256), 0, st, true, chw_dev, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
     count_launch();
     bool forked[2] = {false, false};
     cudaStream_t main_st = st;
@@ -392,14 +395,14 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
         switch (s.kind) {
             case kDw: {
                 const long long t = static_cast<long long>(batch) * s.go.H * s.go.W * (s.cin / 8);
-                dw3x3_kernel<<<blocks_for(t, 256), 256, 0, st>>>(s.in, s.gi, s.out, s.go, s.stride, s.cin, batch, s.w, s.b);
+                launch_k(dw3x3_kernel, dim3(blocks_for(t, 256)), dim3(256), 0, st, true, s.in, s.gi, s.out, s.go, s.stride, s.cin, batch, s.w, s.b);
                 count_launch();
                 break;
             }
             case kDwPwSmall: {
                 const long long t = static_cast<long long>(batch) * s.go.H * s.go.W;
                 const int nb = static_cast<int>(std::min<long long>((t + 255) / 256, 3LL * d->sms));  // grid-stride inside the kernel
-                auto launch = [&](auto kern) { kern<<<nb, 256, 0, st>>>(s.in, s.gi, s.out, s.go, batch, s.w, s.b, s.w2, s.b2); };
+                auto launch = [&](auto kern) { launch_k(kern, dim3(nb), dim3(256), 0, st, true, s.in, s.gi, s.out, s.go, batch, s.w, s.b, s.w2, s.b2); };
                 if (s.cin == 8 && s.cout == 16 && s.stride == 1) launch(dwpw_small_kernel<8, 16, 1>);
                 else if (s.cin == 16 && s.cout == 32 && s.stride == 2) launch(dwpw_small_kernel<16, 32, 2>);
                 else if (s.cin == 32 && s.cout == 32 && s.stride == 1) launch(dwpw_small_kernel<32, 32, 1>);
@@ -423,10 +426,13 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
                 break;
             case kC16: {
                 const long long t = static_cast<long long>(batch) * s.go.H * s.go.W;
+                const int nb = static_cast<int>(std::min<long long>((t + 255) / 256, 2LL * d->sms));  // grid-stride inside the kernel
                 if (s.w2)
-                    conv3x3_c16_kernel<2><<<blocks_for(t, 128), 128, 0, st>>>(s.in, s.go, batch, s.w, s.b, s.out, s.ld_out, s.w2, s.b2, s.out2, s.ld_out2);
+                    launch_k(conv3x3_c16_kernel<2>, dim3(static_cast<unsigned>(std::min<long long>((t + 127) / 128, 4LL * d->sms))), dim3(128), 0, st, true,
+                             s.in, s.go, batch, s.w, s.b, s.out, s.ld_out, s.w2, s.b2, s.out2, s.ld_out2);
                 else
-                    conv3x3_c16_kernel<1><<<blocks_for(t, 128), 128, 0, st>>>(s.in, s.go, batch, s.w, s.b, s.out, s.ld_out, nullptr, nullptr, nullptr, 0);
+                    launch_k(conv3x3_c16_kernel<1>, dim3(nb), dim3(256), 0, st, true, s.in, s.go, batch, s.w, s.b, s.out, s.ld_out,
+                             static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), static_cast<__half*>(nullptr), 0);
                 count_launch();
                 break;
             }
@@ -453,10 +459,9 @@ void run_post(FrDetector* d, const float* loc, const float* conf, const float* l
     p.bbox_thr = d->bbox_thr;
     p.max_faces = d->max_faces;
     p.anchors = d->anchors;
-    det_decode_kernel<<<dim3((d->anchors + 255) / 256, batch), 256, 0, st>>>(loc, conf, p, d->cand, d->n_cand);
-    det_nms_kernel<<<batch, 256, 0, st>>>(landm, p, d->cand, d->n_cand, d->boxes + static_cast<size_t>(slot0) * d->max_faces, d->counts + slot0,
-                                          d->out_landm + static_cast<size_t>(slot0) * d->max_faces * 10,
-                                          d->out_ids + static_cast<size_t>(slot0) * d->max_faces);
+    launch_k(det_decode_kernel, dim3((d->anchors + 255) / 256, batch), dim3(256), 0, st, true, loc, conf, p, d->cand, d->n_cand);
+    launch_k(det_nms_kernel, dim3(batch), dim3(256), 0, st, true, landm, p, d->cand, d->n_cand, d->boxes + static_cast<size_t>(slot0) * d->max_faces,
+             d->counts + slot0, d->out_landm + static_cast<size_t>(slot0) * d->max_faces * 10, d->out_ids + static_cast<size_t>(slot0) * d->max_faces);
     count_launch(2);
     FRB_CUDA(cudaGetLastError());
 }
@@ -565,6 +570,8 @@ int fr_detector_create(const char* weights_path, int net_h, int net_w, int frame
         if (frame_h < 1 || frame_w < 1) throw ArgError{"bad frame size"};
         if (max_batch < 1 || max_batch > 1024) throw ArgError{"max_batch out of range (1..1024)"};
         if (max_faces < 1 || max_faces > 1024) throw ArgError{"max_faces out of range (1..1024)"};
+        // the detector kernels index pixels (x channel chunks) of a batch with 32-bit arithmetic
+        if (static_cast<long long>(max_batch) * (net_h / 2) * (net_w / 2) * 32 >= (1LL << 32)) throw ArgError{"max_batch x network size too large"};
         WeightFile wf = load_weight_file(weights_path);
         if (wf.kind != kKindRetinaTrim && wf.kind != kKindRetinaFull) throw FileError{FR_EFORMAT, "weight file is not a RetinaFace checkpoint"};
         if (with_landmarks && wf.kind != kKindRetinaFull) throw FileError{FR_EFORMAT, "landmarks requested but the checkpoint has no landmark head"};

@@ -11,123 +11,15 @@
 namespace frb {
 
 // ---------------------------------------------------------------------------------------------------------------
-// input_layer: Conv3x3(3->64, s1, p1) + BN (folded) + PReLU  (model_irse.py:139-141). Cin = 3 is not GEMM-shaped: direct conv.
-// Input: either the tensor ArcFaceIR50::preprocessFaces produces (f32 planar R,G,B, (x-127.5)*0.0078125, src/arcface.cpp:118-125)
-// or the u8 BGR HWC crop itself (the same arithmetic is applied on the fly).
-// Output (shared-halo flat NHWC, H = W = 112): y and y_bn = y * bn_s + bn_b (unit 0's pre-activation BN).
-// One thread per PAIR of horizontally adjacent pixels, 64 output channels in four groups of 16: every weight vector fetched from
-// shared memory (LDS.128, broadcast) feeds eight FMAs instead of four, and the pair shares 6 of its 9 input columns. Each output is
-// the same bias + 27-term FMA chain in the same order as a one-pixel-per-thread kernel (bit-identical results).
-// ---------------------------------------------------------------------------------------------------------------
-template <bool kU8>
-__global__ void __launch_bounds__(128) arcface_stem_pair_kernel(const void* __restrict__ in, int batch, const float* __restrict__ w /*[64][27]*/,
-                                                           const float* __restrict__ bias, const float* __restrict__ prelu,
-                                                           const float* __restrict__ bn_s, const float* __restrict__ bn_b,
-                                                           __half* __restrict__ y, __half* __restrict__ y_bn) {
-    constexpr int S = 112, Wp = S + 1, HpWp = Wp * Wp, kPairsPerRow = S / 2;
-    __shared__ float4 ws[27][16];  // ws[k][n/4] = w[n..n+3][k]
-    __shared__ float sb[64], sp[64], ss[64], sbb[64];
-    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
-        const int k = i / 64, n = i % 64;
-        reinterpret_cast<float*>(&ws[k][0])[n] = w[n * 27 + k];
-    }
-    if (threadIdx.x < 64) {
-        sb[threadIdx.x] = bias[threadIdx.x];
-        sp[threadIdx.x] = prelu[threadIdx.x];
-        ss[threadIdx.x] = bn_s ? bn_s[threadIdx.x] : 1.f;
-        sbb[threadIdx.x] = bn_b ? bn_b[threadIdx.x] : 0.f;
-    }
-    __syncthreads();
-    // grid-stride over the pixel pairs: the 6.9 KiB of weights staged above are amortised over several pairs per thread
-    const long long total = static_cast<long long>(batch) * S * kPairsPerRow;
-    for (long long pr = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pr < total;
-         pr += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int img = static_cast<int>(pr / (S * kPairsPerRow));
-        const int rc = static_cast<int>(pr - static_cast<long long>(img) * S * kPairsPerRow);
-        const int r = rc / kPairsPerRow, c = (rc % kPairsPerRow) * 2;
-        float xin[3][4][3];  // [ky][input column c - 1 + j][ch], ch in R,G,B order
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int rr = r + ky - 1, cc = c + j - 1;
-                const bool ok = rr >= 0 && rr < S && cc >= 0 && cc < S;
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    float v = 0.f;
-                    if (ok) {
-                        if (kU8) {
-                            const uint8_t u = static_cast<const uint8_t*>(in)[(static_cast<size_t>(img) * S * S + rr * S + cc) * 3 + (2 - ch)];
-                            v = (static_cast<float>(u) - 127.5f) * 0.0078125f;
-                        } else {
-                            v = static_cast<const float*>(in)[(static_cast<size_t>(img) * 3 + ch) * S * S + rr * S + cc];
-                        }
-                    }
-                    xin[ky][j][ch] = v;
-                }
-            }
-        const size_t o = (static_cast<size_t>(img) * HpWp + r * Wp + c) * 64;  // pixel c; pixel c + 1 follows 64 channels later
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-            float acc[2][16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = sb[g * 16 + j];
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const int k = (ky * 3 + kx) * 3 + ch;
-                        const float a0 = xin[ky][kx][ch], a1 = xin[ky][kx + 1][ch];
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 wv = ws[k][g * 4 + j4];
-                            acc[0][4 * j4 + 0] = fmaf(a0, wv.x, acc[0][4 * j4 + 0]);
-                            acc[0][4 * j4 + 1] = fmaf(a0, wv.y, acc[0][4 * j4 + 1]);
-                            acc[0][4 * j4 + 2] = fmaf(a0, wv.z, acc[0][4 * j4 + 2]);
-                            acc[0][4 * j4 + 3] = fmaf(a0, wv.w, acc[0][4 * j4 + 3]);
-                            acc[1][4 * j4 + 0] = fmaf(a1, wv.x, acc[1][4 * j4 + 0]);
-                            acc[1][4 * j4 + 1] = fmaf(a1, wv.y, acc[1][4 * j4 + 1]);
-                            acc[1][4 * j4 + 2] = fmaf(a1, wv.z, acc[1][4 * j4 + 2]);
-                            acc[1][4 * j4 + 3] = fmaf(a1, wv.w, acc[1][4 * j4 + 3]);
-                        }
-                    }
-#pragma unroll
-            for (int px = 0; px < 2; ++px) {
-                uint4 pk[2], pb[2];
-                __half2* hp = reinterpret_cast<__half2*>(pk);
-                __half2* hb = reinterpret_cast<__half2*>(pb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = g * 16 + 2 * j;
-                    float a = acc[px][2 * j], b = acc[px][2 * j + 1];
-                    a = a > 0.f ? a : a * sp[n];
-                    b = b > 0.f ? b : b * sp[n + 1];
-                    hp[j] = __floats2half2_rn(a, b);
-                    const float2 yr = __half22float2(hp[j]);
-                    hb[j] = __floats2half2_rn(fmaf(yr.x, ss[n], sbb[n]), fmaf(yr.y, ss[n + 1], sbb[n + 1]));
-                }
-                uint4* d0 = reinterpret_cast<uint4*>(y + o + px * 64 + g * 16);
-                d0[0] = pk[0];
-                d0[1] = pk[1];
-                if (y_bn) {
-                    uint4* d1 = reinterpret_cast<uint4*>(y_bn + o + px * 64 + g * 16);
-                    d1[0] = pb[0];
-                    d1[1] = pb[1];
-                }
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// input_layer on the TENSOR cores (default; FR_STEM_TC=0 selects the CUDA-core kernels above/below): the 3x3x3 neighbourhood of a
+// input_layer: Conv3x3(3->64, s1, p1) + BN (folded) + PReLU (model_irse.py:139-141), on the TENSOR cores: the 3x3x3 neighbourhood of a
 // pixel is a K = 27 (padded to 32) row of an im2col operand that the CTA's 128 threads build directly in shared memory in the UMMA
 // layout (K-major 128-byte rows, 128-byte swizzle: 16-byte chunk j of row r at chunk j ^ (r & 7)); one elected thread issues two
 // tcgen05.mma (M = 128 pixels, N = 64 channels, K = 16 each) into a 64-column TMEM accumulator and the same threads run the epilogue
-// (bias, PReLU, y and BN(y) stores). Inputs (u8 - 127.5) / 128 are exact in fp16; the folded weights are rounded to fp16 like every
-// other layer's. The CUDA-core kernel is FMA-issue bound (1728 FMAs per pixel); this one is bound by its 256 B of output per pixel.
+// (bias, PReLU, y and BN(y) stores). Input: either the tensor ArcFaceIR50::preprocessFaces produces (f32 planar R,G,B,
+// (x-127.5)*0.0078125, src/arcface.cpp:118-125) or the u8 BGR HWC crop itself (same arithmetic on the fly); (u8 - 127.5) / 128 is exact
+// in fp16; the folded weights are rounded to fp16 like every other layer's. Output (shared-halo flat NHWC, H = W = 112): y and
+// y_bn = y * bn_s + bn_b (unit 0's pre-activation BN). The round-1 CUDA-core kernels were FMA-issue bound (1728 FMAs per pixel, 440-640 us
+// at batch 256); this one is bound by its 256 B of output per pixel.
 // Persistent: tile = 128 consecutive matrix rows of the output map, tile = blockIdx.x, + gridDim.x, ...; several CTAs per SM overlap
 // one another's build / MMA / store phases.
 // ---------------------------------------------------------------------------------------------------------------
@@ -143,6 +35,7 @@ __global__ void __launch_bounds__(128) arcface_stem_tc_kernel(const void* __rest
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
+    griddep_launch_dependents();
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -164,6 +57,7 @@ __global__ void __launch_bounds__(128) arcface_stem_tc_kernel(const void* __rest
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    griddep_wait();  // the input (crops) and the output maps belong to the kernels before this one
     const uint32_t a_addr = smem_u32(a_tile), b_addr = smem_u32(b_tile);
     constexpr uint32_t idesc = umma_idesc(128, 64, 0, 0);
     const int P = batch * HpWp;
@@ -267,96 +161,6 @@ __global__ void __launch_bounds__(128) arcface_stem_tc_kernel(const void* __rest
     if (warp == 0) tmem_dealloc<64>(tmem_base);
 }
 
-// one thread per pixel (FR_STEM_PAIR=0; see the A/B note at the launch site in embedder.cu)
-template <bool kU8>
-__global__ void __launch_bounds__(128) arcface_stem_kernel(const void* __restrict__ in, int batch, const float* __restrict__ w /*[64][27]*/,
-                                                           const float* __restrict__ bias, const float* __restrict__ prelu,
-                                                           const float* __restrict__ bn_s, const float* __restrict__ bn_b,
-                                                           __half* __restrict__ y, __half* __restrict__ y_bn) {
-    constexpr int S = 112, Wp = S + 1, HpWp = Wp * Wp;
-    __shared__ float4 ws[27][16];  // ws[k][n/4] = w[n..n+3][k]
-    __shared__ float sb[64], sp[64], ss[64], sbb[64];
-    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
-        const int k = i / 64, n = i % 64;
-        reinterpret_cast<float*>(&ws[k][0])[n] = w[n * 27 + k];
-    }
-    if (threadIdx.x < 64) {
-        sb[threadIdx.x] = bias[threadIdx.x];
-        sp[threadIdx.x] = prelu[threadIdx.x];
-        ss[threadIdx.x] = bn_s ? bn_s[threadIdx.x] : 1.f;
-        sbb[threadIdx.x] = bn_b ? bn_b[threadIdx.x] : 0.f;
-    }
-    __syncthreads();
-    // grid-stride over the pixels: the 6.9 KiB of weights staged above are amortised over several pixels per thread
-    const long long total = static_cast<long long>(batch) * S * S;
-    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
-         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int img = static_cast<int>(pix / (S * S));
-    const int rc = static_cast<int>(pix - static_cast<long long>(img) * S * S);
-    const int r = rc / S, c = rc % S;
-    float x[27];  // k = (ky*3 + kx)*3 + ch, ch in R,G,B order
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int rr = r + ky - 1, cc = c + kx - 1;
-            const bool ok = rr >= 0 && rr < S && cc >= 0 && cc < S;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                float v = 0.f;
-                if (ok) {
-                    if (kU8) {
-                        const uint8_t u = static_cast<const uint8_t*>(in)[(static_cast<size_t>(img) * S * S + rr * S + cc) * 3 + (2 - ch)];
-                        v = (static_cast<float>(u) - 127.5f) * 0.0078125f;
-                    } else {
-                        v = static_cast<const float*>(in)[(static_cast<size_t>(img) * 3 + ch) * S * S + rr * S + cc];
-                    }
-                }
-                x[(ky * 3 + kx) * 3 + ch] = v;
-            }
-        }
-    const size_t o = (static_cast<size_t>(img) * HpWp + r * Wp + c) * 64;
-#pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = sb[g * 16 + j];
-#pragma unroll
-        for (int k = 0; k < 27; ++k) {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 wv = ws[k][g * 4 + j4];
-                acc[4 * j4 + 0] = fmaf(x[k], wv.x, acc[4 * j4 + 0]);
-                acc[4 * j4 + 1] = fmaf(x[k], wv.y, acc[4 * j4 + 1]);
-                acc[4 * j4 + 2] = fmaf(x[k], wv.z, acc[4 * j4 + 2]);
-                acc[4 * j4 + 3] = fmaf(x[k], wv.w, acc[4 * j4 + 3]);
-            }
-        }
-        uint4 pk[2], pb[2];
-        __half2* hp = reinterpret_cast<__half2*>(pk);
-        __half2* hb = reinterpret_cast<__half2*>(pb);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = g * 16 + 2 * j;
-            float a = acc[2 * j], b = acc[2 * j + 1];
-            a = a > 0.f ? a : a * sp[n];
-            b = b > 0.f ? b : b * sp[n + 1];
-            hp[j] = __floats2half2_rn(a, b);
-            const float2 yr = __half22float2(hp[j]);
-            hb[j] = __floats2half2_rn(fmaf(yr.x, ss[n], sbb[n]), fmaf(yr.y, ss[n + 1], sbb[n + 1]));
-        }
-        uint4* d0 = reinterpret_cast<uint4*>(y + o + g * 16);
-        d0[0] = pk[0];
-        d0[1] = pk[1];
-        if (y_bn) {
-            uint4* d1 = reinterpret_cast<uint4*>(y_bn + o + g * 16);
-            d1[0] = pb[0];
-            d1[1] = pb[1];
-        }
-    }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // SEModule (model_irse.py:22-45): gate[img][c] = sigmoid(fc2 . relu(fc1 . mean_hw(u[img]))). The per-image channel sums come from the
 // pooling partials the producing conv's epilogue wrote (pool[(group * 2 + seg) * C + c], group = matrix row / 32, see pool_store16 in
@@ -367,6 +171,8 @@ __global__ void __launch_bounds__(512) se_gate_kernel(const int* __restrict__ po
     __shared__ long long part[512];
     __shared__ float mean[512];
     __shared__ float hid[32];
+    griddep_launch_dependents();
+    griddep_wait();
     const int img = blockIdx.x;
     const int HpWp = (H + 1) * (W + 1);
     // ---- pooled mean: groups g_lo..g_hi overlap this image; of the first one only the part inside the image counts.
@@ -429,6 +235,7 @@ __global__ void __launch_bounds__(256, 3) se_apply_kernel(const __half* __restri
                                                        const __half* __restrict__ res, int res_mode, __half* __restrict__ y,
                                                        __half* __restrict__ y_bn, const float* __restrict__ bn_s, const float* __restrict__ bn_b,
                                                        __half* __restrict__ y_sub) {
+    griddep_launch_dependents();
     const int chunks = C / 8;
     const int Wp = W + 1, HpWp = (H + 1) * Wp;
     const int Wh = (W >> 1) + 1, HhWh = ((H >> 1) + 1) * Wh;
@@ -441,6 +248,7 @@ __global__ void __launch_bounds__(256, 3) se_apply_kernel(const __half* __restri
         sc[0] = s0.x, sc[1] = s0.y, sc[2] = s0.z, sc[3] = s0.w, sc[4] = s1.x, sc[5] = s1.y, sc[6] = s1.z, sc[7] = s1.w;
         bi[0] = b0.x, bi[1] = b0.y, bi[2] = b0.z, bi[3] = b0.w, bi[4] = b1.x, bi[5] = b1.y, bi[6] = b1.z, bi[7] = b1.w;
     }
+    griddep_wait();  // the BatchNorm parameters above are static; u, gate and the residual are not
     for (int p0 = (blockIdx.x * 256 + threadIdx.x) / chunks; p0 < P; p0 += 2 * pos_per_pass) {
         uint4 uv[2], rv[2];
         float4 g0[2], g1[2];
@@ -501,6 +309,8 @@ __global__ void __launch_bounds__(256, 3) se_apply_kernel(const __half* __restri
 __global__ void __launch_bounds__(512) fc_reduce_l2norm_kernel(const float* __restrict__ partial, int splits, int batch,
                                                                const float* __restrict__ bias, float* __restrict__ out) {
     __shared__ float red[16];
+    griddep_launch_dependents();
+    griddep_wait();
     const int row = blockIdx.x, o = threadIdx.x;
     float v = bias[o];
     for (int s = 0; s < splits; ++s) v += partial[(static_cast<size_t>(s) * batch + row) * 512 + o];

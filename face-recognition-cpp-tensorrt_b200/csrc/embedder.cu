@@ -180,7 +180,7 @@ void launch_mt(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) {
     }
     const int smem = conv_mt_smem_bytes(BN, ex.halo_chunks, ex.stages);
     const int ctas = std::min(ex.units, g_conv_sms);
-    conv3x3_mt_kernel<BN, MT><<<ctas, kMtThreads, smem, st>>>(s.ta, BN == 64 && s.bn != 64 ? s.tb64 : s.tb, prm, ex);
+    launch_k(conv3x3_mt_kernel<BN, MT>, dim3(ctas), dim3(kMtThreads), smem, st, true, s.ta, BN == 64 && s.bn != 64 ? s.tb64 : s.tb, prm, ex);
 }
 
 // CTA-pair version (conv3x3_pair_kernel<BN>): unit = 256 positions x BN channels, weight boxes of BN / 2 rows per CTA
@@ -205,11 +205,11 @@ void launch_pair(const GemmStep& s, const ConvGemmParams& prm, cudaStream_t st) 
         ex.half_items = 2 * rem;
     }
     const int pairs = std::min(ex.full_units + ex.half_items, all_pairs);
-    conv3x3_pair_kernel<BN><<<2 * pairs, kMtThreads, smem, st>>>(s.ta, BN == 128 ? s.tb64 : s.tb, s.tb64, prm, ex);
+    launch_k(conv3x3_pair_kernel<BN>, dim3(2 * pairs), dim3(kMtThreads), smem, st, true, s.ta, BN == 128 ? s.tb64 : s.tb, s.tb64, prm, ex);
 }
 
 // FR_PAIR=0: never use the CTA-pair kernel; FR_PAIR_BN=128|256 pins its tile width (A/B)
-int pick_pair(const GemmStep& s, const ConvGemmParams& prm) {
+int pick_pair(const GemmStep& s, const ConvGemmParams& prm, double& cost_out) {
     static const bool on = std::getenv("FR_PAIR") == nullptr || std::atoi(std::getenv("FR_PAIR")) != 0;
     static const int force = std::getenv("FR_PAIR_BN") ? std::atoi(std::getenv("FR_PAIR_BN")) : 0;
     if (!on || !g_use_mt || prm.taps != 9 || s.splits != 1 || prm.partial || prm.cout > 512 || s.bn != 128 || !s.has64) return 0;
@@ -221,19 +221,26 @@ int pick_pair(const GemmStep& s, const ConvGemmParams& prm) {
         if (prm.cout % bn || (force && bn != force)) continue;
         const long long units = tiles * (prm.cout / bn);
         if (units < pairs) continue;  // cannot fill the GPU: the single-CTA kernel has smaller units
-        // rounds x unit cost. Measured (IR-SE-50, batch 256, B200): the N = 128 MMAs (64 tensor cycles each) keep the tensor pipe 62-66 %
-        // busy, the N = 256 ones pay for a worse last round (225 units on 74 pairs) and still win: 4.90 vs 5.20 ms per forward
-        const double cost = static_cast<double>((units + pairs - 1) / pairs) * bn / (bn == 256 ? 1.0 : 0.75);
+        // rounds x (unit time + overhead) in units of a single CTA's 128 x 128 tile (pick_mt's scale): a pair does 256 x BN in the time
+        // one CTA needs for 128 x BN, faster still because shared memory no longer limits it. Measured (IR-SE-50, batch 256): N = 128
+        // MMAs keep the tensor pipe 62-66 % busy; N = 256 pays for a worse last round (225 units on 74 pairs, softened by the half-width
+        // split) and still wins, 4.90 vs 5.20 ms per forward
+        long long rounds2 = 2 * ((units + pairs - 1) / pairs);  // in half rounds
+        const long long rem = units % pairs;
+        if (bn == 256 && units > pairs && rem > 0 && 2 * rem <= pairs) rounds2 -= 1;  // short last round split into half-width items
+        const double cost = 0.5 * rounds2 * ((bn / 128.0) * (bn == 256 ? 0.7 : 0.85) + 0.5);
         if (cost < best) {
             best = cost;
             best_bn = bn;
         }
     }
+    cost_out = best;
     return best_bn;
 }
 
 // tile shape of the persistent conv: the largest unit that still gives every SM one; small grids take the smallest
-bool pick_mt(const GemmStep& s, const ConvGemmParams& prm, int& bn, int& mt) {
+bool pick_mt(const GemmStep& s, const ConvGemmParams& prm, int& bn, int& mt, double& cost_out) {
+    cost_out = 1e30;
     if (!g_use_mt || prm.taps != 9 || s.splits != 1 || prm.partial || prm.cout > 512) return false;
     static const bool mt_s2 = std::getenv("FR_MT_S2") == nullptr || std::atoi(std::getenv("FR_MT_S2")) != 0;  // stride-2 convs too (A/B)
     if (prm.tap_phase && !mt_s2) return false;
@@ -244,18 +251,30 @@ bool pick_mt(const GemmStep& s, const ConvGemmParams& prm, int& bn, int& mt) {
             (fb == 64 ? s.has64 || s.bn == 64 : s.bn == 128)) {
             bn = fb;
             mt = fm;
+            cost_out = 0.;
             return true;
         }
     }
+    // cost model: rounds x (unit work + per-unit overhead), in units of a 128 x 128 tile's MMA time. The overhead (the first halo round
+    // trip, the epilogue drain; about half a tile's worth) is what makes small grids prefer ONE round of larger units over two rounds of
+    // small ones (measured at batch 32: 1.42 ms with (128,1) forced against 1.59 ms with the smallest units everywhere).
     const int cand[4][2] = {{128, 2}, {128, 1}, {64, 2}, {64, 1}};
+    double best = 1e30;
+    bn = 0;
     for (const auto& c : cand) {
         if (c[0] == 128 && (s.bn != 128 || prm.cout % 128)) continue;
         if (c[0] == 64 && !(s.bn == 64 || s.has64)) continue;
-        bn = c[0];
-        mt = c[1];
-        const long long units = static_cast<long long>((prm.P + mt * kConvBM - 1) / (mt * kConvBM)) * (prm.cout / bn);
-        if (units >= g_conv_sms) return true;
+        const long long units = static_cast<long long>((prm.P + c[1] * kConvBM - 1) / (c[1] * kConvBM)) * (prm.cout / c[0]);
+        const long long rounds = (units + g_conv_sms - 1) / g_conv_sms;
+        const double work = c[1] * (c[0] / 128.0) * (c[0] == 64 ? 1.25 : 1.0);  // N = 64 MMAs are bound by the A-operand read
+        const double cost = static_cast<double>(rounds) * (work + 0.5);
+        if (cost < best - 1e-9) {
+            best = cost;
+            bn = c[0];
+            mt = c[1];
+        }
     }
+    cost_out = best;
     return bn != 0;
 }
 
@@ -264,8 +283,8 @@ void launch_gemm(const GemmStep& s, int P, cudaStream_t st) {
     ConvGemmParams prm = s.prm;
     prm.P = P;
     dim3 grid((P + kConvBM - 1) / kConvBM, prm.cout / BN, s.splits);
-    if (prm.pool) conv_gemm_kernel<BN, true><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
-    else conv_gemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(s.ta, s.tb, prm);
+    if (prm.pool) launch_k(conv_gemm_kernel<BN, true, false>, grid, dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, st, true, s.ta, s.tb, prm);
+    else launch_k(conv_gemm_kernel<BN, false, false>, grid, dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, st, true, s.ta, s.tb, prm);
     count_launch();
 }
 
@@ -273,13 +292,16 @@ void launch_conv(const GemmStep& g0, int P, int sms, cudaStream_t st) {
     GemmStep g = g0;
     g.prm.P = P;
     int bn = 0, mt = 0;
-    if (const int pbn = pick_pair(g, g.prm)) {
+    double pair_cost = 1e30, mt_cost = 1e30;
+    const int pbn = pick_pair(g, g.prm, pair_cost);
+    const bool mt_ok = pick_mt(g, g.prm, bn, mt, mt_cost);
+    if (pbn && (!mt_ok || pair_cost <= mt_cost)) {
         if (pbn == 256) launch_pair<256>(g, g.prm, st);
         else launch_pair<128>(g, g.prm, st);
         count_launch();
         return;
     }
-    if (pick_mt(g, g.prm, bn, mt)) {
+    if (mt_ok) {
         if (bn == 128 && mt == 2) launch_mt<128, 2>(g, g.prm, st);
         else if (bn == 128) launch_mt<128, 1>(g, g.prm, st);
         else if (mt == 2) launch_mt<64, 2>(g, g.prm, st);
@@ -300,35 +322,15 @@ void launch_conv(const GemmStep& g0, int P, int sms, cudaStream_t st) {
 
 void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cudaStream_t st = nullptr) {
     if (!st) st = e->stream;
-    // one thread per pair of adjacent pixels (arcface_stem_pair_kernel, default) or per pixel (FR_STEM_PAIR=0); bit-identical outputs.
-    // A/B on B200, whole IR-SE-50 forward, two interleaved runs each: 1.545 vs 1.569 ms at batch 32, 7.30 vs 7.36 ms at batch 256.
-    static const bool stem_pair = std::getenv("FR_STEM_PAIR") == nullptr || std::atoi(std::getenv("FR_STEM_PAIR")) != 0;
-    const long long work = static_cast<long long>(batch) * 112 * (stem_pair ? 56 : 112);
-    const int blocks = static_cast<int>(std::min<long long>((work + 127) / 128, 148LL * 16));  // grid-stride inside the kernels
-    static const bool stem_tc = std::getenv("FR_STEM_TC") == nullptr || std::atoi(std::getenv("FR_STEM_TC")) != 0;
-    if (stem_tc) {
-        // tensor-core stem (arcface_stem_tc_kernel): persistent, a few CTAs per SM
+    {   // tensor-core stem (arcface_stem_tc_kernel): persistent, a few CTAs per SM
         const int tiles = (batch * hpwp(0) + 127) / 128;
         const int ctas = std::min(tiles, e->sms * 6);
         if (u8_input)
-            arcface_stem_tc_kernel<true><<<ctas, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
-                                                               e->stem_y.p, e->stem_yb.p);
+            launch_k(arcface_stem_tc_kernel<true>, dim3(ctas), dim3(128), 0, st, true, static_cast<const void*>(e->in_u8), batch, e->stem_w,
+                     e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b, e->stem_y.p, e->stem_yb.p);
         else
-            arcface_stem_tc_kernel<false><<<ctas, 128, 0, st>>>(e->in_f32, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
-                                                                e->stem_y.p, e->stem_yb.p);
-    } else if (stem_pair) {
-        if (u8_input)
-            arcface_stem_pair_kernel<true><<<blocks, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
-                                                                   e->stem_y.p, e->stem_yb.p);
-        else
-            arcface_stem_pair_kernel<false><<<blocks, 128, 0, st>>>(e->in_f32, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
-                                                                    e->stem_y.p, e->stem_yb.p);
-    } else if (u8_input) {
-        arcface_stem_kernel<true><<<blocks, 128, 0, st>>>(e->in_u8, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
-                                                          e->stem_y.p, e->stem_yb.p);
-    } else {
-        arcface_stem_kernel<false><<<blocks, 128, 0, st>>>(e->in_f32, batch, e->stem_w, e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b,
-                                                           e->stem_y.p, e->stem_yb.p);
+            launch_k(arcface_stem_tc_kernel<false>, dim3(ctas), dim3(128), 0, st, true, static_cast<const void*>(e->in_f32), batch, e->stem_w,
+                     e->stem_b, e->stem_prelu, e->u0_bn_s, e->u0_bn_b, e->stem_y.p, e->stem_yb.p);
     }
     count_launch();
     for (const Step& s : e->steps) {
@@ -344,16 +346,17 @@ void run_steps(FrEmbedder* e, int batch, bool u8_input, int stop_after_unit, cud
         } else {
             const SeStep& q = s.se;
             const int H = kGeo[q.geo], P = batch * hpwp(q.geo);
-            se_gate_kernel<<<batch, 512, 0, st>>>(e->se_pool, H, H, q.C, q.fc1, q.fc2, e->gate);
+            launch_k(se_gate_kernel, dim3(batch), dim3(512), 0, st, true, e->se_pool, H, H, q.C, q.fc1, q.fc2, e->gate);
             const long long items = static_cast<long long>(P) * (q.C / 8);
             const int blocks = static_cast<int>(std::min<long long>((items + 511) / 512, 8LL * e->sms));  // 2 items per thread per pass
-            se_apply_kernel<<<blocks, 256, 0, st>>>(q.u, e->gate, P, H, H, q.C, q.res, q.res_mode, q.y, q.y_bn, q.bn_s, q.bn_b, q.y_sub);
+            launch_k(se_apply_kernel, dim3(blocks), dim3(256), 0, st, true, q.u, e->gate, P, H, H, q.C, q.res, q.res_mode, q.y, q.y_bn, q.bn_s,
+                     q.bn_b, q.y_sub);
             count_launch();
             count_launch();
         }
     }
     if (stop_after_unit == kRunAll) {
-        fc_reduce_l2norm_kernel<<<batch, 512, 0, st>>>(e->fc_partial, kFcSplits, batch, e->fc_bias, e->out_dev);
+        launch_k(fc_reduce_l2norm_kernel, dim3(batch), dim3(512), 0, st, true, e->fc_partial, kFcSplits, batch, e->fc_bias, e->out_dev);
         count_launch();
     }
     FRB_CUDA(cudaGetLastError());

@@ -327,6 +327,17 @@ void drain(FrPipeline* p) {  // after an error: leave no work in flight that sti
 
 }  // namespace
 
+// internal hook for the request batcher (service.cu)
+namespace frb {
+void pipeline_dims(const FrPipeline* p, int* device, int* frame_h, int* frame_w, int* max_batch, int* max_faces) {
+    *device = p->device;
+    *frame_h = p->frame_h;
+    *frame_w = p->frame_w;
+    *max_batch = p->max_batch;
+    *max_faces = p->max_faces;
+}
+}  // namespace frb
+
 extern "C" {
 
 int fr_pipeline_create(FrDetector* det, FrEmbedder* emb, FrGallery* gal, FrPipeline** out) {

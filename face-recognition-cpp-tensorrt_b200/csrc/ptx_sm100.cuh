@@ -198,6 +198,39 @@ __device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4&
                  : "l"(p));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is still
+// running: launch_dependents (issued first thing) lets the successor's CTAs take SMs as they free up and run their prologue (barrier
+// init, TMEM allocation, parameter / weight staging - nothing the predecessor writes); griddep_wait() then blocks until the
+// predecessor has COMPLETED and its writes are visible. Both are no-ops in a kernel that was launched normally.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------- warp-level MMA (mma.sync) for tiny-K products
+// The RetinaFace layers with 8-32 channels are far too small for a tcgen05 tile (K = 8..32, N = 16..64): their pointwise / 16-channel
+// products use the warp-level tensor-core instruction on fragments instead of hundreds of FFMAs per thread.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t smem_addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_addr) : "memory");
+}
+// D (16 x 8, fp32) += A (16 x 16, fp16, row) * B (16 x 8, fp16, col)
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// D (16 x 8, fp32) += A (16 x 8, fp16, row) * B (8 x 8, fp16, col)
+__device__ __forceinline__ void mma_m16n8k8(float (&d)[4], const uint32_t (&a)[2], uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+
 // ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

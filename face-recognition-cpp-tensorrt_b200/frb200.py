@@ -633,6 +633,48 @@ class Pipeline:
         return int(lib().fr_pipeline_in_flight(self._h))
 
 
+class Service:
+    """Request batcher in front of a Pipeline (fr_service_*): infer() is thread-safe and blocking, one frame per call."""
+
+    def __init__(self, pipe: "Pipeline", max_wait_us: int = 200):
+        L = lib()
+        L.fr_service_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.fr_service_destroy.restype = None
+        L.fr_service_destroy.argtypes = [C.c_void_p]
+        L.fr_service_infer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fr_service_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        h = C.c_void_p()
+        check(L.fr_service_create(pipe._h, max_wait_us, C.byref(h)))
+        self._h, self.pipe = h, pipe
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_service_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def infer(self, frame: np.ndarray):
+        """frame: H x W x 3 u8 -> dict(boxes[max_faces], count, idx[max_faces], score[max_faces]); ctypes releases the GIL while waiting"""
+        f = np.ascontiguousarray(frame, dtype=np.uint8)
+        mf = self.pipe.det.max_faces
+        boxes = np.zeros(mf, BOX_DTYPE)
+        count = C.c_int()
+        idx = np.zeros(mf, np.int64)
+        score = np.zeros(mf, np.float32)
+        check(lib().fr_service_infer(self._h, _ptr(f), f.shape[1] * 3, _ptr(boxes), C.byref(count), _ptr(idx), _ptr(score)))
+        return {"boxes": boxes, "count": count.value, "idx": idx, "score": score}
+
+    def stats(self):
+        b, f = C.c_int64(), C.c_int64()
+        check(lib().fr_service_stats(self._h, C.byref(b), C.byref(f)))
+        return b.value, f.value
+
+
 class Exchange:
     """Fused cross-GPU exchange + merge of per-shard top-k over NVLink peer memory (csrc/exchange.cu)."""
 

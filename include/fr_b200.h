@@ -333,6 +333,21 @@ int fr_pipeline_submit(FrPipeline *p, const uint8_t *frames, int stride, int bat
 int fr_pipeline_collect(FrPipeline *p, FrBbox *boxes, int *counts, int64_t *top1_idx, float *top1_score, float *embeddings);
 int fr_pipeline_in_flight(const FrPipeline *p);
 
+/* Request batching in front of a pipeline (the serving loop around src/app.cpp:293-352; the reference serves one request
+ * at a time behind a lock, src/app.cpp:367). fr_service_infer is thread-safe and blocking: callers on any number of threads hand in ONE
+ * frame each (frame_h x frame_w x 3 u8 BGR, `stride` bytes per row; it must stay valid until the call returns); a worker thread gathers
+ * the frames that are waiting - up to the detector's max_batch, or whatever arrived within max_wait_us of the oldest one while the GPU
+ * is idle - into a pinned staging batch, runs it through fr_pipeline_submit / fr_pipeline_collect (two batches in flight) and hands
+ * every caller the results of its own frame: boxes[max_faces] (valid for j < *count), top1_idx / top1_score [max_faces] (optional).
+ * The service owns the pipeline's submit / collect ring while it lives: do not call fr_pipeline_* on the same pipeline concurrently.
+ * JPEG decoding and the HTTP layer stay with the host application. */
+typedef struct FrService FrService;
+int fr_service_create(FrPipeline *p, int max_wait_us, FrService **out);
+void fr_service_destroy(FrService *s);
+int fr_service_infer(FrService *s, const uint8_t *frame, int stride, FrBbox *boxes, int *count, int64_t *top1_idx, float *top1_score);
+/* monitoring: batches formed and frames served so far */
+int fr_service_stats(const FrService *s, int64_t *batches, int64_t *frames);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,3 +174,44 @@ def test_two_batches_in_flight_equal_synchronous_runs(nets):
         assert np.array_equal(w["embeddings"].view(np.uint32), g["embeddings"].view(np.uint32))
     pipe.close()
     gal.close()
+
+
+def test_service_batches_concurrent_requests(nets):
+    """fr_service_infer from 12 threads at once: every caller gets exactly what the pipeline returns for its own frame, and the worker
+    really formed batches (fewer batches than frames)."""
+    import threading
+
+    det, emb, arc_sd = nets
+    frames = mgr.det_frames(6, 640, 640, seed=13)
+    blank = np.full((640, 640, 3), 128, np.uint8)
+    reqs = [frames[i % 6] for i in range(20)] + [blank] * 4
+    G = so.synth_rows(np.arange(30_000), seed=5)
+    gal = frb200.Gallery.from_rows(G)
+    pipe = frb200.Pipeline(det, emb, gal)
+    want = {}
+    for i in list(range(6)) + [20]:
+        r = pipe.run(reqs[i][None])
+        want[i] = (r["boxes"][0], int(r["counts"][0]), r["idx"][0], r["score"][0])
+    svc = frb200.Service(pipe, max_wait_us=2000)
+    got = [None] * len(reqs)
+
+    def call(i):
+        got[i] = svc.infer(reqs[i])
+
+    for wave in (range(0, 12), range(12, 24)):
+        ts = [threading.Thread(target=call, args=(i,)) for i in wave]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    for i, g in enumerate(got):
+        b, c, ix, sc = want[i % 6] if i < 20 else want[20]
+        assert g["count"] == c
+        assert np.array_equal(g["boxes"][:c], b[:c])
+        assert np.array_equal(g["idx"], ix)
+        assert np.array_equal(g["score"].view(np.uint32), sc.view(np.uint32))
+    batches, served = svc.stats()
+    assert served == len(reqs) and batches < served
+    svc.close()
+    pipe.close()
+    gal.close()
