@@ -165,61 +165,54 @@ __global__ void __launch_bounds__(256) det_stem_f32_kernel(const float* __restri
     *reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * g.HpWp() + r * g.Wp() + c) * 8) = pk;
 }
 
-// ---- depthwise 3x3 (stride 1 or 2, pad 1) + BN + ReLU (first half of conv_dw, net.py:29-33) for the blocks with >= 64 channels
-//      (their pointwise half is a tcgen05 GEMM). One work item = (output pixel, 8 channels). Grid-stride with a stride that is a
-//      multiple of C / 8, so a thread keeps the same channel chunk for all its items: its 72 weights and 8 biases are loaded ONCE into
-//      registers (the first version fetched them per item: two thirds of its load instructions and of its L1 traffic). w: [9][C] f32.
+// ---- depthwise 3x3 (stride 1 or 2, pad 1) + BN + ReLU (first half of conv_dw, net.py:29-33). One thread per
+//      (output pixel, 8 channels), 40 registers, full occupancy. w: [9][C] f32, fetched per item through L1. (A grid-stride version that
+//      keeps the thread's 72 weights in registers was measured: 118 registers, 16 warps per SM, 540 vs 382 us for the nine layers at
+//      batch 64 - occupancy matters more here than the weight fetches.)
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __half* __restrict__ in, Geo gi, __half* __restrict__ out, Geo go, int stride,
                                                     int C, int batch, const float* __restrict__ w, const float* __restrict__ bias) {
     griddep_launch_dependents();
-    const int chunks = C / 8;                          // divides 256 (C = 64, 128, 256)
-    const int ch = (threadIdx.x % chunks) * 8;         // this thread's channels, fixed
-    float wr[9][8], br[8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * C + ch)), w1 = __ldg(reinterpret_cast<const float4*>(w + t * C + ch) + 1);
-        wr[t][0] = w0.x, wr[t][1] = w0.y, wr[t][2] = w0.z, wr[t][3] = w0.w, wr[t][4] = w1.x, wr[t][5] = w1.y, wr[t][6] = w1.z, wr[t][7] = w1.w;
-    }
-    {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch)), b1 = __ldg(reinterpret_cast<const float4*>(bias + ch) + 1);
-        br[0] = b0.x, br[1] = b0.y, br[2] = b0.z, br[3] = b0.w, br[4] = b1.x, br[5] = b1.y, br[6] = b1.z, br[7] = b1.w;
-    }
     griddep_wait();
-    const int hw = go.H * go.W;
-    const int pixels = batch * hw;                      // < 2^31 (checked by the host)
-    const int ppp = (gridDim.x * 256) / chunks;         // pixels the whole grid covers per pass
-    for (int pix = (blockIdx.x * 256 + threadIdx.x) / chunks; pix < pixels; pix += ppp) {
-        const int img = pix / hw;
-        const int rc = pix - img * hw;
-        const int r = rc / go.W, c = rc - r * go.W;
-        float acc[8];
+    const int chunks = C / 8;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // (pixels x chunks) of a batch < 2^32 (checked by the host)
+    if (t >= static_cast<unsigned>(batch) * go.H * go.W * chunks) return;
+    const int ch = static_cast<int>(t % chunks) * 8;
+    const int pix = static_cast<int>(t / chunks);
+    const int img = pix / (go.H * go.W);
+    const int rc = pix - img * (go.H * go.W);
+    const int r = rc / go.W, c = rc % go.W;
+    float acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = br[j];
-        const __half* ibase = in + static_cast<size_t>(img) * gi.HpWp() * C + ch;
+    for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + ch + j);
+    const __half* ibase = in + static_cast<size_t>(img) * gi.HpWp() * C + ch;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int rr = r * stride + ky - 1;
-            if (rr < 0) continue;  // rr == gi.H is the zero pad row
+    for (int ky = 0; ky < 3; ++ky) {
+        const int rr = r * stride + ky - 1;
+        if (rr < 0) continue;  // rr == gi.H is the zero pad row
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int cc = c * stride + kx - 1;
-                if (cc < 0) continue;  // cc == gi.W is the zero pad column
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(ibase + (static_cast<size_t>(rr) * gi.Wp() + cc) * C));
-                const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f = __half22float2(h[q]);
-                    acc[2 * q] = fmaf(f.x, wr[ky * 3 + kx][2 * q], acc[2 * q]);
-                    acc[2 * q + 1] = fmaf(f.y, wr[ky * 3 + kx][2 * q + 1], acc[2 * q + 1]);
-                }
-            }
+        for (int kx = 0; kx < 3; ++kx) {
+            const int cc = c * stride + kx - 1;
+            if (cc < 0) continue;  // cc == gi.W is the zero pad column
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(ibase + (static_cast<size_t>(rr) * gi.Wp() + cc) * C));
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + ch));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + ch) + 1);
+            const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), d = __half22float2(h[2]), e = __half22float2(h[3]);
+            acc[0] = fmaf(a.x, w0.x, acc[0]);
+            acc[1] = fmaf(a.y, w0.y, acc[1]);
+            acc[2] = fmaf(b.x, w0.z, acc[2]);
+            acc[3] = fmaf(b.y, w0.w, acc[3]);
+            acc[4] = fmaf(d.x, w1.x, acc[4]);
+            acc[5] = fmaf(d.y, w1.y, acc[5]);
+            acc[6] = fmaf(e.x, w1.z, acc[6]);
+            acc[7] = fmaf(e.y, w1.w, acc[7]);
         }
-        uint4 pk;
-        __half2* hp = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * go.HpWp() + r * go.Wp() + c) * C + ch) = pk;
     }
+    uint4 pk;
+    __half2* hp = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * go.HpWp() + r * go.Wp() + c) * C + ch) = pk;
 }
 
 // fp32 weights as mma.sync B fragments: {b0, b1} rounded to fp16 (x, y) and the fp16 of what the rounding lost (z, w)
