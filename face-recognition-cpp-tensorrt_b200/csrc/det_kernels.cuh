@@ -165,54 +165,70 @@ __global__ void __launch_bounds__(256) det_stem_f32_kernel(const float* __restri
     *reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * g.HpWp() + r * g.Wp() + c) * 8) = pk;
 }
 
-// ---- depthwise 3x3 (stride 1 or 2, pad 1) + BN + ReLU (first half of conv_dw, net.py:29-33). One thread per
-//      (output pixel, 8 channels), 40 registers, full occupancy. w: [9][C] f32, fetched per item through L1. (A grid-stride version that
-//      keeps the thread's 72 weights in registers was measured: 118 registers, 16 warps per SM, 540 vs 382 us for the nine layers at
-//      batch 64 - occupancy matters more here than the weight fetches.)
+// ---- depthwise 3x3 (stride 1 or 2, pad 1) + BN + ReLU (first half of conv_dw, net.py:29-33) for the blocks with >= 64 channels
+//      (their pointwise half is a tcgen05 GEMM). One work item = (output pixel, 8 channels); grid-stride, one full wave of CTAs, the
+//      layer's weights ([9][C] f32, <= 9 KiB) and biases staged ONCE per CTA in shared memory. History (nine layers at 64 x 640^2):
+//      weights fetched per item through L1 (two thirds of the load instructions) 382 us; the thread's 72 weights in registers
+//      (118 registers, 16 warps per SM) 540 us - occupancy matters more than the fetches; this version keeps ~40 registers.
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __half* __restrict__ in, Geo gi, __half* __restrict__ out, Geo go, int stride,
                                                     int C, int batch, const float* __restrict__ w, const float* __restrict__ bias) {
+    // weights as two planes of float4 per (tap, 8-channel chunk): channels 0-3 and 4-7 of the chunk, so that the lanes of a warp
+    // (consecutive chunks) read consecutive 16-byte words - conflict-free LDS.128
+    __shared__ float4 sw_lo[9 * 32], sw_hi[9 * 32];
+    __shared__ __align__(16) float sbias[256];
     griddep_launch_dependents();
-    griddep_wait();
-    const int chunks = C / 8;
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // (pixels x chunks) of a batch < 2^32 (checked by the host)
-    if (t >= static_cast<unsigned>(batch) * go.H * go.W * chunks) return;
-    const int ch = static_cast<int>(t % chunks) * 8;
-    const int pix = static_cast<int>(t / chunks);
-    const int img = pix / (go.H * go.W);
-    const int rc = pix - img * (go.H * go.W);
-    const int r = rc / go.W, c = rc % go.W;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + ch + j);
-    const __half* ibase = in + static_cast<size_t>(img) * gi.HpWp() * C + ch;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int rr = r * stride + ky - 1;
-        if (rr < 0) continue;  // rr == gi.H is the zero pad row
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int cc = c * stride + kx - 1;
-            if (cc < 0) continue;  // cc == gi.W is the zero pad column
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(ibase + (static_cast<size_t>(rr) * gi.Wp() + cc) * C));
-            const __half2* h = reinterpret_cast<const __half2*>(&v);
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + ch));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + ch) + 1);
-            const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), d = __half22float2(h[2]), e = __half22float2(h[3]);
-            acc[0] = fmaf(a.x, w0.x, acc[0]);
-            acc[1] = fmaf(a.y, w0.y, acc[1]);
-            acc[2] = fmaf(b.x, w0.z, acc[2]);
-            acc[3] = fmaf(b.y, w0.w, acc[3]);
-            acc[4] = fmaf(d.x, w1.x, acc[4]);
-            acc[5] = fmaf(d.y, w1.y, acc[5]);
-            acc[6] = fmaf(e.x, w1.z, acc[6]);
-            acc[7] = fmaf(e.y, w1.w, acc[7]);
-        }
+    for (int i = threadIdx.x; i < 9 * C; i += 256) {
+        const int tap = i / C, cch = i - tap * C;
+        float4* plane = (cch & 4) ? sw_hi : sw_lo;
+        reinterpret_cast<float*>(&plane[tap * 32 + (cch >> 3)])[cch & 3] = __ldg(w + i);
     }
-    uint4 pk;
-    __half2* hp = reinterpret_cast<__half2*>(&pk);
+    for (int i = threadIdx.x; i < C; i += 256) sbias[i] = __ldg(bias + i);
+    __syncthreads();
+    griddep_wait();  // the weights are static; the input map belongs to the kernel before this one
+    const int chunks = C / 8;                    // divides 256 (C = 64, 128, 256)
+    const int ch = (threadIdx.x % chunks) * 8;   // this thread's channels: fixed, the grid stride is a multiple of `chunks`
+    const int hw = go.H * go.W;
+    const int pixels = batch * hw;               // < 2^31 (checked by the host)
+    const int ppp = (gridDim.x * 256) / chunks;  // pixels the whole grid covers per pass
+    for (int pix = (blockIdx.x * 256 + threadIdx.x) / chunks; pix < pixels; pix += ppp) {
+        const int img = pix / hw;
+        const int rc = pix - img * hw;
+        const int r = rc / go.W, c = rc - r * go.W;
+        float acc[8];
+        {
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + ch), b1 = *reinterpret_cast<const float4*>(sbias + ch + 4);
+            acc[0] = b0.x, acc[1] = b0.y, acc[2] = b0.z, acc[3] = b0.w, acc[4] = b1.x, acc[5] = b1.y, acc[6] = b1.z, acc[7] = b1.w;
+        }
+        const __half* ibase = in + static_cast<size_t>(img) * gi.HpWp() * C + ch;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * go.HpWp() + r * go.Wp() + c) * C + ch) = pk;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int rr = r * stride + ky - 1;
+            if (rr < 0) continue;  // rr == gi.H is the zero pad row
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int cc = c * stride + kx - 1;
+                if (cc < 0) continue;  // cc == gi.W is the zero pad column
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(ibase + (static_cast<size_t>(rr) * gi.Wp() + cc) * C));
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
+                const float4 w0 = sw_lo[(ky * 3 + kx) * 32 + (ch >> 3)];
+                const float4 w1 = sw_hi[(ky * 3 + kx) * 32 + (ch >> 3)];
+                const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), d = __half22float2(h[2]), e = __half22float2(h[3]);
+                acc[0] = fmaf(a.x, w0.x, acc[0]);
+                acc[1] = fmaf(a.y, w0.y, acc[1]);
+                acc[2] = fmaf(b.x, w0.z, acc[2]);
+                acc[3] = fmaf(b.y, w0.w, acc[3]);
+                acc[4] = fmaf(d.x, w1.x, acc[4]);
+                acc[5] = fmaf(d.y, w1.y, acc[5]);
+                acc[6] = fmaf(e.x, w1.z, acc[6]);
+                acc[7] = fmaf(e.y, w1.w, acc[7]);
+            }
+        }
+        uint4 pk;
+        __half2* hp = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(img) * go.HpWp() + r * go.Wp() + c) * C + ch) = pk;
+    }
 }
 
 // fp32 weights as mma.sync B fragments: {b0, b1} rounded to fp16 (x, y) and the fp16 of what the rounding lost (z, w)

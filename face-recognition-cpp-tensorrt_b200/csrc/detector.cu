@@ -395,7 +395,10 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
         switch (s.kind) {
             case kDw: {
                 const long long t = static_cast<long long>(batch) * s.go.H * s.go.W * (s.cin / 8);
-                launch_k(dw3x3_kernel, dim3(blocks_for(t, 256)), dim3(256), 0, st, true, s.in, s.gi, s.out, s.go, s.stride, s.cin, batch, s.w, s.b);
+                static int occ = 0;  // resident CTAs per SM: the grid is one full wave (grid-stride inside the kernel)
+                if (!occ) FRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dw3x3_kernel, 256, 0));
+                const int nb = static_cast<int>(std::min<long long>((t + 255) / 256, static_cast<long long>(std::max(occ, 1)) * d->sms));
+                launch_k(dw3x3_kernel, dim3(nb), dim3(256), 0, st, true, s.in, s.gi, s.out, s.go, s.stride, s.cin, batch, s.w, s.b);
                 count_launch();
                 break;
             }

@@ -346,7 +346,7 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     if (app)
         append_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->app_buf, g->app_cnt, units * 2, cg * kQRows, q_dev, g->rows_f32, g->q_margin,
                                                          g->q_gap, f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, g->row_offset, scores_dev, idx_dev, g->flags,
-                                                         g->gbest, g->push);
+                                                         g->gbest, g->push, f8 && g->f16_ok ? g->rows_f16 : nullptr, g->gmax);
     else
         topk_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->cand_s, g->cand_i, units * 2, cg * kQRows, kc, q_dev, g->rows_f32, g->q_margin,
                                                        g->q_gap, f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, k, g->row_offset, scores_dev, idx_dev, g->flags,
