@@ -357,7 +357,8 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             const uint32_t tempty_leader = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
             volatile int* gb_ptr = reinterpret_cast<volatile int*>(gbest + (live ? qrow : 0));
 
-            auto chunk_max = [&](const uint32_t (&raw)[kLdCols], int col0, int valid, float (&v)[kLdCols]) -> float {
+            // max of a chunk; tri[g] = max of columns 3g .. 3g+2 (g < 5), column 15 stands alone
+            auto chunk_max = [&](const uint32_t (&raw)[kLdCols], int col0, int valid, float (&v)[kLdCols], float (&tri)[5]) -> float {
 #pragma unroll
                 for (int j = 0; j < kLdCols; ++j) v[j] = __uint_as_float(raw[j]);
                 if (valid < kTileRows) {
@@ -365,21 +366,33 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     for (int j = 0; j < kLdCols; ++j)
                         if (col0 + j >= valid) v[j] = -INFINITY;
                 }
-                const float a = fmax3(v[0], v[1], v[2]), b = fmax3(v[3], v[4], v[5]), c = fmax3(v[6], v[7], v[8]);
-                const float d = fmax3(v[9], v[10], v[11]), e = fmax3(v[12], v[13], v[14]);
-                return fmax3(fmax3(a, b, c), fmax3(d, e, v[15]), -INFINITY);
+#pragma unroll
+                for (int g = 0; g < 5; ++g) tri[g] = fmax3(v[3 * g], v[3 * g + 1], v[3 * g + 2]);
+                return fmax3(fmax3(tri[0], tri[1], tri[2]), fmax3(tri[3], tri[4], v[15]), -INFINITY);
+            };
+            // Under the e4m3 copy's wide margin about a quarter of all (warp, chunk) pairs hold a passing value in SOME lane (ncu source
+            // page, 1.25 M-row shard, queries without a match): the straight 16-way predicated append was 240 instructions and 45 % of the
+            // epilogue's time. The slow path now descends by warp votes (uniform branches): column triples first, then single columns, so
+            // the usual case (one lane, one column) runs one append body.
+            auto append_if = [&](float val, int row) {
+                if (val > thr) {
+                    if (cnt < kAppCap) mybuf[cnt] = make_uint2(__float_as_uint(val * kInvRaw), static_cast<uint32_t>(row));
+                    ++cnt;
+                }
             };
             auto consume_app = [&](const uint32_t (&raw)[kLdCols], int col0, int valid, int row_base) {
-                float v[kLdCols];
-                const float m = chunk_max(raw, col0, valid, v);
-                if (m > thr) {
+                float v[kLdCols], tri[5];
+                const float m = chunk_max(raw, col0, valid, v, tri);
+                if (__any_sync(0xffffffffu, m > thr)) {
 #pragma unroll
-                    for (int j = 0; j < kLdCols; ++j) {
-                        if (v[j] > thr) {
-                            if (cnt < kAppCap) mybuf[cnt] = make_uint2(__float_as_uint(v[j] * kInvRaw), static_cast<uint32_t>(row_base + col0 + j));
-                            ++cnt;
+                    for (int g = 0; g < 5; ++g) {
+                        if (__any_sync(0xffffffffu, tri[g] > thr)) {
+#pragma unroll
+                            for (int j = 3 * g; j < 3 * g + 3; ++j)
+                                if (__any_sync(0xffffffffu, v[j] > thr)) append_if(v[j], row_base + col0 + j);
                         }
                     }
+                    if (__any_sync(0xffffffffu, v[15] > thr)) append_if(v[15], row_base + col0 + 15);
                     best = fmaxf(best, m);
                     thr = fmaxf(thr, best - margin);
                 }
@@ -402,16 +415,16 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     // first tile: a max-only pass seeds the threshold (and the shared best) before anything is appended; without it
                     // the first chunks would append every row they see
                     float tm = -INFINITY;
-                    float v[kLdCols];
+                    float v[kLdCols], tri[5];
                     tmem_ld_32x32b_x16(taddr, ra);
 #pragma unroll 1
                     for (int c = 0; c < kChunksA; c += 2) {
                         tmem_ld_wait_x16(ra);
                         tmem_ld_32x32b_x16(taddr + (c + 1) * kLdCols, rb);
-                        tm = fmaxf(tm, chunk_max(ra, cbase + c * kLdCols, valid, v));
+                        tm = fmaxf(tm, chunk_max(ra, cbase + c * kLdCols, valid, v, tri));
                         tmem_ld_wait_x16(rb);
                         if (c + 2 < kChunksA) tmem_ld_32x32b_x16(taddr + (c + 2) * kLdCols, ra);
-                        tm = fmaxf(tm, chunk_max(rb, cbase + (c + 1) * kLdCols, valid, v));
+                        tm = fmaxf(tm, chunk_max(rb, cbase + (c + 1) * kLdCols, valid, v, tri));
                     }
                     if (live) {
                         // strictly below the tile's best, so that the append pass keeps it
@@ -717,10 +730,15 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
     }
 }
 
-// Re-rank for the append epilogue (top-1). One block per query: the best coarse score (the scan's shared per-query best, or a pass
-// over the entries when nothing positive was published), then every appended entry within the margin of it is re-scored in exact
-// fp32 and the best by (score desc, row asc) is the result. The lists x (count <= kAppCap) entries are walked as ONE flat index
-// range (prefix sums of the counts in shared memory, binary search per element), so the loads of a thread are independent.
+// Re-rank for the append epilogue (top-1). One block per query.
+//  1. thread t walks lists t, t + 256 (count <= kAppCap entries each, contiguous): entries within the scan's margin m of the best coarse
+//     score (the scan's shared per-query best, or a pass over the entries when nothing positive was published) are collected.
+//  2. e4m3 copy only (finite gap): the eight per-warp coarse leaders are re-scored exactly, L0 = the best of them, and only rows with
+//     coarse >= L0 - E stay. Sound under the SAME event as the certificate: the true best A has exact_A >= L0, so dropping it here
+//     means exact_A - coarse_A > E, the one-row event of probability <= p (kF8LogP) the certificate already charges. It cuts the
+//     candidates of a query without a match ~4x (m = 1.3 E below the best COARSE score -> E below an EXACT one).
+//  3. more than 32 rows left: pre-filter on the fp16 copy (deterministic error, see below); 4. exact fp32 scores, best by (score
+//     desc, row asc), certificate, push to the peers.
 // A list that overflowed (count > kAppCap) or more than kAppRescoreMax in-margin rows flag the query for the exact scan.
 __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2* __restrict__ app_buf, const int* __restrict__ app_cnt,
                                                                     int lists, int q_stride, const float* __restrict__ q,
@@ -729,16 +747,16 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
                                                                     float* __restrict__ out_s, long long* __restrict__ out_i,
                                                                     int* __restrict__ flag_list, int* __restrict__ gbest, const XPush push,
                                                                     const __half* __restrict__ rows_f16, const float* __restrict__ gmax) {
-    constexpr int kListsMax = 2 * 148;
+    constexpr int kW = kSelThreads / 32;
+    constexpr int kPer = kAppRescoreMax / kSelThreads;
+    constexpr int kListsPer = (2 * 148 + kSelThreads - 1) / kSelThreads;  // lists per thread (lists <= kMaxLists = 296)
     __shared__ float x_s[1];
     __shared__ long long x_i[1];
     const unsigned int push_epoch = push.enabled ? xpush_epoch(push, false) : 0u;
     __shared__ float rs[kAppRescoreMax];
     __shared__ int ri[kAppRescoreMax];
-    __shared__ int s_off[kListsMax + 1];  // exclusive prefix sums of the (clamped) counts
-    __shared__ int warp_tot[kSelThreads / 32];
-    __shared__ float red_s[kSelThreads / 32];
-    __shared__ int red_i[kSelThreads / 32];
+    __shared__ float red_s[kW];
+    __shared__ int red_i[kW];
     __shared__ int n_resc, overflow;
     const int qi = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -746,78 +764,124 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
         n_resc = 0;
         overflow = 0;
     }
+    // this thread's lists: entry pointers and (clamped) counts
+    const uint2* lp[kListsPer];
+    int lc[kListsPer];
+#pragma unroll
+    for (int j = 0; j < kListsPer; ++j) {
+        const int l = threadIdx.x + j * kSelThreads;
+        lc[j] = l < lists ? app_cnt[static_cast<size_t>(qi) * lists + l] : 0;  // [query][list]: one contiguous read per query
+        lp[j] = app_buf + (static_cast<size_t>(l < lists ? l : 0) * q_stride + qi) * kAppCap;
+    }
     float4 qa[4];
     load512(q + static_cast<size_t>(qi) * kDim, lane, qa);
     __syncthreads();
-    // counts -> prefix sums (lists <= 296: at most two per thread, processed in two rounds of a block scan)
-    int base = 0;
-    for (int l0 = 0; l0 < lists; l0 += kSelThreads) {
-        const int l = l0 + threadIdx.x;
-        int c = 0;
-        if (l < lists) {
-            c = app_cnt[static_cast<size_t>(qi) * lists + l];  // [query][list]: one contiguous read per query
-            if (c > kAppCap) {
-                overflow = 1;
-                c = kAppCap;
-            }
-        }
-        int inc = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
+    for (int j = 0; j < kListsPer; ++j)
+        if (lc[j] > kAppCap) {
+            overflow = 1;
+            lc[j] = kAppCap;
         }
-        if (lane == 31) warp_tot[warp] = inc;
+    auto block_max = [&](float mx) {  // all threads; leaves the result in every thread
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        __syncthreads();  // red_s may still be read from a previous use
+        if (lane == 0) red_s[warp] = mx;
         __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-        if (l < lists) s_off[l] = base + wbase + inc - c;
-        int round_total = 0;
-        for (int w = 0; w < kSelThreads / 32; ++w) round_total += warp_tot[w];
-        base += round_total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) s_off[lists] = base;
-    __syncthreads();
-    const int total = base;
-    auto entry_of = [&](int e) -> uint2 {
-        int lo = 0, hi = lists;  // largest l with s_off[l] <= e
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= e) lo = mid;
-            else hi = mid;
-        }
-        return __ldg(app_buf + (static_cast<size_t>(lo) * q_stride + qi) * kAppCap + (e - s_off[lo]));
+        mx = red_s[0];
+#pragma unroll
+        for (int w = 1; w < kW; ++w) mx = fmaxf(mx, red_s[w]);
+        return mx;
     };
     float ck = __int_as_float(gbest[qi]);  // cosine units; 0 = nothing positive was published
     if (!(ck > 0.f)) {
         float mx = -INFINITY;
-        for (int e = threadIdx.x; e < total; e += kSelThreads) mx = fmaxf(mx, __uint_as_float(entry_of(e).x));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) red_s[warp] = mx;
-        __syncthreads();
-        mx = red_s[0];
-        for (int w = 1; w < kSelThreads / 32; ++w) mx = fmaxf(mx, red_s[w]);
-        ck = mx;
-        __syncthreads();
+        for (int j = 0; j < kListsPer; ++j)
+            for (int e = 0; e < lc[j]; ++e) mx = fmaxf(mx, __uint_as_float(__ldg(lp[j] + e).x));
+        ck = block_max(mx);
     }
-    const float thr = ck - __ldg(q_margin + qi) * inv_raw;  // the scan's margin (prep_queries_kernel), in cosine units
-    for (int e = threadIdx.x; e < total; e += kSelThreads) {
-        const uint2 en = entry_of(e);
-        if (__uint_as_float(en.x) >= thr) {
-            const int slot = atomicAdd(&n_resc, 1);
-            if (slot < kAppRescoreMax) ri[slot] = static_cast<int>(en.y);
+    const float m_cos = __ldg(q_margin + qi) * inv_raw;  // the scan's margin (prep_queries_kernel), in cosine units
+    const float thr = ck - m_cos;
+#pragma unroll
+    for (int j = 0; j < kListsPer; ++j) {
+        for (int e0 = 0; e0 < lc[j]; e0 += 4) {  // four independent loads in flight (a list is contiguous: mostly one or two lines)
+            uint2 en[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) en[t] = __ldg(lp[j] + (e0 + t < lc[j] ? e0 + t : e0));
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (e0 + t < lc[j] && __uint_as_float(en[t].x) >= thr) {
+                    const int slot = atomicAdd(&n_resc, 1);
+                    if (slot < kAppRescoreMax) {
+                        rs[slot] = __uint_as_float(en[t].x);
+                        ri[slot] = static_cast<int>(en[t].y);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
     int nr = min(n_resc, kAppRescoreMax);
     if (n_resc > kAppRescoreMax && threadIdx.x == 0) overflow = 1;
-    // Pre-filter on the fp16 copy (e4m3 scan with many in-margin rows: queries without a match keep ~800 of a 1.25 M-row shard, and
-    // re-scoring them from the 2 KiB fp32 rows was 129 us per batch, more than half of the scan itself). An fp16 row costs half the bytes
-    // and its score carries a DETERMINISTIC error |s16 - exact| <= eps16 = kCoarseEps |q| gmax, so only rows with s16 >= max s16 - 2 eps16
-    // can hold the exact maximum: the true best A satisfies s16_A >= exact_A - eps16 >= exact_B - eps16 >= s16_B - 2 eps16 for the fp16
-    // leader B. No probability is involved; the certificate below still judges the exact score.
+    const bool had_rows = nr > 0;
+    // in-place compaction of ri[0, nr): keeps the rows whose rs[] value is >= keep_thr. Every thread reads its candidates before the
+    // barrier, survivors are re-appended after it (rs[] is stale afterwards: the next phase rewrites it).
+    auto compact = [&](float keep_thr) {
+        int keep_id[kPer];
+        int n_keep = 0;
+#pragma unroll
+        for (int t = 0; t < kPer; ++t) {
+            const int c = threadIdx.x + t * kSelThreads;
+            keep_id[t] = (c < nr && rs[c] >= keep_thr) ? ri[c] : -1;
+            n_keep += keep_id[t] >= 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) n_resc = 0;
+        __syncthreads();
+        if (n_keep) {
+            int slot = atomicAdd(&n_resc, n_keep);
+#pragma unroll
+            for (int t = 0; t < kPer; ++t)
+                if (keep_id[t] >= 0) ri[slot++] = keep_id[t];
+        }
+        __syncthreads();
+        nr = n_resc;
+    };
+    const float gap = __ldg(q_gap + qi);
+    if (gap > 0.f && gap < INFINITY && nr > kW) {
+        // e4m3 copy: the per-warp coarse leaders (disjoint subsets; the overall coarse leader is one of them), exactly re-scored
+        float bs = -INFINITY;
+        int bc = -1;
+        for (int c = threadIdx.x; c < nr; c += kSelThreads)
+            if (rs[c] > bs) {
+                bs = rs[c];
+                bc = c;
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (oc >= 0 && (bc < 0 || os > bs)) {
+                bs = os;
+                bc = oc;
+            }
+        }
+        bc = __shfl_sync(0xffffffffu, bc, 0);  // equal scores may leave different lanes with different slots: lane 0 decides
+        float l0 = -INFINITY;
+        if (bc >= 0) {  // warp-uniform
+            float4 b[4];
+            load512(rows + static_cast<size_t>(ri[bc]) * kDim, lane, b);
+            l0 = dot512(qa, b);
+        }
+        l0 = block_max(l0);
+        const float E = m_cos - gap;  // m = (1 + kF8GapFrac) E, gap = kF8GapFrac E
+        compact(fmaxf(thr, l0 - E));
+    }
+    // Pre-filter on the fp16 copy (e4m3 scan with many in-margin rows): an fp16 row costs half the bytes of an fp32 row and its score
+    // carries a DETERMINISTIC error |s16 - exact| <= eps16 = kCoarseEps |q| gmax, so only rows with s16 >= max s16 - 2 eps16 can hold the
+    // exact maximum: the true best A satisfies s16_A >= exact_A - eps16 >= exact_B - eps16 >= s16_B - 2 eps16 for the fp16 leader B.
+    // No probability is involved; the certificate below still judges the exact score.
     if (rows_f16 != nullptr && nr > 32) {
         float q16[16];  // the query in the fp16 row's lane layout: elements 8 (lane + 32 j) .. + 7, j = 0, 1
 #pragma unroll
@@ -845,52 +909,30 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             return acc;
         };
-        constexpr int kW = kSelThreads / 32;
-        for (int c = warp; c < nr; c += 2 * kW) {  // two rows in flight per warp
-            const int c2 = c + kW;
-            const uint4* r0 = reinterpret_cast<const uint4*>(rows_f16 + static_cast<size_t>(ri[c]) * kDim);
-            const uint4* r1 = reinterpret_cast<const uint4*>(rows_f16 + static_cast<size_t>(ri[c2 < nr ? c2 : c]) * kDim);
-            const uint4 a0 = __ldg(r0 + lane), a1 = __ldg(r0 + lane + 32), b0 = __ldg(r1 + lane), b1 = __ldg(r1 + lane + 32);
-            const float s0 = dot16(a0, a1), s1 = dot16(b0, b1);
-            if (lane == 0) {
-                rs[c] = s0;
-                if (c2 < nr) rs[c2] = s1;
+        constexpr int kFly = 4;  // rows in flight per warp (the gather is latency-bound: 1 KiB per row, 8 warps per block)
+        for (int c = warp; c < nr; c += kFly * kW) {
+            uint4 v[kFly][2];
+#pragma unroll
+            for (int t = 0; t < kFly; ++t) {
+                const int ct = c + t * kW;
+                const uint4* r = reinterpret_cast<const uint4*>(rows_f16 + static_cast<size_t>(ri[ct < nr ? ct : c]) * kDim);
+                v[t][0] = __ldg(r + lane);
+                v[t][1] = __ldg(r + lane + 32);
+            }
+#pragma unroll
+            for (int t = 0; t < kFly; ++t) {
+                const float s = dot16(v[t][0], v[t][1]);
+                if (lane == 0 && c + t * kW < nr) rs[c + t * kW] = s;
             }
         }
         __syncthreads();
         float mx = -INFINITY;
         for (int c = threadIdx.x; c < nr; c += kSelThreads) mx = fmaxf(mx, rs[c]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) red_s[warp] = mx;
-        if (threadIdx.x == 0) n_resc = 0;
-        __syncthreads();
-        mx = red_s[0];
-        for (int w = 1; w < kW; ++w) mx = fmaxf(mx, red_s[w]);
-        const float keep_thr = mx - 2.f * eps16;
-        // in-place compaction: every thread reads its candidates before the barrier, survivors are re-appended after it
-        constexpr int kPer = kAppRescoreMax / kSelThreads;
-        int keep_id[kPer];
-        int n_keep = 0;
-#pragma unroll
-        for (int t = 0; t < kPer; ++t) {
-            const int c = threadIdx.x + t * kSelThreads;
-            keep_id[t] = (c < nr && rs[c] >= keep_thr) ? ri[c] : -1;
-            n_keep += keep_id[t] >= 0;
-        }
-        __syncthreads();
-        if (n_keep) {
-            int slot = atomicAdd(&n_resc, n_keep);
-#pragma unroll
-            for (int t = 0; t < kPer; ++t)
-                if (keep_id[t] >= 0) ri[slot++] = keep_id[t];
-        }
-        __syncthreads();
-        nr = n_resc;
+        mx = block_max(mx);
+        compact(mx - 2.f * eps16);
     }
-    constexpr int kWr = kSelThreads / 32;
-    for (int c = warp; c < nr; c += 2 * kWr) {  // two rows in flight per warp
-        const int c2 = c + kWr;
+    for (int c = warp; c < nr; c += 2 * kW) {  // two rows in flight per warp
+        const int c2 = c + kW;
         float4 b0[4], b1[4];
         load512(rows + static_cast<size_t>(ri[c]) * kDim, lane, b0);
         load512(rows + static_cast<size_t>(ri[c2 < nr ? c2 : c]) * kDim, lane, b1);
@@ -927,7 +969,7 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < kSelThreads / 32; ++w) {
+        for (int w = 1; w < kW; ++w) {
             const float os = red_s[w];
             const int oi = red_i[w];
             if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
@@ -940,7 +982,8 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
         // certificate of the e4m3 scan (see kF8LogP): accept only if the best exact score is within the gap of the best coarse score;
         // then a pruned true best would need a rounding error beyond E. (+inf gap on the fp16 copy: always passes.)
         // (a gap of -inf marks a query outside the scan copy's range: always recomputed, even if its coarse scores were NaN)
-        if (__ldg(q_gap + qi) == -INFINITY || (bi >= 0 && bs < ck - __ldg(q_gap + qi))) overflow = 1;
+        // (had_rows && bi < 0: the leader filter emptied the set, which needs the same rare event: recompute)
+        if (gap == -INFINITY || (bi >= 0 && bs < ck - gap) || (bi < 0 && had_rows)) overflow = 1;
         if (overflow) flag_list[1 + atomicAdd(&flag_list[0], 1)] = qi;
         gbest[qi] = 0;  // ready for the next search
         x_s[0] = bi >= 0 ? bs : -INFINITY;

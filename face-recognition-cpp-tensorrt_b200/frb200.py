@@ -509,6 +509,13 @@ class Detector:
         check(lib().fr_detector_run(self._h, _ptr(f), f.shape[2] * 3, n, _ptr(boxes), _ptr(counts), _ptr(lm)))
         return boxes, counts, lm
 
+    def run_dev(self, frames_t, boxes_t, counts_t, stream: int = 0) -> None:
+        """device-resident findFace (fr_detector_run_dev): frames_t u8 [n, H, W, 3], boxes_t [n, max_faces, 5] 32-bit words
+        (FrBbox), counts_t int32 [n], all on the detector's device; asynchronous on `stream`"""
+        n = frames_t.shape[0]
+        check(lib().fr_detector_run_dev(self._h, _ptr(frames_t), frames_t.shape[2] * 3, n, _ptr(boxes_t), _ptr(counts_t), None,
+                                        C.c_void_p(stream)))
+
     def _raw_out(self, n):
         a = self.anchors
         return (np.empty((n, a, 4), np.float32), np.empty((n, a, 2), np.float32), np.empty((n, a, 10), np.float32) if self.landmarks else None)
