@@ -236,7 +236,7 @@ void launch_coarse(FrGallery* g, const float* q_dev, int nq, int units, int tile
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(units * CG);
-    cfg.blockDim = dim3(kSearchThreads);
+    cfg.blockDim = dim3(coarse_threads<CG, F8, APP>());
     cfg.dynamicSmemBytes = CoarseCfg<CG, F8>::kSmemBytes;
     cfg.stream = st;
     static bool attr_done[16][2][2][2][2] = {};
@@ -321,7 +321,8 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
         FRB_CUDA(cudaMalloc(&g->app_cnt, sizeof(int) * kMaxLists * kChunkQ));
     }
     if (cg == 2) {
-        units = std::min({g->sms / 2, tiles, kMaxLists / 2});  // scratch and the re-rank kernels are sized for kMaxLists lists
+        // scratch and the re-rank kernels are sized for kMaxLists lists (the e4m3 append scan writes four lists per unit)
+        units = std::min({g->sms / 2, tiles, kMaxLists / (f8 && app ? coarse_epi_warps<2, true, true>() / 4 : 2)});
         if (f8) {
             if (app) launch_coarse<2, 1, true, true>(g, q_dev, nq, units, tiles, st);
             else if (k == 1) launch_coarse<2, 1, true>(g, q_dev, nq, units, tiles, st);
@@ -344,7 +345,7 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
         }
     }
     if (app)
-        append_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->app_buf, g->app_cnt, units * 2, cg * kQRows, q_dev, g->rows_f32, g->q_margin,
+        append_rerank_kernel<<<nq, kSelThreads, 0, st>>>(g->app_buf, g->app_cnt, units * (cg == 2 && f8 ? coarse_epi_warps<2, true, true>() / 4 : 2), cg * kQRows, q_dev, g->rows_f32, g->q_margin,
                                                          g->q_gap, f8 ? 1.f / (kF8Scale * kF8Scale) : 1.f, g->row_offset, scores_dev, idx_dev, g->flags,
                                                          g->gbest, g->push, f8 && g->f16_ok ? g->rows_f16 : nullptr, g->gmax);
     else

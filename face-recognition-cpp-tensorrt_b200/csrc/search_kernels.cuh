@@ -35,6 +35,18 @@ constexpr int kQBytes = kKBlocks * kQTileBytes;      // 128 KiB
 constexpr int kHalfTileBytes = 128 * 128;            // 128 gallery rows x 64 fp16 : one TMA box, 16 KiB
 constexpr int kEpiWarps = 8;                         // 2 column halves x 4 TMEM lane quarters
 constexpr int kSearchThreads = 128 + kEpiWarps * 32; // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: epilogue
+// The append epilogue of the e4m3 pair scan runs SIXTEEN epilogue warps (4 column quarters x 4 TMEM lane quarters): under the wide
+// certified margin its eight warps were busy 77 % of the time at 29 % issue-slot use (two warps per scheduler, every append a chain of
+// dependent votes and branches): latency-bound, not throughput-bound (profiles/r02_f8_unknown_1250k_before_ncu_source.txt), while an
+// e4m3 tile leaves the epilogue half the time an fp16 tile does. 640 threads x 96 registers still fit one CTA per SM.
+template <int CG, bool F8, bool APP>
+constexpr int coarse_epi_warps() {
+    return (CG == 2 && F8 && APP) ? 16 : kEpiWarps;
+}
+template <int CG, bool F8, bool APP>
+constexpr int coarse_threads() {
+    return 128 + coarse_epi_warps<CG, F8, APP>() * 32;
+}
 constexpr int kRingBytes = 96 * 1024;                // gallery stage ring
 constexpr int kLdCols = 16;                          // accumulator columns per tcgen05.ld
 // |coarse - exact| <= kCoarseEps * |q| * |row|: fp16 round-to-nearest of both operands (2 * 2^-11) plus the tensor core's fp32
@@ -205,7 +217,7 @@ __device__ __forceinline__ void topk_insert(float (&s)[KC], int (&ix)[KC], float
 // still reach the exact top-KSEL survives unless more than KC such rows exist (detected in topk_rerank_kernel).
 // ----------------------------------------------------------------------------------------------------------
 template <int CG, int KSEL, bool F8, bool APP = false>
-__global__ void __launch_bounds__(kSearchThreads, 1)
+__global__ void __launch_bounds__((coarse_threads<CG, F8, APP>()), 1)
 cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapq, const float* __restrict__ q_margin,
                    int nq, long long n_rows, int num_tiles, float* __restrict__ cand_s, int* __restrict__ cand_i,
                    int* __restrict__ flag_list, int* __restrict__ gbest, uint2* __restrict__ app_buf, int* __restrict__ app_cnt) {
@@ -214,6 +226,10 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     constexpr int kKB = Cfg::kKB;
     if (blockIdx.x == 0 && threadIdx.x == 0) flag_list[0] = 0;  // list of queries the re-rank hands to the exact scan
     constexpr int KC = ListCfg<KSEL>::kKC;
+    constexpr int kEW = coarse_epi_warps<CG, F8, APP>();  // epilogue warps
+    constexpr int kSplit = kEW / 4;                       // column slices of an accumulator tile (one per epilogue warp group)
+    constexpr int kColsPer = kTileRows / kSplit;
+    static_assert(APP || kSplit == 2, "the sorted-list epilogue is written for two column halves");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -231,6 +247,16 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const int unit = blockIdx.x / CG;
     const int num_units = gridDim.x / CG;
+    // Tile sequence of this unit: tiles unit, unit + num_units, ... . The e4m3 append scan DEFERS its first kDefer tiles: they are first
+    // processed max-only (they seed the per-query threshold, own and - through gbest - every other unit's) and once more, with appends,
+    // at the end of the unit's sequence. Before, a unit's first tile was appended against the threshold of its own 256 rows (best -
+    // margin ~ 1 sigma: 16 % of its rows passed) and the second against little more: two tiles of 66 produced 65 % of all appends of a
+    // 1.25 M-row shard (4600 per query for 1200 in-margin rows; ncu source counters). Cost: kDefer extra tiles of MMA work per unit.
+    constexpr int kDefer = (APP && F8) ? 2 : 0;
+    const int n_my = unit < num_tiles ? (num_tiles - unit + num_units - 1) / num_units : 0;
+    const int n_def = n_my < kDefer ? n_my : kDefer;
+    const int n_it = n_my + n_def;
+    auto tile_of = [&](int it) { return unit + (it < n_my ? it : it - n_my) * num_units; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
@@ -243,7 +269,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
-            mbar_init(&tempty_bar[b], CG * kEpiWarps);  // one arrive per epilogue warp of every CTA of the unit
+            mbar_init(&tempty_bar[b], CG * kEW);  // one arrive per epilogue warp of every CTA of the unit
         }
         mbar_init(q_bar, 1);  // the leader's expect_tx arrival; both CTAs' query loads complete_tx on it
         fence_mbar_init();
@@ -274,8 +300,8 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 else tma_load_2d_pair(q_smem + kb * kQTileBytes, &tmapq, mapa_u32(smem_u32(q_bar), 0), kb * (F8 ? 128 : 64),
                                       static_cast<int>(cta_rank) * kQRows, kEvictLast);
             }
-            for (int t = unit; t < num_tiles; t += num_units) {
-                const int row0 = t * kTileRows;
+            for (int it = 0; it < n_it; ++it) {
+                const int row0 = tile_of(it) * kTileRows;
                 for (int kb = 0; kb < kKB; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* dst = ring + stage * Cfg::kStageBytes;
@@ -301,10 +327,9 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         if (cta_rank == 0 && elect_one()) {
             constexpr uint32_t idesc = umma_idesc(kQRows * CG, kTileRows, 0, 0);
             uint32_t stage = 0, phase = 0;
-            int it = 0;
             mbar_wait(q_bar, 0);  // query operand staged in both CTAs
             tc_fence_after();
-            for (int t = unit; t < num_tiles; t += num_units, ++it) {
+            for (int it = 0; it < n_it; ++it) {
                 const int buf = it & 1;
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -340,7 +365,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     } else if (warp >= 4) {
         // ===================== epilogue: running candidate list per query, in registers =====================
         const int ew = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
-        const int half = (warp - 4) >> 2;  // accumulator column half
+        const int half = (warp - 4) >> 2;  // accumulator column slice (half; quarter with sixteen epilogue warps)
         const int qrow = static_cast<int>(cta_rank) * kQRows + ew * 32 + lane;
         // margin = 2 eps |q| gmax in accumulator units (prep_queries_kernel); 0 for the padding rows beyond nq
         const float margin = qrow < nq ? __ldg(q_margin + qrow) : 0.f;
@@ -348,9 +373,9 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             // ---------- append epilogue (see kAppCap): thread state = running best, threshold, entry count
             constexpr float kRaw = F8 ? kF8Scale * kF8Scale : 1.f;
             constexpr float kInvRaw = 1.f / kRaw;
-            constexpr int kChunksA = (kTileRows / 2) / kLdCols;
+            constexpr int kChunksA = kColsPer / kLdCols;
             const bool live = qrow < nq;
-            const size_t list = (static_cast<size_t>(unit) * 2 + half) * (CG * kQRows) + qrow;
+            const size_t list = (static_cast<size_t>(unit) * kSplit + half) * (CG * kQRows) + qrow;
             uint2* mybuf = app_buf + list * kAppCap;
             float best = -INFINITY, thr = live ? -INFINITY : INFINITY, published = 0.f;
             int cnt = 0;
@@ -398,22 +423,23 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 }
             };
 
-            int it = 0;
-            for (int t = unit; t < num_tiles; t += num_units, ++it) {
+            for (int it = 0; it < n_it; ++it) {
+                const int t = tile_of(it);
                 const int buf = it & 1;
                 // the shared best of this query, fetched now and consumed after the tile: the L2 round trip hides behind the tile
                 const int gb_bits = *gb_ptr;
                 mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * kTileRows + half * (kTileRows / 2);
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * kTileRows + half * kColsPer;
                 const long long row0 = static_cast<long long>(t) * kTileRows;
                 const int valid = (n_rows - row0 >= kTileRows) ? kTileRows : static_cast<int>(n_rows - row0);
                 const int row_base = static_cast<int>(row0);
-                const int cbase = half * (kTileRows / 2);
+                const int cbase = half * kColsPer;
                 uint32_t ra[kLdCols], rb[kLdCols];
-                if (it == 0) {
-                    // first tile: a max-only pass seeds the threshold (and the shared best) before anything is appended; without it
-                    // the first chunks would append every row they see
+                const bool max_only = it < n_def;  // deferred tile, first visit
+                if (max_only || (kDefer == 0 && it == 0)) {
+                    // a max-only pass seeds the threshold (and the shared best) before anything is appended; without it the first chunks
+                    // would append every row they see. kDefer == 0: the first tile is read twice (this pass, then the append pass below).
                     float tm = -INFINITY;
                     float v[kLdCols], tri[5];
                     tmem_ld_32x32b_x16(taddr, ra);
@@ -432,15 +458,17 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         if (tm > 0.f) atomicMax(gbest + qrow, __float_as_int(tm * kInvRaw));
                     }
                 }
-                tmem_ld_32x32b_x16(taddr, ra);
+                if (!max_only) {
+                    tmem_ld_32x32b_x16(taddr, ra);
 #pragma unroll 1
-                for (int c = 0; c < kChunksA; c += 2) {
-                    tmem_ld_wait_x16(ra);
-                    tmem_ld_32x32b_x16(taddr + (c + 1) * kLdCols, rb);
-                    consume_app(ra, cbase + c * kLdCols, valid, row_base);
-                    tmem_ld_wait_x16(rb);
-                    if (c + 2 < kChunksA) tmem_ld_32x32b_x16(taddr + (c + 2) * kLdCols, ra);
-                    consume_app(rb, cbase + (c + 1) * kLdCols, valid, row_base);
+                    for (int c = 0; c < kChunksA; c += 2) {
+                        tmem_ld_wait_x16(ra);
+                        tmem_ld_32x32b_x16(taddr + (c + 1) * kLdCols, rb);
+                        consume_app(ra, cbase + c * kLdCols, valid, row_base);
+                        tmem_ld_wait_x16(rb);
+                        if (c + 2 < kChunksA) tmem_ld_32x32b_x16(taddr + (c + 2) * kLdCols, ra);
+                        consume_app(rb, cbase + (c + 1) * kLdCols, valid, row_base);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -453,12 +481,15 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         published = best;
                         atomicMax(gbest + qrow, __float_as_int(best * kInvRaw));  // non-negative floats order like their bits
                     }
-                    const float gb = __int_as_float(gb_bits);
+                    float gb = __int_as_float(gb_bits);
+                    // last deferred tile: the appends start with the next one, so read the shared best NOW (one exposed L2 round trip):
+                    // every unit published its first tile a whole tile ago
+                    if (kDefer > 0 && it == n_def - 1) gb = __int_as_float(*gb_ptr);
                     if (gb > 0.f) thr = fmaxf(thr, gb * kRaw - margin);
                 }
             }
             // [query][list] so that the re-rank reads one query's counts contiguously
-            app_cnt[static_cast<size_t>(qrow) * (2 * num_units) + unit * 2 + half] = live ? cnt : 0;
+            app_cnt[static_cast<size_t>(qrow) * (kSplit * num_units) + unit * kSplit + half] = live ? cnt : 0;
         } else {
         float best_s[KC];
         int best_i[KC];
@@ -503,8 +534,8 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             }
         };
 
-        int it = 0;
-        for (int t = unit; t < num_tiles; t += num_units, ++it) {
+        for (int it = 0; it < n_it; ++it) {
+            const int t = tile_of(it);
             const int buf = it & 1;
             mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
             tc_fence_after();
@@ -740,7 +771,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_rerank_kernel(const float* _
 //  3. more than 32 rows left: pre-filter on the fp16 copy (deterministic error, see below); 4. exact fp32 scores, best by (score
 //     desc, row asc), certificate, push to the peers.
 // A list that overflowed (count > kAppCap) or more than kAppRescoreMax in-margin rows flag the query for the exact scan.
-__global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2* __restrict__ app_buf, const int* __restrict__ app_cnt,
+__global__ void __launch_bounds__(kSelThreads, 2) append_rerank_kernel(const uint2* __restrict__ app_buf, const int* __restrict__ app_cnt,
                                                                     int lists, int q_stride, const float* __restrict__ q,
                                                                     const float* __restrict__ rows, const float* __restrict__ q_margin,
                                                                     const float* __restrict__ q_gap, float inv_raw, long long row_offset,
@@ -909,7 +940,7 @@ __global__ void __launch_bounds__(kSelThreads) append_rerank_kernel(const uint2*
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             return acc;
         };
-        constexpr int kFly = 4;  // rows in flight per warp (the gather is latency-bound: 1 KiB per row, 8 warps per block)
+        constexpr int kFly = 6;  // rows in flight per warp (the gather is latency-bound: 1 KiB per row, 8 warps per block, 2 blocks per SM)
         for (int c = warp; c < nr; c += kFly * kW) {
             uint4 v[kFly][2];
 #pragma unroll
