@@ -18,14 +18,16 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-BUILD = PKG / "build"
-LIBDIR = PKG / "lib"
+# A/B builds: FR_BUILD_TAG=<name> FR_BUILD_DEFS="-DFR_AB_X=0 ..." python build.py  ->  lib_ab/<name>/libfr_b200.so (tools/ab_search.py)
+TAG = os.environ.get("FR_BUILD_TAG", "")
+BUILD = PKG / "build_ab" / TAG if TAG else PKG / "build"
+LIBDIR = PKG / "lib_ab" / TAG if TAG else PKG / "lib"
 LIB = LIBDIR / "libfr_b200.so"
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-          "-DFR_BUILDING_LIB"]
+          "-DFR_BUILDING_LIB", *os.environ.get("FR_BUILD_DEFS", "").split()]
 
 
 def _sources() -> list[Path]:
@@ -61,8 +63,8 @@ def _compile(src: Path, force: bool, verbose: bool) -> Path:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    BUILD.mkdir(exist_ok=True)
-    LIBDIR.mkdir(exist_ok=True)
+    BUILD.mkdir(parents=True, exist_ok=True)
+    LIBDIR.mkdir(parents=True, exist_ok=True)
     srcs = _sources()
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, force, verbose), srcs))

@@ -39,9 +39,18 @@ constexpr int kSearchThreads = 128 + kEpiWarps * 32; // warps 0-3: TMA / MMA / T
 // certified margin its eight warps were busy 77 % of the time at 29 % issue-slot use (two warps per scheduler, every append a chain of
 // dependent votes and branches): latency-bound, not throughput-bound (profiles/r02_f8_unknown_1250k_before_ncu_source.txt), while an
 // e4m3 tile leaves the epilogue half the time an fp16 tile does. 640 threads x 96 registers still fit one CTA per SM.
+#ifndef FR_AB_EW  // A/B switches (face-recognition-cpp-tensorrt_b200/build.py, tools/ab_search.py)
+#define FR_AB_EW 16
+#endif
+#ifndef FR_AB_DEFER
+#define FR_AB_DEFER 2
+#endif
+#ifndef FR_AB_GBLAG
+#define FR_AB_GBLAG 1
+#endif
 template <int CG, bool F8, bool APP>
 constexpr int coarse_epi_warps() {
-    return (CG == 2 && F8 && APP) ? 16 : kEpiWarps;
+    return (CG == 2 && F8 && APP) ? FR_AB_EW : kEpiWarps;
 }
 template <int CG, bool F8, bool APP>
 constexpr int coarse_threads() {
@@ -252,7 +261,7 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // at the end of the unit's sequence. Before, a unit's first tile was appended against the threshold of its own 256 rows (best -
     // margin ~ 1 sigma: 16 % of its rows passed) and the second against little more: two tiles of 66 produced 65 % of all appends of a
     // 1.25 M-row shard (4600 per query for 1200 in-margin rows; ncu source counters). Cost: kDefer extra tiles of MMA work per unit.
-    constexpr int kDefer = (APP && F8) ? 2 : 0;
+    constexpr int kDefer = (APP && F8) ? FR_AB_DEFER : 0;
     const int n_my = unit < num_tiles ? (num_tiles - unit + num_units - 1) / num_units : 0;
     const int n_def = n_my < kDefer ? n_my : kDefer;
     const int n_it = n_my + n_def;
@@ -423,13 +432,20 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 }
             };
 
+            int gb_bits = 0;  // the shared best of this query as fetched during the previous tile (bits of a non-negative float)
             for (int it = 0; it < n_it; ++it) {
                 const int t = tile_of(it);
                 const int buf = it & 1;
-                // the shared best of this query, fetched now and consumed after the tile: the L2 round trip hides behind the tile
-                const int gb_bits = *gb_ptr;
                 mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
                 tc_fence_after();
+                // the shared best: the value fetched a whole tile ago is applied now and the next fetch is issued, so its L2 round trip
+                // hides behind this tile AND the wait for the next accumulator (with sixteen epilogue warps a warp's share of a tile is
+                // shorter than the round trip: consumed at the end of the same tile it was 14 % of the epilogue's time)
+                if (FR_AB_GBLAG && live) {
+                    const float gb = __int_as_float(gb_bits);
+                    if (gb > 0.f) thr = fmaxf(thr, gb * kRaw - margin);
+                }
+                gb_bits = *gb_ptr;
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * kTileRows + half * kColsPer;
                 const long long row0 = static_cast<long long>(t) * kTileRows;
                 const int valid = (n_rows - row0 >= kTileRows) ? kTileRows : static_cast<int>(n_rows - row0);
@@ -481,11 +497,16 @@ cosine_topk_coarse(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         published = best;
                         atomicMax(gbest + qrow, __float_as_int(best * kInvRaw));  // non-negative floats order like their bits
                     }
-                    float gb = __int_as_float(gb_bits);
                     // last deferred tile: the appends start with the next one, so read the shared best NOW (one exposed L2 round trip):
                     // every unit published its first tile a whole tile ago
-                    if (kDefer > 0 && it == n_def - 1) gb = __int_as_float(*gb_ptr);
-                    if (gb > 0.f) thr = fmaxf(thr, gb * kRaw - margin);
+                    if (kDefer > 0 && it == n_def - 1) {
+                        const float gb = __int_as_float(*gb_ptr);
+                        if (gb > 0.f) thr = fmaxf(thr, gb * kRaw - margin);
+                    }
+                    if (!FR_AB_GBLAG) {  // A/B: the fetch of this tile applied at its own end
+                        const float gb = __int_as_float(gb_bits);
+                        if (gb > 0.f) thr = fmaxf(thr, gb * kRaw - margin);
+                    }
                 }
             }
             // [query][list] so that the re-rank reads one query's counts contiguously

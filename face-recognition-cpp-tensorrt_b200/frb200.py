@@ -6,12 +6,13 @@ library and raises if the library is missing — there is no CPU fallback here o
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libfr_b200.so"
+LIB_PATH = Path(os.environ["FR_B200_LIB"]) if os.environ.get("FR_B200_LIB") else PKG / "lib" / "libfr_b200.so"  # A/B builds (tools/ab_search.py)
 
 FR_OK, FR_EINVAL, FR_ENODEVICE, FR_ECUDA, FR_ENOENT, FR_EFORMAT, FR_ESTATE = 0, -1, -2, -3, -4, -5, -6
 FR_TOPK_MAX = 8

@@ -126,9 +126,16 @@ def certified_top1(G, q, seed=DEFAULT_SEED, logp=LOGP, rounding="dither"):
     exact_idx = exact.argmax(1)                                                   # first maximum, src/arcface.cpp:210
     ck = coarse.max(1)
     cand = coarse >= (ck - m)[:, None]
+    n_margin = cand.sum(1)
+    # append_rerank_kernel's exact-leader filter: L0 = best EXACT score among a few coarse leaders (the kernel takes its eight per-warp
+    # leaders, which always include the overall coarse leader; here the eight best coarse rows); only rows with coarse >= L0 - E stay.
+    lead = np.argsort(-np.where(cand, coarse, -np.inf), axis=1, kind="stable")[:, :8]
+    rows = np.arange(q.shape[0])[:, None]
+    l0 = np.where(cand[rows, lead], exact[rows, lead], -np.inf).max(1)
+    cand &= coarse >= np.maximum(ck - m, l0 - E)[:, None]
     masked = np.where(cand, exact, -np.inf)
     idx = masked.argmax(1)
     L = masked.max(1)
-    flagged = (L < ck - gap) | (cand.sum(1) > 4096)
-    return {"idx": np.where(flagged, -1, idx), "flagged": flagged, "n_cand": cand.sum(1), "best_in_cand": cand[np.arange(q.shape[0]), exact_idx],
+    flagged = (L < ck - gap) | (n_margin > 4096)
+    return {"idx": np.where(flagged, -1, idx), "flagged": flagged, "n_cand": cand.sum(1), "n_margin": n_margin, "best_in_cand": cand[np.arange(q.shape[0]), exact_idx],
             "exact_idx": exact_idx, "margin": m, "E": E, "coarse": coarse, "exact": exact}
