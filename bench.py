@@ -540,14 +540,16 @@ def run_b200(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if mode == "e2e":
             est = torch.cuda.ExternalStream(sstream.cuda_stream, device=dev)
-            sstream.submit(q_host[kd])                    # one batch in flight before the clock starts
+            sstream.submit(q_host[kd])                    # two batches in flight before the clock starts
+            sstream.submit(q_host[kd])
             barrier()
             ev0.record(est)
             for _ in range(steps):
                 sstream.submit(q_host[kd])                # pinned staging + H2D + search (+ push, + merge of the previous batch) + D2H
-                sstream.collect(res_s, res_i)             # blocks for the OLDER batch; the newer one keeps the GPU busy
+                sstream.collect(res_s, res_i)             # blocks for the OLDEST batch; the two newer ones keep the GPU busy
             ev1.record(est)
             barrier()
+            sstream.collect(res_s, res_i)
             sstream.collect(res_s, res_i)
             if not np.array_equal(res_i[:, 0], want[kd][0]):
                 raise SystemExit(f"bench.py: e2e parity failure ({name})")
@@ -675,7 +677,7 @@ def run_b200(args):
                                     "synchronize, max over ranks; every phase runs `passes` continuous windows (first quarter of each unrecorded: clock settling)",
                        "ms_per_step_min_max": head["ms_per_step_min_max"], "timed_wall_s": timed_wall_s, "phases": [p[0] for p in phases]},
             "e2e": dict(head.get("e2e", {"value": None, "unit": UNIT}), h2d_bytes_per_step=Q * 512 * 4, d2h_bytes_per_step=Q * K * 12,
-                        api="fr_search_stream_submit + fr_search_stream_collect (host buffers; pinned staging, H2D, search, cross-GPU merge, D2H inside), two batches in flight"),
+                        api="fr_search_stream_submit + fr_search_stream_collect (host buffers; pinned staging, H2D, search, cross-GPU merge, D2H inside; copies on a second stream), three batches in flight"),
             "gpu_launches": int((launches_per_step.get(args.scan) or 0) * KS),
             "clocks": clocks,
             "parity": head["parity"]["planted"],

@@ -363,7 +363,11 @@ struct FrSearchStream {
     FrGallery* g = nullptr;
     FrExchange* x = nullptr;
     int k = 1;
-    cudaStream_t st = nullptr;
+    static constexpr int kMaxInFlight = 3;
+    cudaStream_t st = nullptr;       // searches, pushes, merges
+    cudaStream_t cp = nullptr;       // H2D of the queries / D2H of the results: overlap the scans of the neighbouring batches
+    cudaEvent_t h2d[kRing] = {};     // queries of the slot are on the device
+    cudaEvent_t res[kRing] = {};     // results of the slot are final on the device
     float* q_pin[kRing] = {};
     float* q_dev[kRing] = {};
     float* s_pin[kRing] = {};
@@ -382,9 +386,11 @@ void enqueue_delivery(FrSearchStream* s, long long b) {
     const int r = static_cast<int>(b % FrSearchStream::kRing);
     if (s->delivered[r]) return;
     if (s->x) launch_wait_merge(s->x, s->nq[r], s->k, s->res_s[r], s->res_i[r], s->st);
-    FRB_CUDA(cudaMemcpyAsync(s->s_pin[r], s->res_s[r], sizeof(float) * s->nq[r] * s->k, cudaMemcpyDeviceToHost, s->st));
-    FRB_CUDA(cudaMemcpyAsync(s->i_pin[r], s->res_i[r], sizeof(long long) * s->nq[r] * s->k, cudaMemcpyDeviceToHost, s->st));
-    FRB_CUDA(cudaEventRecord(s->done[r], s->st));
+    FRB_CUDA(cudaEventRecord(s->res[r], s->st));
+    FRB_CUDA(cudaStreamWaitEvent(s->cp, s->res[r], 0));
+    FRB_CUDA(cudaMemcpyAsync(s->s_pin[r], s->res_s[r], sizeof(float) * s->nq[r] * s->k, cudaMemcpyDeviceToHost, s->cp));
+    FRB_CUDA(cudaMemcpyAsync(s->i_pin[r], s->res_i[r], sizeof(long long) * s->nq[r] * s->k, cudaMemcpyDeviceToHost, s->cp));
+    FRB_CUDA(cudaEventRecord(s->done[r], s->cp));
     s->delivered[r] = true;
 }
 }  // namespace
@@ -403,7 +409,10 @@ int fr_search_stream_create(FrGallery* g, FrExchange* x, int k, FrSearchStream**
         DeviceGuard dg(g->device);
         try {
             FRB_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+            FRB_CUDA(cudaStreamCreateWithFlags(&s->cp, cudaStreamNonBlocking));
             for (int r = 0; r < FrSearchStream::kRing; ++r) {
+                FRB_CUDA(cudaEventCreateWithFlags(&s->h2d[r], cudaEventDisableTiming));
+                FRB_CUDA(cudaEventCreateWithFlags(&s->res[r], cudaEventDisableTiming));
                 FRB_CUDA(cudaMallocHost(&s->q_pin[r], sizeof(float) * kChunkQ * kDim));
                 FRB_CUDA(cudaMalloc(&s->q_dev[r], sizeof(float) * kChunkQ * kDim));
                 FRB_CUDA(cudaMallocHost(&s->s_pin[r], sizeof(float) * kChunkQ * FR_TOPK_MAX));
@@ -426,7 +435,10 @@ void fr_search_stream_destroy(FrSearchStream* s) {
     cudaGetDevice(&prev);
     cudaSetDevice(s->g->device);
     if (s->st) cudaStreamSynchronize(s->st);
+    if (s->cp) cudaStreamSynchronize(s->cp);
     for (int r = 0; r < FrSearchStream::kRing; ++r) {
+        if (s->h2d[r]) cudaEventDestroy(s->h2d[r]);
+        if (s->res[r]) cudaEventDestroy(s->res[r]);
         cudaFreeHost(s->q_pin[r]);
         cudaFree(s->q_dev[r]);
         cudaFreeHost(s->s_pin[r]);
@@ -436,6 +448,7 @@ void fr_search_stream_destroy(FrSearchStream* s) {
         if (s->done[r]) cudaEventDestroy(s->done[r]);
     }
     if (s->st) cudaStreamDestroy(s->st);
+    if (s->cp) cudaStreamDestroy(s->cp);
     if (prev >= 0) cudaSetDevice(prev);
     delete s;
 }
@@ -447,7 +460,7 @@ int fr_search_stream_submit(FrSearchStream* s, const float* q, int nq) {
     return guarded([&] {
         if (!s || !q) throw ArgError{"null argument"};
         if (nq < 1 || nq > kChunkQ) throw ArgError{"1..256 queries per batch"};
-        if (s->submitted - s->collected >= 2) throw StateError{"two batches already in flight: collect one first"};
+        if (s->submitted - s->collected >= FrSearchStream::kMaxInFlight) throw StateError{"three batches already in flight: collect one first"};
         FrGallery* g = s->g;
         if (!s->x && g->n == 0) throw StateError{"Feature matching: No faces in database or no faces found"};
         DeviceGuard dg(g->device);
@@ -456,7 +469,10 @@ int fr_search_stream_submit(FrSearchStream* s, const float* q, int nq) {
         std::memcpy(s->q_pin[r], q, sizeof(float) * nq * kDim);
         s->nq[r] = nq;
         s->delivered[r] = false;
-        FRB_CUDA(cudaMemcpyAsync(s->q_dev[r], s->q_pin[r], sizeof(float) * nq * kDim, cudaMemcpyHostToDevice, s->st));
+        // the slot's previous batch (kRing >= kMaxInFlight + 1 batches ago) was collected, so its search has long read q_dev[r]
+        FRB_CUDA(cudaMemcpyAsync(s->q_dev[r], s->q_pin[r], sizeof(float) * nq * kDim, cudaMemcpyHostToDevice, s->cp));
+        FRB_CUDA(cudaEventRecord(s->h2d[r], s->cp));
+        FRB_CUDA(cudaStreamWaitEvent(s->st, s->h2d[r], 0));
         if (s->x) {
             const int rc = fr_gallery_topk_push_dev(g, s->x, s->q_dev[r], nq, s->k, g->loc_s, reinterpret_cast<int64_t*>(g->loc_i), s->st);
             if (rc != FR_OK) throw CudaError{std::string("sharded search failed: ") + fr_last_error()};

@@ -338,7 +338,7 @@ class Roster:
 
 
 class SearchStream:
-    """fr_search_stream_*: asynchronous host-buffer search with two batches in flight (the serving form of search_topk)"""
+    """fr_search_stream_*: asynchronous host-buffer search with up to three batches in flight (the serving form of search_topk)"""
 
     def __init__(self, gal: "Gallery", exchange=None, k: int = 1):
         L = lib()

@@ -201,11 +201,13 @@ void fr_exchange_destroy(FrExchange *x);
  * gallery's own stream. With x != NULL every rank must call it with the same queries. */
 int fr_search_topk(FrGallery *g, FrExchange *x, const float *q, int nq, int k, float *scores, int64_t *idx, void *stream);
 
-/* Asynchronous form of fr_search_topk for serving: up to two batches in flight, so the GPU always has the next search queued while
- * the host collects the previous result; on a sharded gallery the cross-GPU merge of batch i is issued after the search of batch
- * i + 1. Queries are copied into library-owned pinned memory inside submit (the caller's buffer is free on return); collect blocks
- * for the OLDEST batch in flight and writes its nq x k results. All ranks of a sharded gallery submit / collect in the same order.
- * submit fails with FR_ESTATE when two batches are already in flight, collect when none is. */
+/* Asynchronous form of fr_search_topk for serving: up to THREE batches in flight, so the GPU always has the next search queued while
+ * the host collects a previous result (with a lagged cross-GPU merge the result of batch i is only final after the search of batch
+ * i + 1: a third batch keeps the search stream fed across the host's collect -> submit turnaround); the H2D of the queries and the
+ * D2H of the results run on a second stream beside the scans. On a sharded gallery the cross-GPU merge of batch i is issued after
+ * the search of batch i + 1. Queries are copied into library-owned pinned memory inside submit (the caller's buffer is free on
+ * return); collect blocks for the OLDEST batch in flight and writes its nq x k results. All ranks of a sharded gallery submit /
+ * collect in the same order. submit fails with FR_ESTATE when three batches are already in flight, collect when none is. */
 typedef struct FrSearchStream FrSearchStream;
 int fr_search_stream_create(FrGallery *g, FrExchange *x, int k, FrSearchStream **out);
 void fr_search_stream_destroy(FrSearchStream *s);

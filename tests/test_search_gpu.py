@@ -770,9 +770,9 @@ def test_roster_lifecycle_on_sharded_gallery(tmp_path):
 
 
 @pytest.mark.parametrize("scan", [frb200.FR_SCAN_F16, frb200.FR_SCAN_F8])
-def test_search_stream_two_batches_in_flight(scan):
+def test_search_stream_batches_in_flight(scan):
     # fr_search_stream_*: the asynchronous host-buffer search (bench.py's e2e). Results come back in submission order, equal to the
-    # synchronous call, with up to two batches in flight; a third submit / an empty collect are refused.
+    # synchronous call, with up to three batches in flight; a fourth submit / an empty collect are refused.
     rng = np.random.default_rng(44)
     n = 80_000
     G = so.l2_normalise(rng.standard_normal((n, 512)))
@@ -787,16 +787,17 @@ def test_search_stream_two_batches_in_flight(scan):
         ss.collect(s_out, i_out)
     ss.submit(batches[0])
     ss.submit(batches[1])
+    ss.submit(batches[2])
     with pytest.raises(frb200.FrError) as e:
-        ss.submit(batches[2])
+        ss.submit(batches[3])
     assert e.value.code == frb200.FR_ESTATE
     for b in range(len(batches)):
         nq = ss.collect(s_out, i_out)
         assert nq == batches[b].shape[0]
         assert np.array_equal(i_out[:nq], want[b][1]) and np.array_equal(s_out[:nq].view(np.uint32), want[b][0].view(np.uint32))
-        if b + 2 < len(batches):
-            batches[b + 2][:] = batches[b + 2]           # the caller's buffer is free again as soon as submit returns
-            ss.submit(batches[b + 2])
+        if b + 3 < len(batches):
+            batches[b + 3][:] = batches[b + 3]           # the caller's buffer is free again as soon as submit returns
+            ss.submit(batches[b + 3])
     ss.close()
     g.close()
 
