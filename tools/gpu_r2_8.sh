@@ -8,7 +8,7 @@ timeout 900 $TR bench.py --gpus $N --steps 20 --warmup 3 --no-pipeline --no-cpu-
 echo "bench$N rc=$?"; tail -c 400 gpurun_out/r2_8_bench_${N}gpu.err | tail -4
 python - <<P
 import json
-d=json.load(open("gpurun_out/r2_8_bench_${N}gpu.json"))
+d=json.loads([l for l in open("gpurun_out/r2_8_bench_${N}gpu.json") if l.startswith("{")][-1])
 print("headline", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"])
 for k,v in d["scans"].items():
     print(k, "ms/step", round(v["ms_per_step"],4), "q/s", round(v["value"]), "unknown q/s", round(v["unknown_queries"]["value"]), "e2e q/s", round(v["e2e"]["value"]), "kernel_ms", round(v["roofline"]["kernel_ms"],4), "frac", round(v["roofline"]["frac"],3), v["parity"])
