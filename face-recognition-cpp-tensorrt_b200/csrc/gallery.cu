@@ -316,7 +316,8 @@ void topk_chunk(FrGallery* g, const float* q_dev, int nq, int k, float* scores_d
     // k > 1 on an e4m3 gallery is served by the resident fp16 copy: the sorted-list epilogue a top-k needs overflows under the e4m3
     // copy's wide certified margin (unmatched queries fell through to the exact scan: correct but slow), while the fp16 copy's margin is
     // a few 1e-3 and its result deterministic. The e4m3 copy keeps the top-1 searches (getOutputs, src/arcface.cpp:203-217).
-    const bool f8 = g->scan == FR_SCAN_F8 && (k == 1 || !g->f16_ok);
+    // (FR_F8_TOPK=1, read per call on this rare path, keeps k > 1 on the e4m3 copy: the accumulation test reads its coarse scores)
+    const bool f8 = g->scan == FR_SCAN_F8 && (k == 1 || !g->f16_ok || [] { const char* e = std::getenv("FR_F8_TOPK"); return e && e[0] == '1'; }());
     const bool app = k == 1 && (append_mode() >= 2 || (append_mode() == 1 && f8));
     if (app && !g->app_buf) {
         // not reached while a stream capture is open: callers warm a search up before capturing it (cudaMalloc is not capturable)
