@@ -74,9 +74,29 @@ __global__ void __launch_bounds__(256) det_letterbox_kernel(const uint8_t* __res
 
 // ---- body.stage1.0: Conv3x3(3->8, s2, p1) + BN + ReLU on the letterboxed u8 canvas, fused with RetinaFace::preprocess's
 //      convertTo(CV_32F) and mean subtraction (104, 117, 123) in B,G,R order (src/retinaface.cpp:128-135).
+// The weights of the per-pixel kernels (this stem, the depthwise halves of dwpw_small_kernel) are KERNEL PARAMETERS: every lane of a
+// warp multiplies by the same weight, so an FFMA takes it as a constant-bank operand (c[0x0][...]) and the shared-memory weight
+// fetches (54 LDS.128 of 380 instructions per stem pixel) disappear. Same fp32 FMAs in the same order: results are bit-identical.
+#ifndef FR_AB_CONSTW
+#define FR_AB_CONSTW 1
+#endif
+struct StemW {
+    float w[27][8];  // [tap * 3 + channel][output channel]
+    float b[8];
+};
+struct DwW {
+    float w[9][32];  // [tap][channel] (CIN <= 32)
+    float b[32];
+};
 __global__ void __launch_bounds__(256) det_stem_kernel(const uint8_t* __restrict__ canvas, int stride_bytes, int batch, int Hn, int Wn,
                                                        const float* __restrict__ w /*[8][27]*/, const float* __restrict__ bias,
-                                                       __half* __restrict__ out) {
+                                                       __half* __restrict__ out, const __grid_constant__ StemW cw) {
+#if FR_AB_CONSTW
+    const auto& ws = cw.w;
+    const auto& sb = cw.b;
+    griddep_launch_dependents();
+    griddep_wait();
+#else
     __shared__ float ws[27][8];
     __shared__ float sb[8];
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) ws[i % 27][i / 27] = w[i];
@@ -84,6 +104,7 @@ __global__ void __launch_bounds__(256) det_stem_kernel(const uint8_t* __restrict
     griddep_launch_dependents();
     __syncthreads();
     griddep_wait();  // the weights staged above are static; the frames and the output map are not
+#endif
     const Geo g{Hn / 2, Wn / 2};
     const int t = blockIdx.x * blockDim.x + threadIdx.x;  // pixels of a batch < 2^31 (checked by the host)
     if (t >= batch * g.H * g.W) return;
@@ -254,14 +275,20 @@ __device__ __forceinline__ uint4 split_weight_frag(float w0, float w1, float w8,
 template <int CIN, int COUT, int S>
 __global__ void __launch_bounds__(256) dwpw_small_kernel(const __half* __restrict__ in, Geo gi, __half* __restrict__ out, Geo go, int batch,
                                                          const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                                                         const float* __restrict__ pw_w, const float* __restrict__ pw_b) {
+                                                         const float* __restrict__ pw_w, const float* __restrict__ pw_b,
+                                                         const __grid_constant__ DwW cw) {
     constexpr int KS = CIN >= 16 ? CIN / 16 : 1;  // k-steps (k16, or one k8 step for CIN = 8)
     constexpr int NT = COUT / 8;                  // 8-column output tiles
     constexpr int kInStride = CIN * 2 + 16;       // bytes per pixel row of the depthwise tile (padded: conflict-free ldmatrix)
     constexpr int kOutStride = COUT * 2 + 16;     // bytes per pixel row of the output tile
     constexpr int kTileBytes = 32 * (kInStride > kOutStride ? kInStride : kOutStride);
+#if FR_AB_CONSTW
+    const auto& sdw = cw.w;  // depthwise weights / bias as constant-bank operands (see StemW)
+    const auto& sdb = cw.b;
+#else
     __shared__ float sdw[9][CIN];
     __shared__ float sdb[CIN];
+#endif
     __shared__ float spb[COUT];
     // weight fragments {b0, b1} of lane l for k-step ks, column tile nt, as fp16 hi + fp16 lo (w = hi + lo to ~22 bits: two MMAs per
     // fragment keep the fp32 weights' accuracy - with single fp16 weights the raw heads drifted past 1e-2 of the fp32 oracle)
@@ -269,8 +296,10 @@ __global__ void __launch_bounds__(256) dwpw_small_kernel(const __half* __restric
     __shared__ __align__(16) uint8_t tiles[8][kTileBytes];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t4 = lane & 3;
+#if !FR_AB_CONSTW
     for (int i = threadIdx.x; i < 9 * CIN; i += blockDim.x) reinterpret_cast<float*>(&sdw[0][0])[i] = dw_w[i];
     for (int i = threadIdx.x; i < CIN; i += blockDim.x) sdb[i] = dw_b[i];
+#endif
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) spb[i] = pw_b[i];
     for (int i = threadIdx.x; i < KS * NT * 32; i += blockDim.x) {
         const int l = i & 31, nt = (i >> 5) % NT, ks = i / (32 * NT);

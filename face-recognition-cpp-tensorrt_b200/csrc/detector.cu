@@ -42,6 +42,7 @@ struct DStep {
     int stride = 1, cin = 0, cout = 0, ld_out = 0;
     const float* w = nullptr;
     const float* b = nullptr;
+    DwW dww{};                  // fused small blocks: host copy of the depthwise weights / bias (kernel parameter, see StemW)
     const float* w2 = nullptr;  // fused blocks: pointwise weights / bias; c16: second conv on the same input
     const float* b2 = nullptr;
     __half* out2 = nullptr;
@@ -67,6 +68,7 @@ struct FrDetector {
     cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
     std::vector<void*> allocs;
     float *stem_w = nullptr, *stem_b = nullptr;
+    StemW stem_cw{};                 // host copy of the stem weights, passed to det_stem_kernel as a kernel parameter
     uint8_t* frames_dev = nullptr;   // max_batch x frame_h x frame_w x 3
     uint8_t* canvas_dev = nullptr;   // max_batch x net_h x net_w x 3 (only when frame size != network size)
     float* chw_dev = nullptr;        // fr_detector_net input
@@ -133,6 +135,12 @@ void build_plan(FrDetector* d, const WeightFile& wf) {
     for (int k = 1; k <= 5; ++k) d->g[k] = Geo{d->net_h >> k, d->net_w >> k};
     d->stem_w = f32("stem.w", 8 * 27);
     d->stem_b = f32("stem.b", 8);
+    {
+        const float* hw = reinterpret_cast<const float*>(wf.get("stem.w", 0, 8 * 27).data);
+        const float* hb = reinterpret_cast<const float*>(wf.get("stem.b", 0, 8).data);
+        for (int i = 0; i < 27 * 8; ++i) d->stem_cw.w[i % 27][i / 27] = hw[i];  // file: [output channel][27]
+        for (int n = 0; n < 8; ++n) d->stem_cw.b[n] = hb[n];
+    }
     d->frames_dev = dalloc<uint8_t>(d, static_cast<size_t>(B) * d->frame_h * d->frame_w * 3, false);
     d->chw_dev = dalloc<float>(d, static_cast<size_t>(B) * 3 * d->net_h * d->net_w, false);
 
@@ -191,6 +199,13 @@ void build_plan(FrDetector* d, const WeightFile& wf) {
             s.cout = dw_cout[n];
             s.w = f32("dw" + id + ".w", 9 * dw_cin[n]);
             s.b = f32("dw" + id + ".b", dw_cin[n]);
+            {
+                const float* hw = reinterpret_cast<const float*>(wf.get("dw" + id + ".w", 0, 9 * dw_cin[n]).data);  // [tap][channel]
+                const float* hb = reinterpret_cast<const float*>(wf.get("dw" + id + ".b", 0, dw_cin[n]).data);
+                for (int t = 0; t < 9; ++t)
+                    for (int c = 0; c < dw_cin[n]; ++c) s.dww.w[t][c] = hw[t * dw_cin[n] + c];
+                for (int c = 0; c < dw_cin[n]; ++c) s.dww.b[c] = hb[c];
+            }
             s.w2 = f32("pw" + id + ".w", static_cast<int64_t>(dw_cin[n]) * dw_cout[n]);
             s.b2 = f32("pw" + id + ".b", dw_cout[n]);
             d->steps.push_back(s);
@@ -375,7 +390,7 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
     const long long px = static_cast<long long>(batch) * g1.H * g1.W;
     if (canvas_dev)
         launch_k(det_stem_kernel, dim3(blocks_for(px, 256)), dim3(256), 0, st, true, canvas_dev, stride_bytes, batch, d->net_h, d->net_w, d->stem_w,
-                 d->stem_b, d->a0);
+                 d->stem_b, d->a0, d->stem_cw);
     else
         launch_k(det_stem_f32_kernel, dim3(blocks_for(px, 256)), dim3(256), 0, st, true, chw_dev, batch, d->net_h, d->net_w, d->stem_w, d->stem_b, d->a0);
     count_launch();
@@ -408,7 +423,7 @@ void run_net(FrDetector* d, const uint8_t* canvas_dev, int stride_bytes, const f
                     int occ = 1;  // resident CTAs per SM of this instantiation: the grid is exactly one full wave (grid-stride inside)
                     FRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
                     const int nb = static_cast<int>(std::min<long long>((t + 255) / 256, static_cast<long long>(std::max(occ, 1)) * d->sms));
-                    launch_k(kern, dim3(nb), dim3(256), 0, st, true, s.in, s.gi, s.out, s.go, batch, s.w, s.b, s.w2, s.b2);
+                    launch_k(kern, dim3(nb), dim3(256), 0, st, true, s.in, s.gi, s.out, s.go, batch, s.w, s.b, s.w2, s.b2, s.dww);
                 };
                 if (s.cin == 8 && s.cout == 16 && s.stride == 1) launch(dwpw_small_kernel<8, 16, 1>);
                 else if (s.cin == 16 && s.cout == 32 && s.stride == 2) launch(dwpw_small_kernel<16, 32, 2>);
