@@ -220,7 +220,11 @@ int pick_pair(const GemmStep& s, const ConvGemmParams& prm, double& cost_out) {
     for (int bn : {256, 128}) {
         if (prm.cout % bn || (force && bn != force)) continue;
         const long long units = tiles * (prm.cout / bn);
-        if (units < pairs) continue;  // cannot fill the GPU: the single-CTA kernel has smaller units
+        // far from filling the GPU: the single-CTA kernel has smaller units. From 3/4 of the pairs on (FR_PAIR_MINFILL, A/B) the pair kernel
+        // still wins: each CTA of a pair streams only half of every weight tile from L2 (batch 32: 1.201 -> 1.171 ms, batch 64: 1.767 ->
+        // 1.710 ms per forward, profiles/r02_embed_ab_pair_minfill.txt)
+        static const double minfill = std::getenv("FR_PAIR_MINFILL") ? std::atof(std::getenv("FR_PAIR_MINFILL")) : 0.75;
+        if (units < pairs * minfill) continue;
         // rounds x (unit time + overhead) in units of a single CTA's 128 x 128 tile (pick_mt's scale): a pair does 256 x BN in the time
         // one CTA needs for 128 x BN, faster still because shared memory no longer limits it. Measured (IR-SE-50, batch 256): N = 128
         // MMAs keep the tensor pipe 62-66 % busy; N = 256 pays for a worse last round (225 units on 74 pairs, softened by the half-width
