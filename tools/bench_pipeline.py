@@ -23,15 +23,17 @@ EMB_GFLOP_PER_FACE = 12.593
 DET_MB_PER_FRAME = 54.9 + 1.23
 
 
-def _event_time(torch, fn, reps, warm=3):
+def _event_time(torch, fn, reps, warm=3, stream=None):
+    """CUDA events on `stream` (the stream fn launches on; None = torch's current stream, for the host-buffer calls that synchronise
+    themselves)"""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(stream)
     for _ in range(reps):
         fn()
-    e1.record()
+    e1.record(stream)
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e-3 / reps
 
@@ -137,31 +139,39 @@ def run_gpu(device: int, frames_batch=64, gallery_rows=1_000_000, reps=10, hbm_g
         # ---- timed: `reps` batches back to back through the public host-buffer calls, wall clock between barriers, max over ranks.
         # (a) fr_pipeline_run: synchronous, one batch at a time; (b) fr_pipeline_submit / fr_pipeline_collect: two batches in flight (batch
         # i + 1 crosses PCIe and is enqueued while batch i computes) - what a serving loop does. Identities are checked in both loops.
-        def timed(step_fn, drain_fn=None):
+        windows_ms = {}
+
+        def timed(step_fn, drain_fn=None, name="", windows=5):
+            """median of `windows` windows of `reps` batches each (a window is ~65 ms of wall clock: one host hiccup - a page fault, a
+            scheduler stall - used to decide the whole number); every window: barrier + synchronize on both sides, max over ranks"""
             for _ in range(3):
                 step_fn()
             if drain_fn:
                 drain_fn()
-            barrier()
-            l0 = frb200.launch_count()
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                step_fn()
-            if drain_fn:
-                drain_fn()
-            torch.cuda.synchronize()
-            t = (time.perf_counter() - t0) / reps
-            launches = (frb200.launch_count() - l0) // reps
-            t_all = max_over_ranks(t)
-            barrier()
-            return t_all, launches
+            ts, launches = [], 0
+            for _ in range(windows):
+                torch.cuda.synchronize()
+                barrier()
+                l0 = frb200.launch_count()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    step_fn()
+                if drain_fn:
+                    drain_fn()
+                torch.cuda.synchronize()
+                t = (time.perf_counter() - t0) / reps
+                launches = (frb200.launch_count() - l0) // reps
+                ts.append(max_over_ranks(t))
+                barrier()
+            windows_ms[name] = [round(x * 1e3, 4) for x in ts]
+            return float(np.median(ts)), launches
 
         last = {}
 
         def sync_step():
             last["res"] = pipe.run(frames)
 
-        t_sync, launches = timed(sync_step)
+        t_sync, launches = timed(sync_step, name="synchronous")
         if not np.array_equal(last["res"]["idx"], exp):
             raise RuntimeError("pipeline parity gate failed inside the timed loop (synchronous call)")
         bad = []
@@ -179,7 +189,7 @@ def run_gpu(device: int, frames_batch=64, gallery_rows=1_000_000, reps=10, hbm_g
                 if not np.array_equal(r["idx"], exp):
                     bad.append(1)
 
-        t_fl, _ = timed(flight_step, flight_drain)
+        t_fl, _ = timed(flight_step, flight_drain, name="in_flight")
         if bad:
             raise RuntimeError("pipeline parity gate failed inside the timed loop (two batches in flight)")
         t_all = t_fl
@@ -191,7 +201,8 @@ def run_gpu(device: int, frames_batch=64, gallery_rows=1_000_000, reps=10, hbm_g
         out["e2e"] = {**line(t_fl, "fr_pipeline_submit + fr_pipeline_collect: host frames (pinned) -> identities on the host, two batches in flight"),
                       "batch_frames": frames_batch, "faces_per_batch": faces, "gallery_rows": gallery_rows, "parallelism": "replicas (one pipeline per GPU, no collective)",
                       "h2d_bytes_per_batch": int(frames.numel()), "d2h_bytes_per_batch": faces * 12 + frames_batch * (4 * 20 + 4),
-                      "gpu_launches_per_batch": int(launches), "parity_gate": gate, "timing": "wall clock around `reps` batches, barrier + synchronize on both sides, max over ranks; identities of every batch checked",
+                      "gpu_launches_per_batch": int(launches), "parity_gate": gate, "timing": "median of 5 windows of `reps` batches, wall clock, barrier + synchronize on both sides, max over ranks; identities of every batch checked",
+                      "ms_per_batch_windows": windows_ms,
                       "config": "detect(RetinaFace mobile0.25 640x640) -> device-side face compaction -> crop+bicubic 112x112 -> embed(ArcFace IR-SE-50) -> top-1 search (BASELINE.json configs[3])",
                       "synchronous_call": line(t_sync, "fr_pipeline_run: one batch at a time, the call returns the identities")}
         if stage_breakdown:
@@ -202,12 +213,15 @@ def run_gpu(device: int, frames_batch=64, gallery_rows=1_000_000, reps=10, hbm_g
                              "roofline": {"bound": "hbm", "achieved": DET_MB_PER_FRAME * 16e-3 / td_, "peak": hbm_gbs, "unit": "GB/s",
                                           "frac": DET_MB_PER_FRAME * 16e-3 / td_ / hbm_gbs, "note": "whole detector step incl. H2D, not one kernel"}}
             # the detector's kernels alone, frames resident in HBM (what the pipeline runs: its H2D rides the copy stream)
+            # (an explicit stream: the library reads a NULL stream as "the handle's own stream", which torch's events would not see)
+            tstream = torch.cuda.Stream(device=dev)
+            st = tstream.cuda_stream
             for b in sorted({16, frames_batch}):
                 fd = frames[:b].to(dev)
                 bx = torch.empty((b, 4, 5), dtype=torch.int32, device=dev)
                 ct = torch.empty((b,), dtype=torch.int32, device=dev)
-                st = torch.cuda.current_stream().cuda_stream
-                tdd = _event_time(torch, lambda: det.run_dev(fd, bx, ct, stream=st), reps)
+                torch.cuda.synchronize()
+                tdd = _event_time(torch, lambda: det.run_dev(fd, bx, ct, stream=st), reps, stream=tstream)
                 out["detect" if b == frames_batch else f"detect_b{b}_dev"] = {"batch": b, "ms": tdd * 1e3, "frames_per_s": b / tdd, "us_per_frame": tdd * 1e6 / b,
                                             "inputs": "device-resident u8 HWC frames",
                                             "roofline": {"bound": "hbm", "achieved": DET_MB_PER_FRAME * b * 1e-3 / tdd, "peak": hbm_gbs, "unit": "GB/s",
@@ -218,8 +232,8 @@ def run_gpu(device: int, frames_batch=64, gallery_rows=1_000_000, reps=10, hbm_g
                 crops = np.ascontiguousarray(np.concatenate([mg.arcface_inputs()] * ((b + 7) // 8))[:b])
                 x = torch.from_numpy((crops[..., ::-1].transpose(0, 3, 1, 2).astype(np.float32) - 127.5) * 0.0078125).to(dev).contiguous()
                 y = torch.empty((b, 512), dtype=torch.float32, device=dev)
-                st = torch.cuda.current_stream().cuda_stream
-                te = _event_time(torch, lambda: emb.run_dev(x, y, stream=st), reps)
+                torch.cuda.synchronize()
+                te = _event_time(torch, lambda: emb.run_dev(x, y, stream=st), reps, stream=tstream)
                 out[f"embed_b{b}"] = {"batch": b, "mode": "ir_se", "ms": te * 1e3, "faces_per_s": b / te, "inputs": "device-resident f32 CHW",
                                       "roofline": {"bound": "tensor", "achieved": EMB_GFLOP_PER_FACE * b * 1e-3 / te, "peak": tf_sust, "unit": "TFLOP/s",
                                                    "frac": EMB_GFLOP_PER_FACE * b * 1e-3 / te / tf_sust, "note": "whole embedder forward (all kernels), device-resident"}}
