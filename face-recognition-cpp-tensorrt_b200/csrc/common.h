@@ -153,6 +153,10 @@ void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
 // Select `device`, check it is sm_100, return its SM count.
 int use_device(int device);
 
+// cv::resize(src, dst, Size(out_w, out_h)) for u8 BGR frames on the device (INTER_LINEAR, OpenCV's fixed-point arithmetic): the
+// detector's letterbox kernel with the resized area covering the whole canvas (defined in detector.cu, used by jpeg.cu)
+void launch_stretch_resize_u8(const uint8_t* src, int h, int w, int stride_bytes, int out_h, int out_w, uint8_t* dst, cudaStream_t st);
+
 // RAII device switch for entry points
 struct DeviceGuard {
     int prev = -1;

@@ -582,6 +582,15 @@ void detector_dims(const FrDetector* d, int* frame_h, int* frame_w, int* max_bat
 }
 }  // namespace frb
 
+namespace frb {
+void launch_stretch_resize_u8(const uint8_t* src, int h, int w, int stride_bytes, int out_h, int out_w, uint8_t* dst, cudaStream_t st) {
+    const long long px = static_cast<long long>(out_w) * out_h;
+    det_letterbox_kernel<<<static_cast<unsigned>((px + 255) / 256), 256, 0, st>>>(src, h, w, stride_bytes, 1, out_h, out_w, out_w, out_h, 0, 0, dst);
+    count_launch();
+    FRB_CUDA(cudaGetLastError());
+}
+}  // namespace frb
+
 extern "C" {
 
 int fr_detector_create(const char* weights_path, int net_h, int net_w, int frame_h, int frame_w, int max_batch, int max_faces, float nms_thr,

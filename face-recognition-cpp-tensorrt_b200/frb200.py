@@ -747,3 +747,43 @@ class Exchange:
             self.close()
         except Exception:
             pass
+
+class JpegDecoder:
+    """fr_jpeg_*: cv::imdecode (+ cv::resize) of the request handlers (/root/reference src/app.cpp:247-256,294-301) on the GPU (nvJPEG)"""
+
+    def __init__(self, device: int = 0):
+        L = lib()
+        L.fr_jpeg_decoder_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.fr_jpeg_decoder_destroy.restype = None
+        L.fr_jpeg_decoder_destroy.argtypes = [C.c_void_p]
+        L.fr_jpeg_info.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.fr_jpeg_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        h = C.c_void_p()
+        check(L.fr_jpeg_decoder_create(device, C.byref(h)))
+        self._h = h
+
+    def close(self) -> None:
+        if self._h:
+            lib().fr_jpeg_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self, jpeg: bytes):
+        """-> (width, height) of the encoded image"""
+        buf = np.frombuffer(jpeg, np.uint8)
+        w, h = C.c_int(), C.c_int()
+        check(lib().fr_jpeg_info(self._h, _ptr(buf) if buf.size else None, buf.size, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def decode(self, jpeg: bytes, size=None) -> np.ndarray:
+        """-> u8 BGR frame [H, W, 3]; size = (W, H) stretches it like cv::resize(frame, Size(W, H)), None keeps the decoded size"""
+        buf = np.frombuffer(jpeg, np.uint8)
+        w, h = size if size is not None else self.info(jpeg)
+        out = np.empty((h, w, 3), np.uint8)
+        check(lib().fr_jpeg_decode(self._h, _ptr(buf) if buf.size else None, buf.size, w, h, _ptr(out), w * 3))
+        return out

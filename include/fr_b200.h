@@ -350,6 +350,19 @@ int fr_service_infer(FrService *s, const uint8_t *frame, int stride, FrBbox *box
 /* monitoring: batches formed and frames served so far */
 int fr_service_stats(const FrService *s, int64_t *batches, int64_t *frames);
 
+/* JPEG decode for the serving loop: replaces cv::imdecode + cv::resize of the request handlers (src/app.cpp:247-256
+ * "/recognize", :294-301 "/inference"). Huffman decoding on the host, IDCT and colour conversion on the GPU (nvJPEG, loaded on first
+ * use), output u8 BGR interleaved (what cv::imdecode returns for a colour JPEG) stretched to out_w x out_h with OpenCV's INTER_LINEAR
+ * fixed-point arithmetic when the decoded size differs (out_w <= 0 or out_h <= 0: as decoded, see fr_jpeg_info). `bgr` is a host
+ * buffer of out_h rows of `stride` bytes - ready for fr_service_infer / fr_pipeline_run / fr_detector_run. A stream that is not a
+ * decodable JPEG fails with FR_EINVAL and the reference's message "Empty image" (src/app.cpp:251,298); a missing nvJPEG library with
+ * FR_ENOENT. One handle = one CUDA stream, not re-entrant (one decoder per serving thread). */
+typedef struct FrJpegDecoder FrJpegDecoder;
+int fr_jpeg_decoder_create(int device, FrJpegDecoder **out);
+void fr_jpeg_decoder_destroy(FrJpegDecoder *d);
+int fr_jpeg_info(FrJpegDecoder *d, const uint8_t *jpeg, size_t nbytes, int *width, int *height);
+int fr_jpeg_decode(FrJpegDecoder *d, const uint8_t *jpeg, size_t nbytes, int out_w, int out_h, uint8_t *bgr, int stride);
+
 #ifdef __cplusplus
 }
 #endif

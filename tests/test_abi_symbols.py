@@ -44,3 +44,7 @@ def test_no_cpu_fallback_without_device(built_lib):
         frb200.Gallery.synthetic(16, seed=1)
     assert e.value.code == frb200.FR_ENODEVICE
     assert "no CPU fallback" in e.value.msg
+    with pytest.raises(frb200.FrError) as e:    # the JPEG decoder too: no libjpeg path behind it
+        frb200.JpegDecoder()
+    assert e.value.code == frb200.FR_ENODEVICE
+
