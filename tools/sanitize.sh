@@ -11,3 +11,6 @@ for tool in memcheck racecheck; do
   echo "$tool rc=$?" | tee -a gpurun_out/r02_sanitizer_$tool.log
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/r02_sanitizer_$tool.log | tail -4
 done
+# the e4m3 top-1 path (append scan, per-list re-rank with its filters and compactions) on a gallery small enough for racecheck
+timeout 300 compute-sanitizer --tool racecheck --print-limit 10 python tools/racecheck_f8_small.py > gpurun_out/r02_racecheck_f8_small.log 2>&1
+grep -E "RACECHECK SUMMARY|flagged|top1" gpurun_out/r02_racecheck_f8_small.log
