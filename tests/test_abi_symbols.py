@@ -48,3 +48,18 @@ def test_no_cpu_fallback_without_device(built_lib):
         frb200.JpegDecoder()
     assert e.value.code == frb200.FR_ENODEVICE
 
+
+def test_header_is_plain_c(tmp_path):
+    """include/fr_b200.h is the FFI boundary: it must compile as strict C99 (no C++-isms, every type it uses declared)"""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "fr_b200.h"\nint main(void) { FrJpegDecoder *d = 0; FrGallery *g = 0; (void)d; (void)g; return fr_abi_version() < 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", f"-I{ROOT / 'include'}", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
