@@ -155,3 +155,22 @@ def test_saturating_query_is_always_recomputed():
     q[2] *= 40.0                                           # components beyond 1.75 saturate e4m3
     r = fd.certified_top1(G, q)
     assert r["flagged"].tolist() == [False, False, True, False]
+
+
+def test_exact_leader_filter_cuts_the_rerank_set_and_keeps_the_best():
+    """append_rerank_kernel's second filter: rows with coarse < L0 - E are dropped, L0 = best exact score among a few coarse
+    leaders. Sound under the certificate's own event (the true best A has exact_A >= L0, so dropping it needs exact_A - coarse_A > E);
+    here: it never drops the true best, never changes the answer, and does shrink the set the fp16 / fp32 re-score has to gather."""
+    rng = np.random.default_rng(12)
+    G = unit(rng.standard_normal((120_000, 512)))
+    q = unit(rng.standard_normal((96, 512)))             # unmatched queries: hundreds of rows inside the margin
+    q[:8] = unit(0.8 * G[rng.integers(0, len(G), 8)] + 0.6 * q[:8])   # and a few with a match
+    r = fd.certified_top1(G, q)
+    assert r["best_in_cand"].all() and (r["idx"] == r["exact_idx"]).all() and not r["flagged"].any()
+    assert (r["n_cand"] <= r["n_margin"]).all()
+    unmatched = slice(8, None)
+    assert float(r["n_cand"][unmatched].mean()) < 0.6 * float(r["n_margin"][unmatched].mean())
+    # the event everything rests on, in numbers: the true best row's coarse score is within E of its exact score (by a wide factor)
+    rows = np.arange(len(q))
+    err_best = r["exact"][rows, r["exact_idx"]] - r["coarse"][rows, r["exact_idx"]]
+    assert (err_best <= 0.5 * r["E"]).all()
